@@ -1,0 +1,350 @@
+"""gsv_b200 -- host-side mirror of the reference's garbling API on top of libgsv_cuda.so.
+
+The reference's entry points for this path are `CircuitBuilder::streaming_garbling` /
+`streaming_evaluation` (src/circuit/mod.rs:185-250) driven per instance by the cut-and-choose
+loops (src/cut_and_choose/garbler.rs:191-242).  Here the same calls take a *batch* of seeds and
+run on one B200 through the C ABI in include/gsv_cuda.h.  There is no CPU fallback: if the CUDA
+library or a device is missing the calls raise.
+
+Labels are numpy uint8 arrays whose last axis is the 16 bytes of `S::to_bytes()`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgsv_cuda.so")
+
+HASH_AES = 0
+HASH_BLAKE3 = 1
+CT_NONE = 0
+CT_COMMIT = 1
+CT_KEEP = 2
+WIRE_UNREACHABLE = 0xFFFFFFFF
+
+GATE_NAMES = ["And", "Nand", "Nimp", "Imp", "Ncimp", "Cimp", "Nor", "Or", "Xor", "Xnor", "Not"]
+
+
+class GsvError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"gsv error {code}: {msg}")
+        self.code = code
+
+
+class _PlanOptions(C.Structure):
+    _fields_ = [("max_task_gates", C.c_uint64), ("max_task_slots", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class _ProgramInfo(C.Structure):
+    _fields_ = [
+        ("n_gates", C.c_uint64),
+        ("n_live_gates", C.c_uint64),
+        ("n_ciphertexts", C.c_uint64),
+        ("type_count", C.c_uint64 * 11),
+        ("n_inputs", C.c_uint32),
+        ("n_outputs", C.c_uint32),
+        ("n_tasks", C.c_uint32),
+        ("n_calls", C.c_uint32),
+        ("n_global_slots", C.c_uint32),
+        ("max_task_slots", C.c_uint32),
+        ("max_task_levels", C.c_uint32),
+        ("max_call_deps", C.c_uint32),
+        ("sum_call_levels", C.c_uint64),
+    ]
+
+
+class _SessionOptions(C.Structure):
+    _fields_ = [
+        ("device", C.c_int),
+        ("n_instances", C.c_uint32),
+        ("group", C.c_uint32),
+        ("worker_threads", C.c_uint32),
+        ("ct_mode", C.c_uint32),
+        ("reserved", C.c_uint32 * 3),
+    ]
+
+
+class _GarbleResult(C.Structure):
+    _fields_ = [
+        ("delta", C.c_void_p),
+        ("false_label0", C.c_void_p),
+        ("true_label0", C.c_void_p),
+        ("input_label0", C.c_void_p),
+        ("output_label0", C.c_void_p),
+        ("ct_commit", C.c_void_p),
+        ("n_ciphertexts", C.c_uint64),
+        ("ms_seed", C.c_float),
+        ("ms_garble", C.c_float),
+        ("ms_commit", C.c_float),
+        ("ms_total", C.c_float),
+        ("n_launches", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
+class _EvaluateIO(C.Structure):
+    _fields_ = [
+        ("true_label", C.c_void_p),
+        ("false_label", C.c_void_p),
+        ("input_active", C.c_void_p),
+        ("input_bits", C.c_void_p),
+        ("ct_streams", C.POINTER(C.c_void_p)),
+        ("ct_stream_len", C.c_uint64),
+        ("output_active", C.c_void_p),
+        ("output_bits", C.c_void_p),
+        ("ct_commit", C.c_void_p),
+        ("ms_evaluate", C.c_float),
+        ("ms_commit", C.c_float),
+        ("ms_total", C.c_float),
+        ("n_launches", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Loads libgsv_cuda.so (built by `__graft_entry__.build()`); raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(the CUDA engine has no CPU fallback)"
+        )
+    lib = C.CDLL(LIB_PATH)
+    lib.gsv_last_error.restype = C.c_char_p
+    lib.gsv_version.restype = C.c_char_p
+    lib.gsv_device_count.restype = C.c_int
+    lib.gsv_program_build.restype = C.c_void_p
+    lib.gsv_program_build.argtypes = [C.c_char_p, C.POINTER(_PlanOptions)]
+    lib.gsv_program_destroy.argtypes = [C.c_void_p]
+    lib.gsv_program_get_info.argtypes = [C.c_void_p, C.POINTER(_ProgramInfo)]
+    lib.gsv_program_flat_stream.restype = C.c_int64
+    lib.gsv_program_flat_stream.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.gsv_session_create.restype = C.c_void_p
+    lib.gsv_session_create.argtypes = [C.c_void_p, C.POINTER(_SessionOptions)]
+    lib.gsv_session_destroy.argtypes = [C.c_void_p]
+    lib.gsv_garble_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(_GarbleResult)]
+    lib.gsv_session_read_ciphertexts.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]
+    lib.gsv_evaluate_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(_EvaluateIO)]
+    lib.gsv_commit_labels.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.gsv_hash_blocks.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.gsv_bench_hash.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
+    _lib = lib
+    return lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise GsvError(rc, load_library().gsv_last_error().decode())
+
+
+def device_count() -> int:
+    return load_library().gsv_device_count()
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Program:
+    """A recorded + planned circuit (the once-per-topology flatten step)."""
+
+    def __init__(self, circuit: str, max_task_slots: int = 0, max_task_gates: int = 0):
+        lib = load_library()
+        opt = _PlanOptions(max_task_gates, max_task_slots, 0)
+        self._h = lib.gsv_program_build(circuit.encode(), C.byref(opt))
+        if not self._h:
+            raise GsvError(-1, lib.gsv_last_error().decode())
+        self.circuit = circuit
+        info = _ProgramInfo()
+        _check(lib.gsv_program_get_info(self._h, C.byref(info)))
+        self.n_gates = info.n_gates
+        self.n_live_gates = info.n_live_gates
+        self.n_ciphertexts = info.n_ciphertexts
+        self.type_count = list(info.type_count)
+        self.n_inputs = info.n_inputs
+        self.n_outputs = info.n_outputs
+        self.n_tasks = info.n_tasks
+        self.n_calls = info.n_calls
+        self.n_global_slots = info.n_global_slots
+        self.max_task_slots = info.max_task_slots
+        self.max_task_levels = info.max_task_levels
+        self.max_call_deps = info.max_call_deps
+        self.sum_call_levels = info.sum_call_levels
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.gsv_program_destroy(self._h)
+            self._h = None
+
+    def flat_stream(self):
+        """Emission-order gate stream (type, a, b, c, outputs, n_wires) for checkers."""
+        lib = load_library()
+        n = self.n_gates
+        t = np.zeros(n, np.uint8)
+        a = np.zeros(n, np.uint32)
+        b = np.zeros(n, np.uint32)
+        c = np.zeros(n, np.uint32)
+        outs = np.zeros(max(self.n_outputs, 1), np.uint32)
+        nw = C.c_uint32(0)
+        got = lib.gsv_program_flat_stream(self._h, _ptr(t), _ptr(a), _ptr(b), _ptr(c), n, _ptr(outs), C.byref(nw))
+        if got < 0:
+            _check(int(got))
+        return t, a, b, c, outs[: self.n_outputs], nw.value
+
+
+@dataclass
+class GarbleResult:
+    """Per-instance results of streaming_garbling (StreamingResult, src/circuit/mod.rs:82-107)."""
+
+    delta: np.ndarray          # [B,16]
+    false_label0: np.ndarray   # [B,16]
+    true_label0: np.ndarray    # [B,16]
+    input_label0: Optional[np.ndarray]   # [B,n_inputs,16]
+    output_label0: Optional[np.ndarray]  # [B,n_outputs,16]
+    ct_commit: np.ndarray      # [B,16]
+    n_ciphertexts: int
+    ms_seed: float
+    ms_garble: float
+    ms_commit: float
+    ms_total: float
+    n_launches: int
+
+    @property
+    def true_label1(self) -> np.ndarray:
+        return self.true_label0 ^ self.delta
+
+
+@dataclass
+class EvalResult:
+    output_active: np.ndarray  # [B,n_outputs,16]
+    output_bits: np.ndarray    # [B,n_outputs]
+    ct_commit: np.ndarray      # [B,16]
+    ms_evaluate: float
+    ms_commit: float
+    ms_total: float
+    n_launches: int
+
+
+class Session:
+    """Device state for a batch of instances of one program on one GPU."""
+
+    def __init__(self, program: Program, n_instances: int, device: int = 0, group: int = 0,
+                 worker_threads: int = 0, ct_mode: int = CT_KEEP):
+        lib = load_library()
+        self.program = program
+        self.n_instances = n_instances
+        self.device = device
+        self.ct_mode = ct_mode
+        opt = _SessionOptions(device, n_instances, group, worker_threads, ct_mode)
+        self._h = lib.gsv_session_create(program._h, C.byref(opt))
+        if not self._h:
+            msg = lib.gsv_last_error().decode()
+            raise GsvError(-2 if "no CUDA device" in msg else -3, msg)
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.gsv_session_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def garble(self, seeds: Sequence[int], hasher: int = HASH_AES, want_inputs: bool = True,
+               want_outputs: bool = True) -> GarbleResult:
+        lib = load_library()
+        B, p = self.n_instances, self.program
+        seeds_a = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
+        if seeds_a.shape != (B,):
+            raise ValueError("need one seed per instance")
+        delta = np.zeros((B, 16), np.uint8)
+        fl = np.zeros((B, 16), np.uint8)
+        tl = np.zeros((B, 16), np.uint8)
+        il = np.zeros((B, p.n_inputs, 16), np.uint8) if want_inputs else None
+        ol = np.zeros((B, p.n_outputs, 16), np.uint8) if want_outputs else None
+        cc = np.zeros((B, 16), np.uint8)
+        r = _GarbleResult()
+        r.delta, r.false_label0, r.true_label0 = _ptr(delta), _ptr(fl), _ptr(tl)
+        r.input_label0, r.output_label0, r.ct_commit = _ptr(il), _ptr(ol), _ptr(cc)
+        _check(lib.gsv_garble_batch(self._h, hasher, _ptr(seeds_a), C.byref(r)))
+        return GarbleResult(delta, fl, tl, il, ol, cc, int(r.n_ciphertexts), r.ms_seed, r.ms_garble,
+                            r.ms_commit, r.ms_total, r.n_launches)
+
+    def read_ciphertexts(self, instance: int, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        lib = load_library()
+        if count is None:
+            count = self.program.n_ciphertexts - first
+        out = np.zeros((count, 16), np.uint8)
+        _check(lib.gsv_session_read_ciphertexts(self._h, instance, first, count, _ptr(out)))
+        return out
+
+    def evaluate(self, hasher: int, true_label: np.ndarray, false_label: np.ndarray,
+                 input_active: np.ndarray, input_bits: np.ndarray,
+                 ct_streams: Optional[Sequence[np.ndarray]] = None) -> EvalResult:
+        lib = load_library()
+        B, p = self.n_instances, self.program
+        tl = np.ascontiguousarray(true_label, np.uint8).reshape(B, 16)
+        fl = np.ascontiguousarray(false_label, np.uint8).reshape(B, 16)
+        ia = np.ascontiguousarray(input_active, np.uint8).reshape(B, p.n_inputs, 16)
+        ib = np.ascontiguousarray(input_bits, np.uint8).reshape(B, p.n_inputs)
+        oa = np.zeros((B, p.n_outputs, 16), np.uint8)
+        ob = np.zeros((B, p.n_outputs), np.uint8)
+        cc = np.zeros((B, 16), np.uint8)
+        io = _EvaluateIO()
+        io.true_label, io.false_label, io.input_active, io.input_bits = _ptr(tl), _ptr(fl), _ptr(ia), _ptr(ib)
+        keep = None
+        if ct_streams is not None:
+            keep = [np.ascontiguousarray(s, np.uint8) for s in ct_streams]
+            lens = {k.size // 16 for k in keep}
+            if len(keep) != B or len(lens) != 1:
+                raise ValueError("need B ciphertext streams of equal length")
+            arr = (C.c_void_p * B)(*[k.ctypes.data for k in keep])
+            io.ct_streams = C.cast(arr, C.POINTER(C.c_void_p))
+            io.ct_stream_len = lens.pop()
+        io.output_active, io.output_bits, io.ct_commit = _ptr(oa), _ptr(ob), _ptr(cc)
+        _check(lib.gsv_evaluate_batch(self._h, hasher, C.byref(io)))
+        return EvalResult(oa, ob, cc, io.ms_evaluate, io.ms_commit, io.ms_total, io.n_launches)
+
+
+def commit_labels(labels: np.ndarray, device: int = 0) -> np.ndarray:
+    """commit_label for many labels (src/cut_and_choose/mod.rs:41-48)."""
+    lib = load_library()
+    a = np.ascontiguousarray(labels, np.uint8).reshape(-1, 16)
+    out = np.zeros_like(a)
+    _check(lib.gsv_commit_labels(device, _ptr(a), a.shape[0], _ptr(out)))
+    return out.reshape(np.asarray(labels).shape)
+
+
+def hash_blocks(hasher: int, x: np.ndarray, gid: np.ndarray, device: int = 0) -> np.ndarray:
+    lib = load_library()
+    a = np.ascontiguousarray(x, np.uint8).reshape(-1, 16)
+    g = np.ascontiguousarray(gid, np.uint64).reshape(-1)
+    out = np.zeros_like(a)
+    _check(lib.gsv_hash_blocks(device, hasher, _ptr(a), _ptr(g), a.shape[0], _ptr(out)))
+    return out
+
+
+def bench_hash(hasher: int, n_blocks: int = 1 << 30, iters: int = 3, device: int = 0) -> float:
+    lib = load_library()
+    r = C.c_double(0)
+    _check(lib.gsv_bench_hash(device, hasher, n_blocks, iters, C.byref(r)))
+    return r.value
+
+
+def streaming_garbling(program: Program, seeds: Sequence[int], hasher: int = HASH_AES,
+                       ct_mode: int = CT_COMMIT, device: int = 0, **session_kw) -> GarbleResult:
+    """CircuitBuilder::streaming_garbling for a batch of seeds (one-shot session)."""
+    s = Session(program, len(seeds), device=device, ct_mode=ct_mode, **session_kw)
+    try:
+        return s.garble(seeds, hasher)
+    finally:
+        s.close()

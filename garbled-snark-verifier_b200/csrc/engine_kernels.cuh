@@ -1,0 +1,362 @@
+// engine_kernels.cuh -- the persistent task-dataflow kernels of the garbling engine (sm_100a).
+//
+// Execution model:
+//   grid  = one CTA per SM (persistent), CTA = NW workers of NT threads;
+//   work  = items (call, instance-group) claimed in emission order by an atomic ticket;
+//           a worker spins on the done-flags of the call's producer calls (RAW) before it
+//           starts, so independent calls of one instance and all instances run concurrently;
+//   task  = gather the call's input labels from the instance's global slot array into shared
+//           memory, run the task level by level (named barrier per level, labels never leave
+//           shared memory), write ciphertexts straight to their stream position, scatter the
+//           produced labels back, publish the done-flag.
+// Thread mapping inside a level: idx -> (gate = idx / G, instance = idx % G); G instances of a
+// gate sit in adjacent lanes so label accesses are contiguous 16-byte vectors and the gate
+// record load is a broadcast.
+#pragma once
+#include "device_hash.cuh"
+
+namespace gsvdev {
+
+struct DevGateD {  // mirrors gsv::DevGate (program.h)
+  uint16_t a, b, c;
+  uint8_t type;
+  uint8_t flags;
+  uint32_t gid_off;
+  uint32_t ct_off;
+};
+struct DevTaskD {
+  uint32_t gate_off, level_off, n_levels, n_in, n_out, n_slots, in_slot_off, out_slot_off;
+};
+struct DevCallD {
+  uint32_t task, in_off, out_off, dep_off, n_deps, pad;
+  unsigned long long gid_base, ct_base;
+};
+
+struct EngineParams {
+  const uint4* gates;  // DevGateD as uint4
+  const uint32_t* level_off;
+  const uint16_t* in_slot;
+  const uint16_t* out_slot;
+  const DevTaskD* tasks;
+  const DevCallD* calls;
+  const uint32_t* call_slots;
+  const uint32_t* deps;
+  uint4* labels;        // [group][global slot][G]
+  uint8_t* vals;        // evaluate: plaintext bit per label, same indexing
+  const uint4* delta;   // [B]
+  uint4* ct;            // [ct index][B]  (garble: written, evaluate: read)
+  uint32_t* flags;      // [call][group] == epoch when done
+  uint32_t* next_item;
+  uint32_t n_calls, n_groups, n_global_slots, B;
+  uint32_t slots_per_worker;  // shared-memory label slots per instance reserved per worker
+  uint32_t worker_threads;
+  uint32_t epoch;
+  uint32_t write_ct;          // garble: store ciphertexts
+  unsigned long long ct_capacity;  // evaluate: ciphertexts available per instance
+  uint32_t* error_flag;       // evaluate: set to 1 on ciphertext exhaustion
+};
+
+__device__ __forceinline__ void named_bar(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// MODE 0 = garble (labels are label0, ciphertexts produced), MODE 1 = evaluate.
+template <int G, int HASH, int MODE>
+__global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
+  extern __shared__ uint4 smem[];
+  uint32_t* te = reinterpret_cast<uint32_t*>(smem);  // 1024 words
+  const uint32_t NT = p.worker_threads;
+  const uint32_t worker = threadIdx.x / NT;
+  const uint32_t wt = threadIdx.x - worker * NT;
+  const uint32_t n_workers = blockDim.x / NT;
+  const uint32_t bar_id = worker + 1;
+  // per-worker regions
+  const uint32_t lab_words = p.slots_per_worker * G;  // uint4 entries
+  uint4* lab = smem + 256 + worker * lab_words;
+  uint8_t* sval = reinterpret_cast<uint8_t*>(smem + 256 + n_workers * lab_words) + worker * lab_words;
+  volatile uint32_t* ctrl =
+      reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint8_t*>(smem + 256 + n_workers * lab_words) +
+                                           (MODE == 1 ? n_workers * lab_words : 0)) + worker;
+
+  load_tables(te, threadIdx.x, blockDim.x);
+  __syncthreads();
+
+  const uint32_t inst = wt % G;  // NT % G == 0, so a thread always serves the same instance lane
+  const uint32_t n_items = p.n_calls * p.n_groups;
+
+  for (;;) {
+    if (wt == 0) *ctrl = atomicAdd(p.next_item, 1u);
+    named_bar(bar_id, NT);
+    const uint32_t item = *ctrl;
+    if (item >= n_items) break;
+    const uint32_t call_i = item / p.n_groups;
+    const uint32_t grp = item - call_i * p.n_groups;
+    const DevCallD call = p.calls[call_i];
+    const DevTaskD task = p.tasks[call.task];
+
+    // ---- wait for producer calls of this instance group
+    for (uint32_t d = wt; d < call.n_deps; d += NT) {
+      const uint32_t* f = p.flags + (size_t)p.deps[call.dep_off + d] * p.n_groups + grp;
+      while (ld_acquire(f) != p.epoch) __nanosleep(64);
+    }
+    named_bar(bar_id, NT);
+
+    // ---- gather inputs (and the two constant wires) into shared memory
+    const size_t gbase = (size_t)grp * p.n_global_slots;
+    uint4 delta = make_uint4(0, 0, 0, 0);
+    if (MODE == 0) delta = p.delta[grp * G + inst];
+    if (wt < 2 * G) {
+      const uint32_t s = wt / G;
+      lab[s * G + inst] = __ldcg(p.labels + (gbase + s) * G + inst);
+      if (MODE == 1) sval[s * G + inst] = (uint8_t)s;
+    }
+    for (uint32_t k = wt; k < task.n_in * G; k += NT) {
+      const uint32_t pos = k / G;
+      const uint32_t s = p.in_slot[task.in_slot_off + pos];
+      if (s != 0xFFFFu) {
+        const size_t gi = (gbase + p.call_slots[call.in_off + pos]) * G + inst;
+        lab[s * G + inst] = __ldcg(p.labels + gi);
+        if (MODE == 1) sval[s * G + inst] = __ldcg(p.vals + gi);
+      }
+    }
+    named_bar(bar_id, NT);
+
+    // ---- level loop
+    const uint4* gates = p.gates + task.gate_off;
+    const uint32_t* loff = p.level_off + task.level_off;
+    uint32_t lo = __ldg(loff), hi = (task.n_levels ? __ldg(loff + 1) : lo);
+    uint4 nxt = make_uint4(0, 0, 0, 0);
+    if (wt < (hi - lo) * G) nxt = __ldg(gates + lo + wt / G);
+    for (uint32_t lvl = 0; lvl < task.n_levels; ++lvl) {
+      const uint32_t cur_lo = lo, n = (hi - lo) * G;
+      uint4 graw = nxt;
+      // prefetch the first gate of the next level while this level computes
+      lo = hi;
+      if (lvl + 1 < task.n_levels) {
+        hi = __ldg(loff + lvl + 2);
+        if (wt < (hi - lo) * G) nxt = __ldg(gates + lo + wt / G);
+      }
+      for (uint32_t idx = wt; idx < n; idx += NT) {
+        if (idx != wt) graw = __ldg(gates + cur_lo + idx / G);
+        const uint32_t sa = graw.x & 0xFFFFu, sb = graw.x >> 16, sc = graw.y & 0xFFFFu;
+        const uint32_t type = (graw.y >> 16) & 0xFFu;
+        const uint4 la = lab[sa * G + inst];
+        const uint4 lb = lab[sb * G + inst];
+        uint4 lc;
+        if (MODE == 0) {
+          if (type >= 8) {
+            // free gates: Xor, Xnor (^delta), Not (a ^ delta)
+            lc = (type == 10) ? xor4(la, delta) : xor4(la, lb);
+            if (type == 9) lc = xor4(lc, delta);
+          } else {
+            const unsigned long long gid = call.gid_base + graw.z;
+            uint4 ct;
+            lc = garble_nonfree<HASH>(te, type, la, lb, delta, gid, ct);
+            if (p.write_ct) __stcs(p.ct + (size_t)(call.ct_base + graw.w) * p.B + grp * G + inst, ct);
+          }
+        } else {
+          const uint32_t va = sval[sa * G + inst], vb = sval[sb * G + inst];
+          if (type >= 8) {
+            lc = (type == 10) ? la : xor4(la, lb);
+          } else {
+            const unsigned long long gid = call.gid_base + graw.z;
+            const unsigned long long cti = call.ct_base + graw.w;
+            uint4 ct = make_uint4(0, 0, 0, 0);
+            if (cti < p.ct_capacity) ct = __ldcs(p.ct + (size_t)cti * p.B + grp * G + inst);
+            else *p.error_flag = 1u;
+            lc = degarble_nonfree<HASH>(te, type, ct, la, va, lb, gid);
+          }
+          sval[sc * G + inst] = (uint8_t)gate_value(type, va, vb);
+        }
+        lab[sc * G + inst] = lc;
+      }
+      named_bar(bar_id, NT);
+    }
+
+    // ---- scatter produced labels to the instance's global slots
+    for (uint32_t k = wt; k < task.n_out * G; k += NT) {
+      const uint32_t pos = k / G;
+      const uint32_t s = p.out_slot[task.out_slot_off + pos];
+      const size_t gi = (gbase + p.call_slots[call.out_off + pos]) * G + inst;
+      p.labels[gi] = lab[s * G + inst];
+      if (MODE == 1) p.vals[gi] = sval[s * G + inst];
+    }
+    __threadfence();
+    named_bar(bar_id, NT);
+    if (wt == 0) st_release(p.flags + (size_t)call_i * p.n_groups + grp, p.epoch);
+  }
+}
+
+// ---- seed expansion: ChaCha20Rng::seed_from_u64(seed) -> delta, constants, input label0s
+// (garble_mode.rs:80-97,116-118; rand_core 0.6.4 seed_from_u64; rand_chacha 0.3.1).
+// One thread per (instance, 64-byte ChaCha block) = 4 u128 draws.
+__device__ __forceinline__ uint32_t rotl(uint32_t x, int n) { return __funnelshift_l(x, x, n); }
+#define GSV_QR(a, b, c, d) \
+  a += b; d ^= a; d = rotl(d, 16); \
+  c += d; b ^= c; b = rotl(b, 12); \
+  a += b; d ^= a; d = rotl(d, 8);  \
+  c += d; b ^= c; b = rotl(b, 7);
+
+template <int DUMMY>
+__global__ void k_seed_expand(const unsigned long long* seeds, uint32_t B, uint32_t G, uint32_t n_inputs,
+                              uint32_t n_global_slots, uint4* labels, uint4* delta) {
+  const uint32_t n_draws = 3 + n_inputs;
+  const uint32_t n_blocks = (n_draws + 3) / 4;
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (size_t)B * n_blocks) return;
+  const uint32_t instance = (uint32_t)(gid / n_blocks);
+  const uint32_t blk = (uint32_t)(gid - (size_t)instance * n_blocks);
+  // PCG32 expansion of the u64 seed into the 256-bit key
+  uint32_t key[8];
+  unsigned long long st = seeds[instance];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    st = st * 6364136223846793005ull + 11634580027462260723ull;
+    uint32_t xs = (uint32_t)(((st >> 18) ^ st) >> 27);
+    uint32_t rot = (uint32_t)(st >> 59);
+    key[i] = __funnelshift_r(xs, xs, rot);
+  }
+  uint32_t s[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3],
+                    key[4], key[5], key[6], key[7], blk, 0u, 0u, 0u};
+  uint32_t x[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) x[i] = s[i];
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    GSV_QR(x[0], x[4], x[8], x[12])
+    GSV_QR(x[1], x[5], x[9], x[13])
+    GSV_QR(x[2], x[6], x[10], x[14])
+    GSV_QR(x[3], x[7], x[11], x[15])
+    GSV_QR(x[0], x[5], x[10], x[15])
+    GSV_QR(x[1], x[6], x[11], x[12])
+    GSV_QR(x[2], x[7], x[8], x[13])
+    GSV_QR(x[3], x[4], x[9], x[14])
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i++) x[i] += s[i];
+  const uint32_t grp = instance / G, lane = instance % G;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint32_t draw = blk * 4 + q;
+    if (draw >= n_draws) break;
+    // u128 = w0 | w1<<32 | w2<<64 | w3<<96 ; to_bytes() is big-endian
+    uint4 v = make_uint4(__byte_perm(x[4 * q + 3], 0, 0x0123), __byte_perm(x[4 * q + 2], 0, 0x0123),
+                         __byte_perm(x[4 * q + 1], 0, 0x0123), __byte_perm(x[4 * q + 0], 0, 0x0123));
+    if (draw == 0) delta[instance] = v;
+    else {
+      const uint32_t slot = draw - 1;  // 0 = false, 1 = true, 2.. = inputs
+      labels[((size_t)grp * n_global_slots + slot) * G + lane] = v;
+    }
+  }
+}
+
+// ---- serial ciphertext commitment: h <- AES_K(h ^ ct_k), one lane per instance
+// (src/ciphertext_hasher.rs:23-29).  Inherently sequential per instance; lanes = instances.
+template <int DUMMY>
+__global__ void __launch_bounds__(32) k_chain(const uint4* __restrict__ ct, unsigned long long n_ct, uint32_t B,
+                                              uint4* __restrict__ out) {
+  __shared__ uint32_t te[1024];
+  load_tables(te, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const uint32_t instance = blockIdx.x * blockDim.x + threadIdx.x;
+  if (instance >= B) return;
+  uint4 h = make_uint4(0, 0, 0, 0);
+  const uint4* p = ct + instance;
+  unsigned long long k = 0;
+  constexpr int U = 8;
+  for (; k + U <= n_ct; k += U) {
+    uint4 c[U];
+#pragma unroll
+    for (int j = 0; j < U; j++) c[j] = __ldcs(p + (size_t)(k + j) * B);
+#pragma unroll
+    for (int j = 0; j < U; j++) h = aes_fixed(te, xor4(h, c[j]));
+  }
+  for (; k < n_ct; k++) h = aes_fixed(te, xor4(h, __ldcs(p + (size_t)k * B)));
+  out[instance] = h;
+}
+
+// ---- small utility kernels
+// labels of selected global slots -> dense [instance][j] (and optionally the value bits)
+template <int DUMMY>
+__global__ void k_gather_slots(const uint4* labels, const uint8_t* vals, const uint32_t* slots, uint32_t n,
+                               uint32_t B, uint32_t G, uint32_t n_global_slots, uint4* out, uint8_t* out_vals) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * n) return;
+  const uint32_t instance = (uint32_t)(i / n), j = (uint32_t)(i % n);
+  const size_t gi = ((size_t)(instance / G) * n_global_slots + slots[j]) * G + instance % G;
+  out[i] = labels[gi];
+  if (out_vals) out_vals[i] = vals[gi];
+}
+// dense [instance][j] evaluator inputs -> global slots 2.. ; constants into slots 0/1
+template <int DUMMY>
+__global__ void k_scatter_inputs(const uint4* in_labels, const uint8_t* in_bits, const uint4* true_l,
+                                 const uint4* false_l, uint32_t n_inputs, uint32_t B, uint32_t G,
+                                 uint32_t n_global_slots, uint4* labels, uint8_t* vals) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t per = n_inputs + 2;
+  if (i >= (size_t)B * per) return;
+  const uint32_t instance = (uint32_t)(i / per), j = (uint32_t)(i % per);
+  const size_t gi = ((size_t)(instance / G) * n_global_slots + j) * G + instance % G;
+  if (j == 0) { labels[gi] = false_l[instance]; vals[gi] = 0; }
+  else if (j == 1) { labels[gi] = true_l[instance]; vals[gi] = 1; }
+  else {
+    labels[gi] = in_labels[(size_t)instance * n_inputs + (j - 2)];
+    vals[gi] = in_bits[(size_t)instance * n_inputs + (j - 2)] ? 1 : 0;
+  }
+}
+// interleaved ct[k][B] <-> one instance's contiguous stream
+template <int DUMMY>
+__global__ void k_ct_extract(const uint4* ct, uint32_t B, uint32_t instance, unsigned long long first,
+                             unsigned long long count, uint4* out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = ct[(first + i) * B + instance];
+}
+template <int DUMMY>
+__global__ void k_ct_insert(uint4* ct, uint32_t B, uint32_t instance, unsigned long long first,
+                            unsigned long long count, const uint4* in) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) ct[(first + i) * B + instance] = in[i];
+}
+// commit(label) = AES_K(label)
+template <int DUMMY>
+__global__ void k_commit_labels(const uint4* in, unsigned long long n, uint4* out) {
+  __shared__ uint32_t te[1024];
+  load_tables(te, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = aes_fixed(te, in[i]);
+}
+// H(x_i, gid_i) for the primitive parity tests
+template <int HASH>
+__global__ void k_hash_blocks(const uint4* x, const unsigned long long* gid, unsigned long long n, uint4* out) {
+  __shared__ uint32_t te[1024];
+  load_tables(te, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = hash1<HASH>(te, x[i], gid[i]);
+}
+// register-resident hash throughput probe (the integer-ALU roof): each thread chains
+// `per_thread` two-block hashes, like a stream of AND gates with no memory traffic.
+template <int HASH>
+__global__ void __launch_bounds__(256) k_bench_hash(unsigned long long per_thread, uint4* sink) {
+  __shared__ uint32_t te[1024];
+  load_tables(te, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint4 a = make_uint4((uint32_t)t, 1, 2, 3), b = make_uint4(4, 5, 6, (uint32_t)t);
+  for (unsigned long long i = 0; i < per_thread; i++) {
+    hash2<HASH>(te, a, b, (unsigned long long)t * per_thread + i);
+    a.x ^= b.w;
+  }
+  if (a.x == 0x12345678u && b.y == 0x9abcdef0u) sink[0] = xor4(a, b);  // defeat DCE
+}
+
+}  // namespace gsvdev

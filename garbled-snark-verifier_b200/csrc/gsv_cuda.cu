@@ -1,0 +1,738 @@
+// gsv_cuda.cu -- host runtime + C ABI of libgsv_cuda.so (see include/gsv_cuda.h).
+// No CPU fallback lives here: every compute entry point needs a CUDA device.
+#include "gsv_cuda.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "engine_kernels.cuh"
+#include "gadgets.h"
+#include "program.h"
+
+using namespace gsvdev;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+
+// ---- AES tables for the device (computed, not typed in)
+uint8_t gmul(uint8_t a, uint8_t b) {
+  uint8_t p = 0;
+  for (int i = 0; i < 8; i++) {
+    if (b & 1) p ^= a;
+    uint8_t hi = a & 0x80;
+    a = (uint8_t)(a << 1);
+    if (hi) a ^= 0x1b;
+    b >>= 1;
+  }
+  return p;
+}
+struct AesTables {
+  uint32_t te0[256];
+  uint32_t rk[44];
+  AesTables() {
+    uint8_t sbox[256];
+    for (int x = 0; x < 256; x++) {
+      uint8_t inv = 0;
+      if (x)
+        for (int y = 1; y < 256; y++)
+          if (gmul((uint8_t)x, (uint8_t)y) == 1) { inv = (uint8_t)y; break; }
+      uint8_t s = inv, r = inv;
+      for (int i = 0; i < 4; i++) { r = (uint8_t)((r << 1) | (r >> 7)); s ^= r; }
+      sbox[x] = s ^ 0x63;
+    }
+    for (int x = 0; x < 256; x++) {
+      uint8_t s = sbox[x], s2 = gmul(s, 2), s3 = gmul(s, 3);
+      te0[x] = (uint32_t)s2 | ((uint32_t)s << 8) | ((uint32_t)s << 16) | ((uint32_t)s3 << 24);
+    }
+    // FIPS-197 key schedule of K = 0x42 * 16 (src/hashers/aes_ni.rs:165,179-216)
+    static const uint8_t rcon[10] = {0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40, 0x80, 0x1b, 0x36};
+    uint8_t k[11][16];
+    memset(k[0], 0x42, 16);
+    for (int r = 1; r <= 10; r++) {
+      const uint8_t* p = k[r - 1];
+      uint8_t t[4] = {sbox[p[13]], sbox[p[14]], sbox[p[15]], sbox[p[12]]};
+      t[0] ^= rcon[r - 1];
+      for (int i = 0; i < 4; i++) k[r][i] = p[i] ^ t[i];
+      for (int i = 4; i < 16; i++) k[r][i] = p[i] ^ k[r][i - 4];
+    }
+    for (int r = 0; r < 11; r++)
+      for (int j = 0; j < 4; j++)
+        rk[4 * r + j] = (uint32_t)k[r][4 * j] | ((uint32_t)k[r][4 * j + 1] << 8) |
+                        ((uint32_t)k[r][4 * j + 2] << 16) | ((uint32_t)k[r][4 * j + 3] << 24);
+  }
+};
+
+bool g_tables_loaded[64] = {false};
+void ensure_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+    throw std::runtime_error("no CUDA device visible (libgsv_cuda has no CPU fallback)");
+  if (device < 0 || device >= n) throw std::runtime_error("bad device ordinal");
+  CUDA_TRY(cudaSetDevice(device));
+  if (!g_tables_loaded[device]) {
+    static const AesTables T;
+    CUDA_TRY(cudaMemcpyToSymbol(c_te0, T.te0, sizeof(T.te0)));
+    CUDA_TRY(cudaMemcpyToSymbol(c_rk, T.rk, sizeof(T.rk)));
+    g_tables_loaded[device] = true;
+  }
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) CUDA_TRY(cudaMalloc(&p, count * sizeof(T)));
+  }
+  void upload(const std::vector<T>& v) {
+    alloc(v.size());
+    if (!v.empty()) CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+}  // namespace
+
+// =============================================================================== program
+struct gsv_program {
+  std::unique_ptr<gsv::Builder> builder;
+  uint32_t root = 0;
+  gsv::Program prog;
+  uint32_t max_task_levels = 0;
+  uint64_t sum_call_levels = 0;
+};
+
+struct gsv_ctx {
+  gsv::Builder* b;
+};
+
+namespace {
+gsv_program* finish_program(std::unique_ptr<gsv::Builder> b, uint32_t root, const gsv_plan_options* opt) {
+  gsv::PlanOptions po;
+  if (opt) {
+    if (opt->max_task_gates) po.max_task_gates = opt->max_task_gates;
+    if (opt->max_task_slots) po.max_task_slots = opt->max_task_slots;
+  }
+  auto p = std::make_unique<gsv_program>();
+  p->prog = gsv::plan_program(*b, root, po);
+  p->builder = std::move(b);
+  p->root = root;
+  for (const auto& t : p->prog.tasks) p->max_task_levels = std::max(p->max_task_levels, t.n_levels);
+  for (const auto& c : p->prog.calls) p->sum_call_levels += p->prog.tasks[c.task].n_levels;
+  return p.release();
+}
+}  // namespace
+
+extern "C" {
+
+const char* gsv_last_error(void) { return g_err.c_str(); }
+const char* gsv_version(void) { return "gsv-cuda 0.1 (sm_100a)"; }
+int gsv_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+uint32_t gsv_ctx_issue_wire(gsv_ctx* ctx) { return ctx->b->issue_wire(); }
+void gsv_ctx_add_gate(gsv_ctx* ctx, int gate_type, uint32_t a, uint32_t b, uint32_t c) {
+  ctx->b->add_gate((uint8_t)gate_type, a, b, c);
+}
+void gsv_ctx_component(gsv_ctx* ctx, const char* key, const uint32_t* inputs, uint32_t n_in, uint32_t arity,
+                       gsv_body_fn body, void* user, uint32_t* outputs) {
+  gsv::Wires in(inputs, inputs + n_in);
+  gsv::Wires out = ctx->b->component(key, in, arity, [body, user, arity](gsv::Builder& b, const gsv::Wires& ins) {
+    gsv_ctx c{&b};
+    gsv::Wires o(arity);
+    body(&c, user, ins.data(), (uint32_t)ins.size(), o.data(), arity);
+    return o;
+  });
+  std::copy(out.begin(), out.end(), outputs);
+}
+
+gsv_program* gsv_program_record(const char* name, uint32_t n_inputs, uint32_t n_outputs, gsv_body_fn root,
+                                void* user, const gsv_plan_options* opt) {
+  try {
+    auto b = std::make_unique<gsv::Builder>();
+    uint32_t r = b->build_root(name ? name : "root", n_inputs, [root, user, n_outputs](gsv::Builder& bb, const gsv::Wires& ins) {
+      gsv_ctx c{&bb};
+      gsv::Wires o(n_outputs);
+      root(&c, user, ins.data(), (uint32_t)ins.size(), o.data(), n_outputs);
+      return o;
+    });
+    return finish_program(std::move(b), r, opt);
+  } catch (const std::exception& e) {
+    fail(GSV_ERR_INVALID, e.what());
+    return nullptr;
+  }
+}
+
+gsv_program* gsv_program_build(const char* circuit, const gsv_plan_options* opt) {
+  try {
+    auto b = std::make_unique<gsv::Builder>();
+    std::string c = circuit ? circuit : "";
+    uint32_t r;
+    if (c == "fq12_mul") r = gsv::build_fq12_mul(*b);
+    else if (c == "fq6_mul") r = gsv::build_fq6_mul(*b);
+    else if (c == "fq2_mul") r = gsv::build_fq2_mul(*b);
+    else if (c == "fq_mul") r = gsv::build_fq_mul(*b);
+    else if (c == "fq_add") r = gsv::build_fq_add(*b);
+    else if (c == "fq_expr") r = gsv::build_fq_expr(*b);
+    else if (c == "gate_zoo") r = gsv::build_gate_zoo(*b);
+    else if (c.rfind("bn_mul", 0) == 0) r = gsv::build_bn_mul(*b, (size_t)std::stoul(c.substr(6)));
+    else {
+      fail(GSV_ERR_INVALID, "unknown circuit: " + c);
+      return nullptr;
+    }
+    return finish_program(std::move(b), r, opt);
+  } catch (const std::exception& e) {
+    fail(GSV_ERR_INVALID, e.what());
+    return nullptr;
+  }
+}
+
+void gsv_program_destroy(gsv_program* p) { delete p; }
+
+int gsv_program_get_info(const gsv_program* p, gsv_program_info* out) {
+  if (!p || !out) return fail(GSV_ERR_INVALID, "null argument");
+  memset(out, 0, sizeof(*out));
+  const gsv::Program& g = p->prog;
+  out->n_gates = g.total_gates;
+  out->n_live_gates = g.total_live;
+  out->n_ciphertexts = g.total_ct;
+  for (int i = 0; i < 11; i++) out->type_count[i] = g.type_count[i];
+  out->n_inputs = g.n_inputs;
+  out->n_outputs = (uint32_t)g.output_slots.size();
+  out->n_tasks = (uint32_t)g.tasks.size();
+  out->n_calls = (uint32_t)g.calls.size();
+  out->n_global_slots = g.n_global_slots;
+  out->max_task_slots = g.max_task_slots;
+  out->max_task_levels = p->max_task_levels;
+  out->max_call_deps = g.max_call_deps;
+  out->sum_call_levels = p->sum_call_levels;
+  return GSV_OK;
+}
+
+int64_t gsv_program_flat_stream(const gsv_program* p, uint8_t* type, uint32_t* a, uint32_t* b, uint32_t* c,
+                                uint64_t capacity, uint32_t* outputs, uint32_t* n_wires) {
+  if (!p) return fail(GSV_ERR_INVALID, "null program");
+  try {
+    const gsv::Template& rt = p->builder->tmpl(p->root);
+    if (!type) {
+      if (n_wires) *n_wires = 0;
+      return (int64_t)rt.total_gates;
+    }
+    if (capacity < rt.total_gates) return fail(GSV_ERR_CAPACITY, "flat stream buffers too small");
+    gsv::FlatStream fs = gsv::flatten(*p->builder, p->root, rt.total_gates + 1);
+    memcpy(type, fs.type.data(), fs.type.size());
+    memcpy(a, fs.a.data(), fs.a.size() * 4);
+    memcpy(b, fs.b.data(), fs.b.size() * 4);
+    memcpy(c, fs.c.data(), fs.c.size() * 4);
+    if (outputs) memcpy(outputs, fs.outputs.data(), fs.outputs.size() * 4);
+    if (n_wires) *n_wires = fs.n_wires;
+    return (int64_t)fs.type.size();
+  } catch (const std::exception& e) {
+    return fail(GSV_ERR_INVALID, e.what());
+  }
+}
+
+}  // extern "C"
+
+// =============================================================================== session
+struct gsv_session {
+  const gsv_program* prog = nullptr;
+  int device = 0;
+  uint32_t B = 0, G = 1, NT = 256, n_workers = 4, n_groups = 0;
+  uint32_t slots_per_worker = 0;
+  uint32_t ct_mode = GSV_CT_COMMIT;
+  int sm_count = 0;
+  size_t smem_garble = 0, smem_eval = 0;
+  uint32_t epoch = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // program on device
+  DevBuf<uint4> d_gates;
+  DevBuf<uint32_t> d_level_off;
+  DevBuf<uint16_t> d_in_slot, d_out_slot;
+  DevBuf<DevTaskD> d_tasks;
+  DevBuf<DevCallD> d_calls;
+  DevBuf<uint32_t> d_call_slots, d_deps, d_output_slots;
+  // instance state
+  DevBuf<uint4> d_labels, d_delta, d_ct, d_commit, d_io, d_stage;
+  DevBuf<uint8_t> d_vals, d_io_bits;
+  DevBuf<uint32_t> d_flags, d_ctrl;  // d_ctrl[0] = next_item, [1] = error flag
+  DevBuf<unsigned long long> d_seeds;
+  bool ct_valid = false;
+  ~gsv_session() {
+    if (stream) cudaStreamDestroy(stream);
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+  }
+};
+
+namespace {
+
+void upload_program(gsv_session* s) {
+  const gsv::Program& g = s->prog->prog;
+  std::vector<uint4> gates;
+  std::vector<uint32_t> level_off;
+  std::vector<uint16_t> in_slot, out_slot;
+  std::vector<DevTaskD> tasks;
+  for (const gsv::Task& t : g.tasks) {
+    DevTaskD d;
+    d.gate_off = (uint32_t)gates.size();
+    d.level_off = (uint32_t)level_off.size();
+    d.n_levels = t.n_levels;
+    d.n_in = t.n_in;
+    d.n_out = t.n_out;
+    d.n_slots = t.n_slots;
+    d.in_slot_off = (uint32_t)in_slot.size();
+    d.out_slot_off = (uint32_t)out_slot.size();
+    for (const gsv::DevGate& dg : t.gates) {
+      uint4 v;
+      memcpy(&v, &dg, 16);
+      gates.push_back(v);
+    }
+    level_off.insert(level_off.end(), t.level_off.begin(), t.level_off.end());
+    if (t.level_off.empty()) level_off.push_back(0);
+    in_slot.insert(in_slot.end(), t.in_slot.begin(), t.in_slot.end());
+    out_slot.insert(out_slot.end(), t.out_slot.begin(), t.out_slot.end());
+    tasks.push_back(d);
+  }
+  // level offsets are task-relative already (gate_off added on device)
+  std::vector<DevCallD> calls;
+  for (const gsv::Call& c : g.calls) {
+    DevCallD d;
+    d.task = c.task;
+    d.in_off = c.in_off;
+    d.out_off = c.out_off;
+    d.dep_off = c.dep_off;
+    d.n_deps = c.n_deps;
+    d.pad = 0;
+    d.gid_base = c.gid_base;
+    d.ct_base = c.ct_base;
+    calls.push_back(d);
+  }
+  if (gates.empty()) gates.push_back(make_uint4(0, 0, 0, 0));
+  if (in_slot.empty()) in_slot.push_back(0);
+  if (out_slot.empty()) out_slot.push_back(0);
+  s->d_gates.upload(gates);
+  s->d_level_off.upload(level_off);
+  s->d_in_slot.upload(in_slot);
+  s->d_out_slot.upload(out_slot);
+  s->d_tasks.upload(tasks);
+  s->d_calls.upload(calls);
+  std::vector<uint32_t> cs = g.call_slots, dp = g.deps, os = g.output_slots;
+  if (cs.empty()) cs.push_back(0);
+  if (dp.empty()) dp.push_back(0);
+  if (os.empty()) os.push_back(0);
+  s->d_call_slots.upload(cs);
+  s->d_deps.upload(dp);
+  s->d_output_slots.upload(os);
+}
+
+EngineParams make_params(gsv_session* s) {
+  EngineParams p;
+  memset(&p, 0, sizeof(p));
+  p.gates = s->d_gates.p;
+  p.level_off = s->d_level_off.p;
+  p.in_slot = s->d_in_slot.p;
+  p.out_slot = s->d_out_slot.p;
+  p.tasks = s->d_tasks.p;
+  p.calls = s->d_calls.p;
+  p.call_slots = s->d_call_slots.p;
+  p.deps = s->d_deps.p;
+  p.labels = s->d_labels.p;
+  p.vals = s->d_vals.p;
+  p.delta = s->d_delta.p;
+  p.ct = s->d_ct.p;
+  p.flags = s->d_flags.p;
+  p.next_item = s->d_ctrl.p;
+  p.error_flag = s->d_ctrl.p + 1;
+  p.n_calls = (uint32_t)s->prog->prog.calls.size();
+  p.n_groups = s->n_groups;
+  p.n_global_slots = s->prog->prog.n_global_slots;
+  p.B = s->B;
+  p.slots_per_worker = s->slots_per_worker;
+  p.worker_threads = s->NT;
+  p.epoch = s->epoch;
+  return p;
+}
+
+template <int MODE>
+void launch_engine(gsv_session* s, int hasher, const EngineParams& p) {
+  const size_t smem = MODE == 0 ? s->smem_garble : s->smem_eval;
+  dim3 grid(s->sm_count), block(s->n_workers * s->NT);
+#define GSV_LAUNCH(GG, HH)                                                                              \
+  do {                                                                                                  \
+    CUDA_TRY(cudaFuncSetAttribute(k_engine<GG, HH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                  (int)smem));                                                          \
+    k_engine<GG, HH, MODE><<<grid, block, smem, s->stream>>>(p);                                        \
+  } while (0)
+#define GSV_LAUNCH_G(HH)                         \
+  switch (s->G) {                                \
+    case 1: GSV_LAUNCH(1, HH); break;            \
+    case 2: GSV_LAUNCH(2, HH); break;            \
+    case 4: GSV_LAUNCH(4, HH); break;            \
+    case 8: GSV_LAUNCH(8, HH); break;            \
+    default: throw std::runtime_error("bad group size"); \
+  }
+  if (hasher == GSV_HASH_AES) { GSV_LAUNCH_G(HASH_AES) }
+  else if (hasher == GSV_HASH_BLAKE3) { GSV_LAUNCH_G(HASH_BLAKE3) }
+  else throw std::runtime_error("unknown hasher");
+#undef GSV_LAUNCH_G
+#undef GSV_LAUNCH
+  CUDA_TRY(cudaGetLastError());
+}
+
+}  // namespace
+
+extern "C" {
+
+gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options* opt) {
+  if (!p || !opt) {
+    fail(GSV_ERR_INVALID, "null argument");
+    return nullptr;
+  }
+  try {
+    ensure_device(opt->device);
+    auto s = std::make_unique<gsv_session>();
+    s->prog = p;
+    s->device = opt->device;
+    s->B = opt->n_instances;
+    s->ct_mode = opt->ct_mode;
+    if (s->B == 0) throw std::runtime_error("n_instances must be > 0");
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
+    s->sm_count = prop.multiProcessorCount;
+    const gsv::Program& g = p->prog;
+    const size_t smem_max = prop.sharedMemPerBlockOptin;
+    uint32_t slots = std::max<uint32_t>(g.max_task_slots, 4);
+    slots = (slots + 3) & ~3u;
+    s->slots_per_worker = slots;
+    s->NT = opt->worker_threads ? opt->worker_threads : 256;
+    if (s->NT != 64 && s->NT != 128 && s->NT != 256 && s->NT != 512 && s->NT != 1024)
+      throw std::runtime_error("worker_threads must be 64/128/256/512/1024");
+    uint32_t n_workers = 1024 / s->NT;
+    // largest G (power of two dividing B, <= 8) whose label working set fits next to the tables
+    auto smem_for = [&](uint32_t G, uint32_t nw, bool eval) {
+      size_t lab = (size_t)slots * G;
+      return (size_t)4096 + nw * lab * 16 + (eval ? nw * lab : 0) + nw * 4 + 16;
+    };
+    uint32_t G = opt->group;
+    if (G == 0) {
+      G = 2;
+      while (G > 1 && (s->B % G != 0)) G >>= 1;
+    }
+    if (G != 1 && G != 2 && G != 4 && G != 8) throw std::runtime_error("group must be 1/2/4/8");
+    if (s->B % G) throw std::runtime_error("n_instances must be a multiple of group");
+    while (n_workers > 1 && smem_for(G, n_workers, true) > smem_max) n_workers >>= 1;
+    if (smem_for(G, n_workers, true) > smem_max)
+      throw std::runtime_error("task working set does not fit shared memory; lower group or max_task_slots");
+    s->G = G;
+    s->n_workers = n_workers;
+    s->n_groups = s->B / G;
+    s->smem_garble = smem_for(G, n_workers, false);
+    s->smem_eval = smem_for(G, n_workers, true);
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (auto& e : s->ev) CUDA_TRY(cudaEventCreate(&e));
+    upload_program(s.get());
+    s->d_labels.alloc((size_t)s->B * g.n_global_slots);
+    s->d_delta.alloc(s->B);
+    s->d_commit.alloc(s->B);
+    s->d_seeds.alloc(s->B);
+    s->d_flags.alloc((size_t)g.calls.size() * s->n_groups + 1);
+    CUDA_TRY(cudaMemset(s->d_flags.p, 0, s->d_flags.n * 4));
+    s->d_ctrl.alloc(4);
+    CUDA_TRY(cudaMemset(s->d_ctrl.p, 0, 16));
+    if (s->ct_mode != GSV_CT_NONE) s->d_ct.alloc((size_t)std::max<uint64_t>(g.total_ct, 1) * s->B);
+    return s.release();
+  } catch (const std::exception& e) {
+    fail(std::string(e.what()).find("no CUDA device") != std::string::npos ? GSV_ERR_NO_DEVICE : GSV_ERR_CUDA, e.what());
+    return nullptr;
+  }
+}
+
+void gsv_session_destroy(gsv_session* s) {
+  if (s) cudaSetDevice(s->device);
+  delete s;
+}
+
+int gsv_garble_batch(gsv_session* s, int hasher, const uint64_t* seeds, gsv_garble_result* res) {
+  if (!s || !seeds || !res) return fail(GSV_ERR_INVALID, "null argument");
+  try {
+    CUDA_TRY(cudaSetDevice(s->device));
+    const gsv::Program& g = s->prog->prog;
+    const uint32_t B = s->B;
+    uint32_t launches = 0;
+    s->epoch++;
+    CUDA_TRY(cudaMemcpyAsync(s->d_seeds.p, seeds, (size_t)B * 8, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->d_ctrl.p, 0, 16, s->stream));
+    CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
+    {
+      const uint32_t n_blocks = (3 + g.n_inputs + 3) / 4;
+      const size_t total = (size_t)B * n_blocks;
+      k_seed_expand<0><<<(unsigned)((total + 127) / 128), 128, 0, s->stream>>>(
+          s->d_seeds.p, B, s->G, g.n_inputs, g.n_global_slots, s->d_labels.p, s->d_delta.p);
+      CUDA_TRY(cudaGetLastError());
+      launches++;
+    }
+    CUDA_TRY(cudaEventRecord(s->ev[1], s->stream));
+    EngineParams p = make_params(s);
+    p.write_ct = (s->ct_mode != GSV_CT_NONE) ? 1u : 0u;
+    launch_engine<0>(s, hasher, p);
+    launches++;
+    CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
+    if (s->ct_mode != GSV_CT_NONE) {
+      k_chain<0><<<(B + 31) / 32, 32, 0, s->stream>>>(s->d_ct.p, g.total_ct, B, s->d_commit.p);
+      CUDA_TRY(cudaGetLastError());
+      launches++;
+    }
+    CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
+    // ---- results
+    if (res->delta) CUDA_TRY(cudaMemcpyAsync(res->delta, s->d_delta.p, (size_t)B * 16, cudaMemcpyDeviceToHost, s->stream));
+    if (res->ct_commit && s->ct_mode != GSV_CT_NONE)
+      CUDA_TRY(cudaMemcpyAsync(res->ct_commit, s->d_commit.p, (size_t)B * 16, cudaMemcpyDeviceToHost, s->stream));
+    auto gather = [&](const std::vector<uint32_t>& slots, uint8_t* host_out) {
+      if (!host_out || slots.empty()) return;
+      DevBuf<uint32_t> d_slots;
+      d_slots.upload(slots);
+      const size_t total = (size_t)B * slots.size();
+      if (s->d_io.n < total) s->d_io.alloc(total);
+      k_gather_slots<0><<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(
+          s->d_labels.p, nullptr, d_slots.p, (uint32_t)slots.size(), B, s->G, g.n_global_slots, s->d_io.p, nullptr);
+      CUDA_TRY(cudaGetLastError());
+      launches++;
+      CUDA_TRY(cudaMemcpyAsync(host_out, s->d_io.p, total * 16, cudaMemcpyDeviceToHost, s->stream));
+      CUDA_TRY(cudaStreamSynchronize(s->stream));
+    };
+    gather({0u}, res->false_label0);
+    gather({1u}, res->true_label0);
+    if (res->input_label0) {
+      std::vector<uint32_t> in(g.n_inputs);
+      for (uint32_t i = 0; i < g.n_inputs; i++) in[i] = 2 + i;
+      gather(in, res->input_label0);
+    }
+    gather(g.output_slots, res->output_label0);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    cudaEventElapsedTime(&res->ms_seed, s->ev[0], s->ev[1]);
+    cudaEventElapsedTime(&res->ms_garble, s->ev[1], s->ev[2]);
+    cudaEventElapsedTime(&res->ms_commit, s->ev[2], s->ev[3]);
+    cudaEventElapsedTime(&res->ms_total, s->ev[0], s->ev[3]);
+    res->n_ciphertexts = g.total_ct;
+    res->n_launches = launches;
+    s->ct_valid = (s->ct_mode == GSV_CT_KEEP || s->ct_mode == GSV_CT_COMMIT);
+    return GSV_OK;
+  } catch (const std::exception& e) {
+    return fail(GSV_ERR_CUDA, e.what());
+  }
+}
+
+int gsv_session_read_ciphertexts(gsv_session* s, uint32_t instance, uint64_t first, uint64_t count, uint8_t* out) {
+  if (!s || !out) return fail(GSV_ERR_INVALID, "null argument");
+  try {
+    CUDA_TRY(cudaSetDevice(s->device));
+    const gsv::Program& g = s->prog->prog;
+    if (!s->ct_valid || s->ct_mode == GSV_CT_NONE) return fail(GSV_ERR_INVALID, "no ciphertext stream kept");
+    if (instance >= s->B || first + count > g.total_ct) return fail(GSV_ERR_INVALID, "range out of bounds");
+    if (count == 0) return GSV_OK;
+    if (s->d_stage.n < count) s->d_stage.alloc(count);
+    k_ct_extract<0><<<(unsigned)((count + 255) / 256), 256, 0, s->stream>>>(s->d_ct.p, s->B, instance, first, count, s->d_stage.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, s->d_stage.p, count * 16, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return GSV_OK;
+  } catch (const std::exception& e) {
+    return fail(GSV_ERR_CUDA, e.what());
+  }
+}
+
+int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io) {
+  if (!s || !io || !io->true_label || !io->false_label) return fail(GSV_ERR_INVALID, "null argument");
+  try {
+    CUDA_TRY(cudaSetDevice(s->device));
+    const gsv::Program& g = s->prog->prog;
+    const uint32_t B = s->B;
+    const uint32_t n_in = g.n_inputs, n_out = (uint32_t)g.output_slots.size();
+    if (n_in && (!io->input_active || !io->input_bits)) return fail(GSV_ERR_INVALID, "missing inputs");
+    uint32_t launches = 0;
+    uint64_t ct_avail = g.total_ct;
+    if (io->ct_streams) {
+      // FileSource-style host streams: upload and interleave
+      if (s->d_ct.n < (size_t)std::max<uint64_t>(g.total_ct, 1) * B) s->d_ct.alloc((size_t)std::max<uint64_t>(g.total_ct, 1) * B);
+      ct_avail = std::min<uint64_t>(io->ct_stream_len, g.total_ct);
+      if (ct_avail) {
+        if (s->d_stage.n < ct_avail) s->d_stage.alloc(ct_avail);
+        for (uint32_t i = 0; i < B; i++) {
+          CUDA_TRY(cudaMemcpyAsync(s->d_stage.p, io->ct_streams[i], ct_avail * 16, cudaMemcpyHostToDevice, s->stream));
+          k_ct_insert<0><<<(unsigned)((ct_avail + 255) / 256), 256, 0, s->stream>>>(s->d_ct.p, B, i, 0, ct_avail, s->d_stage.p);
+          CUDA_TRY(cudaGetLastError());
+          launches++;
+        }
+      }
+      ct_avail = io->ct_stream_len;
+    } else if (!s->ct_valid) {
+      return fail(GSV_ERR_INVALID, "no ciphertext stream in the session (garble with GSV_CT_KEEP first)");
+    }
+    if (s->d_vals.n < (size_t)B * g.n_global_slots) s->d_vals.alloc((size_t)B * g.n_global_slots);
+    // inputs -> device
+    DevBuf<uint4> d_true, d_false, d_in;
+    DevBuf<uint8_t> d_bits;
+    d_true.alloc(B);
+    d_false.alloc(B);
+    d_in.alloc(std::max<size_t>((size_t)B * n_in, 1));
+    d_bits.alloc(std::max<size_t>((size_t)B * n_in, 1));
+    CUDA_TRY(cudaMemcpyAsync(d_true.p, io->true_label, (size_t)B * 16, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_false.p, io->false_label, (size_t)B * 16, cudaMemcpyHostToDevice, s->stream));
+    if (n_in) {
+      CUDA_TRY(cudaMemcpyAsync(d_in.p, io->input_active, (size_t)B * n_in * 16, cudaMemcpyHostToDevice, s->stream));
+      CUDA_TRY(cudaMemcpyAsync(d_bits.p, io->input_bits, (size_t)B * n_in, cudaMemcpyHostToDevice, s->stream));
+    }
+    s->epoch++;
+    CUDA_TRY(cudaMemsetAsync(s->d_ctrl.p, 0, 16, s->stream));
+    CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
+    {
+      const size_t total = (size_t)B * (n_in + 2);
+      k_scatter_inputs<0><<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(
+          d_in.p, d_bits.p, d_true.p, d_false.p, n_in, B, s->G, g.n_global_slots, s->d_labels.p, s->d_vals.p);
+      CUDA_TRY(cudaGetLastError());
+      launches++;
+    }
+    CUDA_TRY(cudaEventRecord(s->ev[1], s->stream));
+    EngineParams p = make_params(s);
+    p.ct_capacity = ct_avail;
+    launch_engine<1>(s, hasher, p);
+    launches++;
+    CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
+    // the evaluator's own chain hash over what it consumed (FileSource hashes while reading)
+    const uint64_t used = std::min<uint64_t>(ct_avail, g.total_ct);
+    k_chain<0><<<(B + 31) / 32, 32, 0, s->stream>>>(s->d_ct.p, used, B, s->d_commit.p);
+    CUDA_TRY(cudaGetLastError());
+    launches++;
+    CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
+    uint32_t ctrl[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(ctrl, s->d_ctrl.p, 16, cudaMemcpyDeviceToHost, s->stream));
+    if (io->ct_commit) CUDA_TRY(cudaMemcpyAsync(io->ct_commit, s->d_commit.p, (size_t)B * 16, cudaMemcpyDeviceToHost, s->stream));
+    if (n_out && (io->output_active || io->output_bits)) {
+      const size_t total = (size_t)B * n_out;
+      if (s->d_io.n < total) s->d_io.alloc(total);
+      if (s->d_io_bits.n < total) s->d_io_bits.alloc(total);
+      k_gather_slots<0><<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(
+          s->d_labels.p, s->d_vals.p, s->d_output_slots.p, n_out, B, s->G, g.n_global_slots, s->d_io.p, s->d_io_bits.p);
+      CUDA_TRY(cudaGetLastError());
+      launches++;
+      if (io->output_active) CUDA_TRY(cudaMemcpyAsync(io->output_active, s->d_io.p, total * 16, cudaMemcpyDeviceToHost, s->stream));
+      if (io->output_bits) CUDA_TRY(cudaMemcpyAsync(io->output_bits, s->d_io_bits.p, total, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    cudaEventElapsedTime(&io->ms_evaluate, s->ev[1], s->ev[2]);
+    cudaEventElapsedTime(&io->ms_commit, s->ev[2], s->ev[3]);
+    cudaEventElapsedTime(&io->ms_total, s->ev[0], s->ev[3]);
+    io->n_launches = launches;
+    if (ctrl[1]) return fail(GSV_ERR_CT_EXHAUSTED, "Ciphertext source exhausted");
+    return GSV_OK;
+  } catch (const std::exception& e) {
+    return fail(GSV_ERR_CUDA, e.what());
+  }
+}
+
+int gsv_commit_labels(int device, const uint8_t* labels, uint64_t n, uint8_t* out) {
+  if (!labels || !out) return fail(GSV_ERR_INVALID, "null argument");
+  try {
+    ensure_device(device);
+    if (n == 0) return GSV_OK;
+    DevBuf<uint4> d_in, d_out;
+    d_in.alloc(n);
+    d_out.alloc(n);
+    CUDA_TRY(cudaMemcpy(d_in.p, labels, n * 16, cudaMemcpyHostToDevice));
+    k_commit_labels<0><<<(unsigned)((n + 255) / 256), 256>>>(d_in.p, n, d_out.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, d_out.p, n * 16, cudaMemcpyDeviceToHost));
+    return GSV_OK;
+  } catch (const std::exception& e) {
+    return fail(std::string(e.what()).find("no CUDA device") != std::string::npos ? GSV_ERR_NO_DEVICE : GSV_ERR_CUDA, e.what());
+  }
+}
+
+int gsv_hash_blocks(int device, int hasher, const uint8_t* x, const uint64_t* gid, uint64_t n, uint8_t* out) {
+  if (!x || !gid || !out) return fail(GSV_ERR_INVALID, "null argument");
+  try {
+    ensure_device(device);
+    if (n == 0) return GSV_OK;
+    DevBuf<uint4> d_in, d_out;
+    DevBuf<unsigned long long> d_gid;
+    d_in.alloc(n);
+    d_out.alloc(n);
+    d_gid.alloc(n);
+    CUDA_TRY(cudaMemcpy(d_in.p, x, n * 16, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_gid.p, gid, n * 8, cudaMemcpyHostToDevice));
+    if (hasher == GSV_HASH_AES) k_hash_blocks<HASH_AES><<<(unsigned)((n + 255) / 256), 256>>>(d_in.p, d_gid.p, n, d_out.p);
+    else k_hash_blocks<HASH_BLAKE3><<<(unsigned)((n + 255) / 256), 256>>>(d_in.p, d_gid.p, n, d_out.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, d_out.p, n * 16, cudaMemcpyDeviceToHost));
+    return GSV_OK;
+  } catch (const std::exception& e) {
+    return fail(std::string(e.what()).find("no CUDA device") != std::string::npos ? GSV_ERR_NO_DEVICE : GSV_ERR_CUDA, e.what());
+  }
+}
+
+int gsv_bench_hash(int device, int hasher, uint64_t n_blocks, int iters, double* blocks_per_s) {
+  if (!blocks_per_s) return fail(GSV_ERR_INVALID, "null argument");
+  try {
+    ensure_device(device);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const unsigned grid = (unsigned)prop.multiProcessorCount * 8, block = 256;
+    const unsigned long long threads = (unsigned long long)grid * block;
+    unsigned long long per_thread = std::max<unsigned long long>(1, n_blocks / (2 * threads));
+    DevBuf<uint4> sink;
+    sink.alloc(1);
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int it = 0; it < std::max(iters, 1) + 1; it++) {
+      CUDA_TRY(cudaEventRecord(e0));
+      if (hasher == GSV_HASH_AES) k_bench_hash<HASH_AES><<<grid, block>>>(per_thread, sink.p);
+      else k_bench_hash<HASH_BLAKE3><<<grid, block>>>(per_thread, sink.p);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaEventRecord(e1));
+      CUDA_TRY(cudaEventSynchronize(e1));
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (it > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *blocks_per_s = (double)(2 * per_thread * threads) / (best * 1e-3);
+    return GSV_OK;
+  } catch (const std::exception& e) {
+    return fail(std::string(e.what()).find("no CUDA device") != std::string::npos ? GSV_ERR_NO_DEVICE : GSV_ERR_CUDA, e.what());
+  }
+}
+
+}  // extern "C"

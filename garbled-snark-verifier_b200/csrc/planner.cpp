@@ -1,0 +1,430 @@
+// planner.cpp -- cuts the template DAG into shared-memory-sized tasks, levelises them and
+// emits the call list with global slots and dependencies.  See program.h.
+#include <algorithm>
+#include <cassert>
+#include <map>
+#include <stdexcept>
+#include <unordered_map>
+
+#include "program.h"
+
+namespace gsv {
+
+namespace {
+
+constexpr uint32_t UNSET = 0xFFFFFFFEu;
+
+// Levelise + slot-pack one flat SSA stream (ids: 0/1 consts, [2, 2+n_in) inputs, then defs).
+Task compile_flat(const FlatStream& fs, const std::string& key, const PlanOptions& opt) {
+  Task t;
+  t.key = key;
+  t.n_in = fs.n_inputs;
+  const size_t ng = fs.type.size();
+  t.n_gates_total = ng;
+  const uint32_t nw = fs.n_wires;
+  const uint32_t first_def = WIRE_MIN + fs.n_inputs;
+
+  // ---- ASAP levels (inputs / constants at level 0)
+  std::vector<uint32_t> wlevel(nw, 0);       // level at which a wire becomes available
+  std::vector<uint32_t> asap(ng, 0), sched(ng, 0);
+  std::vector<uint32_t> ct_off(ng, 0);
+  uint32_t depth = 0;
+  uint64_t n_ct = 0, n_live = 0;
+  for (size_t g = 0; g < ng; g++) {
+    if (fs.c[g] == WIRE_DEAD) continue;
+    uint32_t l = 1 + std::max(wlevel[fs.a[g]], wlevel[fs.b[g]]);
+    asap[g] = l;
+    wlevel[fs.c[g]] = l;
+    depth = std::max(depth, l);
+    n_live++;
+    if (!is_free(fs.type[g])) ct_off[g] = (uint32_t)n_ct++;
+  }
+  t.n_ct = n_ct;
+  t.n_live = n_live;
+  t.n_levels = depth;
+
+  // ---- ALAP levels: as late as the consumers allow; sinks (outputs, unread wires) at `depth`
+  if (opt.alap) {
+    std::vector<uint32_t> req(nw, depth);  // latest level at which the wire must be available
+    for (size_t gi = ng; gi-- > 0;) {
+      if (fs.c[gi] == WIRE_DEAD) continue;
+      uint32_t l = req[fs.c[gi]];
+      sched[gi] = l;
+      if (l < asap[gi]) throw std::logic_error("ALAP below ASAP in " + key);
+      req[fs.a[gi]] = std::min(req[fs.a[gi]], l - 1);
+      req[fs.b[gi]] = std::min(req[fs.b[gi]], l - 1);
+    }
+  } else {
+    sched = asap;
+  }
+
+  // ---- order: by level, non-free first, then emission order
+  std::vector<uint32_t> order;
+  order.reserve(n_live);
+  for (size_t g = 0; g < ng; g++)
+    if (fs.c[g] != WIRE_DEAD) order.push_back((uint32_t)g);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+    if (sched[x] != sched[y]) return sched[x] < sched[y];
+    return (int)is_free(fs.type[x]) < (int)is_free(fs.type[y]);
+  });
+
+  // ---- last use per wire (in scheduled levels); outputs are pinned to the end
+  const uint32_t PIN = depth + 1;
+  std::vector<uint32_t> last_use(nw, 0), def_level(nw, 0);
+  std::vector<uint8_t> is_read(nw, 0);
+  for (uint32_t g : order) {
+    last_use[fs.a[g]] = std::max(last_use[fs.a[g]], sched[g]);
+    last_use[fs.b[g]] = std::max(last_use[fs.b[g]], sched[g]);
+    is_read[fs.a[g]] = is_read[fs.b[g]] = 1;
+    def_level[fs.c[g]] = sched[g];
+    last_use[fs.c[g]] = std::max(last_use[fs.c[g]], sched[g]);
+  }
+  for (size_t j = 0; j < fs.outputs.size(); j++) {
+    uint32_t o = fs.outputs[j];
+    if (o != WIRE_DEAD && o >= first_def) last_use[o] = PIN;
+  }
+
+  // ---- interval colouring.  A slot whose wire is last read at level l is reusable by a gate
+  // at level >= l+1 (readers and writers of one level run concurrently between two barriers).
+  std::vector<uint32_t> slot(nw, UNSET);
+  slot[0] = 0;
+  slot[1] = 1;
+  uint32_t next_slot = 2;
+  std::vector<uint32_t> free_slots;
+  std::vector<std::vector<uint32_t>> release(depth + 3);  // release[l]: wires whose last use is l
+  t.in_slot.assign(fs.n_inputs, 0xFFFF);
+  for (uint32_t i = 0; i < fs.n_inputs; i++) {
+    uint32_t w = WIRE_MIN + i;
+    if (!is_read[w]) continue;  // never read inside the task: no gather, no slot
+    slot[w] = next_slot++;
+    t.in_slot[i] = (uint16_t)slot[w];
+    release[last_use[w]].push_back(w);
+  }
+  t.level_off.assign(depth + 1, 0);
+  t.gates.reserve(order.size());
+  size_t oi = 0;
+  for (uint32_t l = 1; l <= depth; l++) {
+    for (uint32_t w : release[l - 1]) free_slots.push_back(slot[w]);
+    t.level_off[l - 1] = (uint32_t)t.gates.size();
+    size_t begin = oi;
+    while (oi < order.size() && sched[order[oi]] == l) oi++;
+    t.max_width = std::max<uint32_t>(t.max_width, (uint32_t)(oi - begin));
+    for (size_t k = begin; k < oi; k++) {
+      uint32_t g = order[k];
+      uint32_t c = fs.c[g];
+      uint32_t s;
+      if (!free_slots.empty()) {
+        s = free_slots.back();
+        free_slots.pop_back();
+      } else {
+        s = next_slot++;
+      }
+      slot[c] = s;
+      if (last_use[c] != PIN) release[std::max(last_use[c], l)].push_back(c);
+      if (slot[fs.a[g]] == UNSET || slot[fs.b[g]] == UNSET) throw std::logic_error("unslotted read in " + key);
+      if (next_slot > 0xFFFF) throw std::length_error("task needs more than 65535 slots: " + key);
+      DevGate dg;
+      dg.a = (uint16_t)slot[fs.a[g]];
+      dg.b = (uint16_t)slot[fs.b[g]];
+      dg.c = (uint16_t)s;
+      dg.type = fs.type[g];
+      dg.flags = is_free(fs.type[g]) ? 0 : 1;
+      dg.gid_off = g;
+      dg.ct_off = ct_off[g];
+      t.gates.push_back(dg);
+    }
+  }
+  t.level_off[depth] = (uint32_t)t.gates.size();
+  t.n_slots = next_slot;
+
+  // ---- produced outputs
+  for (size_t j = 0; j < fs.outputs.size(); j++) {
+    uint32_t o = fs.outputs[j];
+    if (o == WIRE_DEAD || o < first_def) continue;  // dead / constant / passthrough input
+    t.out_pos.push_back((uint32_t)j);
+    t.out_slot.push_back((uint16_t)slot[o]);
+  }
+  t.n_out = (uint32_t)t.out_pos.size();
+  return t;
+}
+
+struct Planner {
+  const Builder& b;
+  PlanOptions opt;
+  Program prog;
+  // per builder template: -2 unknown, -1 structural, >=0 task index
+  std::vector<int64_t> kind;
+  // loose-gate runs of structural templates: (template, first item) -> task index
+  std::map<std::pair<uint32_t, uint32_t>, uint32_t> loose_task;
+  std::vector<int64_t> producer;  // global wire -> producing call (-1: circuit input / constant)
+  uint32_t next_global = 0;
+  uint64_t gid = 0, ct = 0;
+
+  Planner(const Builder& b_, const PlanOptions& o) : b(b_), opt(o), kind(b_.n_templates(), -2) {}
+
+  int64_t classify(uint32_t ti) {
+    if (kind[ti] != -2) return kind[ti];
+    const Template& t = b.tmpl(ti);
+    bool can_split = !t.calls.empty();
+    if (t.total_gates > opt.max_task_gates && can_split) return kind[ti] = -1;
+    if (t.total_gates == 0) {
+      // pure re-wiring component (e.g. add_constant(0)): an empty task
+      Task e;
+      e.key = t.key;
+      e.n_in = t.n_in;
+      e.in_slot.assign(t.n_in, 0xFFFF);
+      e.n_slots = 2;
+      e.level_off.assign(1, 0);
+      prog.tasks.push_back(std::move(e));
+      return kind[ti] = (int64_t)prog.tasks.size() - 1;
+    }
+    FlatStream fs = flatten(b, ti, std::max<uint64_t>(opt.max_task_gates, t.total_gates) + 1);
+    Task task = compile_flat(fs, t.key, opt);
+    if (task.n_slots > opt.max_task_slots && can_split) return kind[ti] = -1;
+    if (task.n_slots > opt.max_task_slots)
+      throw std::length_error("unsplittable component exceeds the slot budget: " + t.key + " (" +
+                              std::to_string(task.n_slots) + " slots)");
+    prog.tasks.push_back(std::move(task));
+    return kind[ti] = (int64_t)prog.tasks.size() - 1;
+  }
+
+  void emit_call(uint32_t task_idx, const std::vector<uint32_t>& in_global, std::vector<uint32_t>& out_global) {
+    const Task& task = prog.tasks[task_idx];
+    Call c;
+    c.task = task_idx;
+    c.gid_base = gid;
+    c.ct_base = ct;
+    c.in_off = (uint32_t)prog.call_slots.size();
+    std::vector<uint32_t> deps;
+    for (uint32_t i = 0; i < task.n_in; i++) {
+      uint32_t w = in_global[i];
+      // inputs the task never reads are not gathered; keep the slot list dense anyway
+      prog.call_slots.push_back(w == WIRE_DEAD ? 0u : w);
+      if (task.in_slot[i] != 0xFFFF && w != WIRE_DEAD && producer[w] >= 0) deps.push_back((uint32_t)producer[w]);
+    }
+    c.out_off = (uint32_t)prog.call_slots.size();
+    uint32_t call_idx = (uint32_t)prog.calls.size();
+    out_global.assign(task.n_out, UNSET);
+    // duplicate produced outputs (same slot) share one global wire
+    std::unordered_map<uint16_t, uint32_t> by_slot;
+    for (uint32_t k = 0; k < task.n_out; k++) {
+      auto it = by_slot.find(task.out_slot[k]);
+      uint32_t w;
+      if (it != by_slot.end()) w = it->second;
+      else {
+        w = next_global++;
+        producer.push_back((int64_t)call_idx);
+        by_slot.emplace(task.out_slot[k], w);
+      }
+      out_global[k] = w;
+      prog.call_slots.push_back(w);
+    }
+    std::sort(deps.begin(), deps.end());
+    deps.erase(std::unique(deps.begin(), deps.end()), deps.end());
+    c.dep_off = (uint32_t)prog.deps.size();
+    c.n_deps = (uint32_t)deps.size();
+    prog.deps.insert(prog.deps.end(), deps.begin(), deps.end());
+    prog.max_call_deps = std::max(prog.max_call_deps, c.n_deps);
+    prog.calls.push_back(c);
+    gid += task.n_gates_total;
+    ct += task.n_ct;
+  }
+
+  // Expands a structural template; returns the global wire of every callee output position.
+  std::vector<uint32_t> expand(uint32_t ti, const std::vector<uint32_t>& in_global) {
+    const Template& t = b.tmpl(ti);
+    std::vector<uint32_t> l2g(t.n_wires, UNSET);
+    l2g[0] = 0;
+    l2g[1] = 1;
+    for (uint32_t i = 0; i < t.n_in; i++) l2g[WIRE_MIN + i] = in_global[i];
+
+    // last item that reads each local wire (for loose-run outputs)
+    std::vector<uint32_t> last_read;
+    bool has_gates = !t.gates.empty();
+    if (has_gates) {
+      last_read.assign(t.n_wires, 0);
+      for (uint32_t k = 0; k < t.items.size(); k++) {
+        const Item& it = t.items[k];
+        if (!it.is_call) {
+          const GateRec& g = t.gates[it.idx];
+          last_read[g.a] = k + 1;
+          last_read[g.b] = k + 1;
+        } else {
+          const CallRec& c = t.calls[it.idx];
+          uint32_t n_in = b.tmpl(c.tmpl).n_in;
+          for (uint32_t i = 0; i < n_in; i++) {
+            Wire w = t.call_wires[c.in_off + i];
+            if (w != WIRE_DEAD) last_read[w] = k + 1;
+          }
+        }
+      }
+      for (Wire o : t.outs)
+        if (o != WIRE_DEAD) last_read[o] = (uint32_t)t.items.size() + 1;
+    }
+
+    size_t k = 0;
+    while (k < t.items.size()) {
+      const Item& it = t.items[k];
+      if (!it.is_call) {
+        // ---- a run of loose gates [k, e): wrap it into an anonymous task
+        size_t e = k;
+        while (e < t.items.size() && !t.items[e].is_call) e++;
+        auto key = std::make_pair(ti, (uint32_t)k);
+        // build the run's flat stream (also needed to bind wires on a cache hit)
+        FlatStream fs;
+        std::unordered_map<Wire, uint32_t> ext;  // external local wire -> flat input id
+        std::vector<Wire> ext_order;
+        std::unordered_map<Wire, uint32_t> def;  // local wire -> flat id (latest def)
+        auto rd = [&](Wire w) -> uint32_t {
+          if (w < WIRE_MIN) return w;
+          auto d = def.find(w);
+          if (d != def.end()) return d->second;
+          auto x = ext.find(w);
+          if (x != ext.end()) return x->second;
+          uint32_t id = WIRE_MIN + (uint32_t)ext_order.size();
+          ext.emplace(w, id);
+          ext_order.push_back(w);
+          return id;
+        };
+        // two passes: first discover the external inputs so that def ids start after them
+        for (size_t q = k; q < e; q++) {
+          const GateRec& g = t.gates[t.items[q].idx];
+          if (g.a >= WIRE_MIN && !def.count(g.a)) rd(g.a);
+          if (g.b >= WIRE_MIN && !def.count(g.b)) rd(g.b);
+          if (g.c != WIRE_DEAD) def[g.c] = 0;
+        }
+        def.clear();
+        fs.n_inputs = (uint32_t)ext_order.size();
+        uint32_t next = WIRE_MIN + fs.n_inputs;
+        std::vector<std::pair<Wire, uint32_t>> defs_in_order;
+        for (size_t q = k; q < e; q++) {
+          const GateRec& g = t.gates[t.items[q].idx];
+          uint32_t fa = rd(g.a), fb = rd(g.b);
+          uint32_t fc = WIRE_DEAD;
+          if (g.c != WIRE_DEAD) {
+            fc = next++;
+            def[g.c] = fc;
+          }
+          fs.type.push_back(g.type);
+          fs.a.push_back(fa);
+          fs.b.push_back(fb);
+          fs.c.push_back(fc);
+        }
+        fs.n_wires = next;
+        std::vector<Wire> out_local;
+        for (auto& d : def)
+          if (last_read[d.first] > e) out_local.push_back(d.first);
+        std::sort(out_local.begin(), out_local.end());
+        for (Wire w : out_local) fs.outputs.push_back(def[w]);
+        uint32_t task_idx;
+        auto lt = loose_task.find(key);
+        if (lt != loose_task.end()) task_idx = lt->second;
+        else {
+          Task task = compile_flat(fs, t.key + "@run" + std::to_string(k), opt);
+          if (task.n_slots > opt.max_task_slots)
+            throw std::length_error("loose gate run exceeds the slot budget in " + t.key);
+          prog.tasks.push_back(std::move(task));
+          task_idx = (uint32_t)prog.tasks.size() - 1;
+          loose_task.emplace(key, task_idx);
+        }
+        std::vector<uint32_t> ins(ext_order.size());
+        for (size_t i = 0; i < ext_order.size(); i++) {
+          ins[i] = l2g[ext_order[i]];
+          if (ins[i] == UNSET) throw std::logic_error("loose run reads unset wire in " + t.key);
+        }
+        std::vector<uint32_t> outs;
+        emit_call(task_idx, ins, outs);
+        const Task& task = prog.tasks[task_idx];
+        for (uint32_t q = 0; q < task.n_out; q++) l2g[out_local[task.out_pos[q]]] = outs[q];
+        k = e;
+        continue;
+      }
+      const CallRec& c = t.calls[it.idx];
+      const Template& ch = b.tmpl(c.tmpl);
+      std::vector<uint32_t> ins(ch.n_in);
+      for (uint32_t i = 0; i < ch.n_in; i++) {
+        Wire w = t.call_wires[c.in_off + i];
+        ins[i] = (w == WIRE_DEAD) ? WIRE_DEAD : l2g[w];
+        if (ins[i] == UNSET) throw std::logic_error("call passes unset wire in " + t.key);
+      }
+      int64_t kd = classify(c.tmpl);
+      if (kd >= 0) {
+        std::vector<uint32_t> outs;
+        emit_call((uint32_t)kd, ins, outs);
+        const Task& task = prog.tasks[(size_t)kd];
+        for (uint32_t q = 0; q < task.n_out; q++) {
+          Wire p = t.call_wires[c.out_off + task.out_pos[q]];
+          if (p == WIRE_DEAD || p < WIRE_MIN) throw std::logic_error("produced output bound to const/dead");
+          l2g[p] = outs[q];
+        }
+      } else {
+        std::vector<uint32_t> outs = expand(c.tmpl, ins);
+        for (size_t j = 0; j < outs.size(); j++) {
+          Wire p = t.call_wires[c.out_off + j];
+          if (p == WIRE_DEAD || p < WIRE_MIN) continue;
+          if (l2g[p] == UNSET) l2g[p] = outs[j];
+        }
+      }
+      k++;
+    }
+    std::vector<uint32_t> res(t.outs.size());
+    for (size_t j = 0; j < t.outs.size(); j++) {
+      Wire o = t.outs[j];
+      res[j] = (o == WIRE_DEAD) ? WIRE_DEAD : l2g[o];
+      if (res[j] == UNSET) throw std::logic_error("unset output in " + t.key);
+    }
+    return res;
+  }
+};
+
+}  // namespace
+
+Task compile_task(const Builder& b, uint32_t tmpl, const PlanOptions& opt) {
+  FlatStream fs = flatten(b, tmpl);
+  return compile_flat(fs, b.tmpl(tmpl).key, opt);
+}
+
+Program plan_program(const Builder& b, uint32_t root, const PlanOptions& opt) {
+  Planner p(b, opt);
+  const Template& rt = b.tmpl(root);
+  p.prog.n_inputs = rt.n_in;
+  p.next_global = WIRE_MIN + rt.n_in;
+  p.producer.assign(p.next_global, -1);
+  std::vector<uint32_t> ins(rt.n_in);
+  for (uint32_t i = 0; i < rt.n_in; i++) ins[i] = WIRE_MIN + i;
+  std::vector<uint32_t> outs;
+  int64_t kd = p.classify(root);
+  if (kd >= 0) {
+    // the whole circuit is one task
+    std::vector<uint32_t> produced;
+    p.emit_call((uint32_t)kd, ins, produced);
+    const Task& task = p.prog.tasks[(size_t)kd];
+    outs.assign(rt.outs.size(), UNSET);
+    for (size_t j = 0; j < rt.outs.size(); j++) {
+      Wire o = rt.outs[j];
+      if (o == WIRE_DEAD) outs[j] = WIRE_DEAD;
+      else if (o < WIRE_MIN) outs[j] = o;
+      else if (o - WIRE_MIN < rt.n_in) outs[j] = ins[o - WIRE_MIN];
+    }
+    for (uint32_t q = 0; q < task.n_out; q++) outs[task.out_pos[q]] = produced[q];
+  } else {
+    outs = p.expand(root, ins);
+  }
+  Program& prog = p.prog;
+  prog.output_slots = outs;
+  prog.n_global_slots = p.next_global;  // v1: one slot per inter-task wire (no recycling)
+  prog.total_gates = p.gid;
+  prog.total_ct = p.ct;
+  prog.total_live = rt.total_live;
+  for (int i = 0; i < 11; i++) prog.type_count[i] = rt.type_count[i];
+  for (const Task& t : prog.tasks) {
+    prog.max_task_slots = std::max(prog.max_task_slots, t.n_slots);
+    prog.max_task_in = std::max(prog.max_task_in, t.n_in);
+  }
+  if (prog.total_gates != rt.total_gates || prog.total_ct != rt.total_ct)
+    throw std::logic_error("planner lost gates: " + std::to_string(prog.total_gates) + " vs " +
+                           std::to_string(rt.total_gates));
+  return prog;
+}
+
+}  // namespace gsv

@@ -1,0 +1,95 @@
+// program.h -- the flattened, levelised gate program the GPU executes.
+//
+// The reference walks gates one at a time through a slab of live wires with run-time credits
+// (src/circuit/modes/garble_mode.rs:160-222, src/storage.rs).  On the GPU that per-gate
+// bookkeeping is resolved ONCE at flatten time:
+//
+//   * the template DAG (circuit.h) is cut into TASKS: component bodies small enough that all of
+//     their live wires fit in shared memory.  A task is flattened, levelised (dependency depth)
+//     and its wires are packed into compact shared-memory SLOTS by interval colouring -- the
+//     static replacement of the credits slab.
+//   * the program is the emission-ordered list of CALLS of those tasks.  Each call carries the
+//     running gate index base (the AES/BLAKE3 tweak, hashers/mod.rs:56-64) and the running
+//     ciphertext index base (position in the commitment stream, ciphertext_hasher.rs:23-29), so
+//     gates may execute in any dependency-respecting order and still produce the reference's
+//     bytes at the reference's positions.
+//   * wires that cross task boundaries live in a per-instance GLOBAL slot array in HBM/L2;
+//     calls list their producer calls (RAW) and, when slots are recycled, the readers of the
+//     previous occupant (WAR) as dependencies.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "circuit.h"
+
+namespace gsv {
+
+// 16-byte device gate record.  Slots are task-local shared-memory label slots.
+struct alignas(16) DevGate {
+  uint16_t a, b, c;
+  uint8_t type;
+  uint8_t flags;    // bit0: has ciphertext
+  uint32_t gid_off; // gate index relative to the call's gid_base (dead gates counted)
+  uint32_t ct_off;  // ciphertext index relative to the call's ct_base
+};
+static_assert(sizeof(DevGate) == 16, "DevGate must be 16 bytes");
+
+struct Task {
+  std::string key;
+  uint32_t n_in = 0;        // input positions
+  uint32_t n_out = 0;       // produced (non-passthrough, live) outputs
+  uint32_t n_slots = 0;     // shared-memory slots incl. 0/1 constants
+  uint32_t n_levels = 0;
+  uint32_t max_width = 0;
+  uint64_t n_gates_total = 0;  // gate-index advance (dead gates included)
+  uint64_t n_ct = 0;
+  uint64_t n_live = 0;
+  std::vector<DevGate> gates;        // sorted by level, non-free first inside a level
+  std::vector<uint32_t> level_off;   // n_levels + 1
+  std::vector<uint16_t> in_slot;     // per input position; 0xFFFF when the input is never read
+  std::vector<uint16_t> out_slot;    // per produced output
+  std::vector<uint32_t> out_pos;     // callee output position of each produced output
+};
+
+struct Call {
+  uint32_t task;
+  uint64_t gid_base;
+  uint64_t ct_base;
+  uint32_t in_off;    // into Program::call_slots, task.n_in entries (global slots)
+  uint32_t out_off;   // into Program::call_slots, task.n_out entries
+  uint32_t dep_off;   // into Program::deps
+  uint32_t n_deps;
+};
+
+struct Program {
+  std::vector<Task> tasks;
+  std::vector<Call> calls;
+  std::vector<uint32_t> call_slots;
+  std::vector<uint32_t> deps;
+  uint32_t n_global_slots = 0;       // incl. slots 0/1 (constants) and the circuit inputs
+  uint32_t n_inputs = 0;             // circuit inputs live in global slots [2, 2+n_inputs)
+  std::vector<uint32_t> output_slots;  // global slot per circuit output (0/1 = constants)
+  uint64_t total_gates = 0;
+  uint64_t total_ct = 0;
+  uint64_t total_live = 0;
+  uint32_t max_task_slots = 0;
+  uint32_t max_task_in = 0;
+  uint32_t max_call_deps = 0;
+  uint64_t type_count[11] = {0};
+};
+
+struct PlanOptions {
+  uint64_t max_task_gates = 600000;  // templates above this are structural (split into children)
+  uint32_t max_task_slots = 1536;    // shared-memory label slots per instance
+  bool alap = true;                  // schedule gates as late as possible (smaller live sets)
+  uint32_t reuse_distance = 0;       // 0: never recycle global slots; else min #calls before reuse
+};
+
+// Cuts, flattens, levelises and packs.  Throws on circuits it cannot plan.
+Program plan_program(const Builder& b, uint32_t root, const PlanOptions& opt);
+
+// Schedules one flattened leaf (exposed for tests / statistics).
+Task compile_task(const Builder& b, uint32_t tmpl, const PlanOptions& opt);
+
+}  // namespace gsv

@@ -1,0 +1,215 @@
+/*
+ * gsv_cuda.h -- C ABI of libgsv_cuda.so, the B200 (sm_100a) garbling / evaluation engine.
+ *
+ * The reference (BitVM/garbled-snark-verifier v0.4.0) has no FFI layer: the seam this library
+ * replaces is the Rust trait set around `CircuitMode` (src/circuit/modes.rs:26-51).  A Rust shim
+ * crate (`gsv-cuda`) binds exactly the functions below:
+ *
+ *   reference interface                                       -> entry point here
+ *   -----------------------------------------------------------------------------------------
+ *   CircuitContext::{issue_wire,add_gate,with_named_child}     gsv_rec_*        (record topology once)
+ *     (src/circuit/circuit_context_trait.rs:12-27)
+ *   CircuitBuilder::streaming_garbling<H, CTH>                 gsv_garble_batch (GarbleMode hot loop,
+ *     (src/circuit/mod.rs:185-208), GarbleMode::evaluate_gate    src/circuit/modes/garble_mode.rs:160-222)
+ *   AESAccumulatingHash as CiphertextHandler                   GSV_CT_COMMIT    (src/ciphertext_hasher.rs:23-29)
+ *   channel::Sender<S> / FileCiphertextHandler                 GSV_CT_KEEP + gsv_session_read_ciphertexts
+ *     (src/circuit/mod.rs:160-170, cut_and_choose/ciphertext_repository.rs:59-136)
+ *   CircuitBuilder::streaming_evaluation<H, SRC>               gsv_evaluate_batch (EvaluateMode hot loop,
+ *     (src/circuit/mod.rs:229-250)                               src/circuit/modes/evaluate_mode.rs:123-158)
+ *   commit_label / GarbledInstanceCommit::new                  gsv_commit_labels
+ *     (src/cut_and_choose/mod.rs:41-65, garbler.rs:85-116)
+ *   GateHasher = AesNiHasher | Blake3Hasher                    enum gsv_hasher (src/hashers/mod.rs:15-96)
+ *
+ * Conventions: every label crosses the ABI as 16 bytes in `S::to_bytes()` order (big-endian
+ * u128, src/core/s.rs:25-32).  The caller owns all in/out buffers.  Functions return 0 on
+ * success and a negative gsv_status otherwise (never unwind); gsv_last_error() describes the
+ * last failure of the calling thread.  One host thread drives one device; the library uses its
+ * own CUDA streams.  There is NO CPU fallback: every compute entry point fails with
+ * GSV_ERR_NO_DEVICE when no CUDA device is present.
+ */
+#ifndef GSV_CUDA_H
+#define GSV_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gsv_recorder gsv_recorder;
+typedef struct gsv_program gsv_program;
+typedef struct gsv_session gsv_session;
+
+enum gsv_status {
+  GSV_OK = 0,
+  GSV_ERR_INVALID = -1,
+  GSV_ERR_NO_DEVICE = -2,
+  GSV_ERR_CUDA = -3,
+  GSV_ERR_CAPACITY = -4,
+  GSV_ERR_CT_EXHAUSTED = -5 /* "Ciphertext source exhausted", evaluate_mode.rs:140-142 */
+};
+
+/* src/hashers/mod.rs:7-11 */
+enum gsv_hasher { GSV_HASH_AES = 0, GSV_HASH_BLAKE3 = 1 };
+
+/* src/core/gate_type.rs:1-15 */
+enum gsv_gate_type {
+  GSV_AND = 0, GSV_NAND = 1, GSV_NIMP = 2, GSV_IMP = 3, GSV_NCIMP = 4, GSV_CIMP = 5,
+  GSV_NOR = 6, GSV_OR = 7, GSV_XOR = 8, GSV_XNOR = 9, GSV_NOT = 10
+};
+
+#define GSV_WIRE_FALSE 0u
+#define GSV_WIRE_TRUE 1u
+#define GSV_WIRE_UNREACHABLE 0xFFFFFFFFu
+
+/* What happens to the ciphertext stream of a garbling run (the CiphertextHandler choice). */
+enum gsv_ct_mode {
+  GSV_CT_NONE = 0,   /* `()` handler: ciphertexts are dropped (src/circuit/mod.rs:172-178)       */
+  GSV_CT_COMMIT = 1, /* AESAccumulatingHash: bit-exact chain commitment, stream not kept         */
+  GSV_CT_KEEP = 2    /* commitment + the stream stays in HBM for evaluation / read-back / P2P     */
+};
+
+const char* gsv_last_error(void);
+/* Number of visible CUDA devices (0 when none). */
+int gsv_device_count(void);
+const char* gsv_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Topology recording: the C mirror of CircuitContext (circuit_context_trait.rs:12-27).
+ * The recorder runs the reference's two passes (metadata/credits, execution) itself; a caller
+ * describes each component as a callback that re-emits the body on demand.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gsv_ctx gsv_ctx; /* opaque per-callback context */
+/* body(ctx, user, inputs[n_in], outputs[arity]) must issue wires / add gates / call children
+ * deterministically; it is invoked once for the credits pass and once per liveness variant. */
+typedef void (*gsv_body_fn)(gsv_ctx* ctx, void* user, const uint32_t* inputs, uint32_t n_in,
+                            uint32_t* outputs, uint32_t arity);
+
+uint32_t gsv_ctx_issue_wire(gsv_ctx* ctx);
+void gsv_ctx_add_gate(gsv_ctx* ctx, int gate_type, uint32_t a, uint32_t b, uint32_t c);
+/* with_named_child: `key` = component name + off-circuit parameters (component_key.rs:15-39). */
+void gsv_ctx_component(gsv_ctx* ctx, const char* key, const uint32_t* inputs, uint32_t n_in,
+                       uint32_t arity, gsv_body_fn body, void* user, uint32_t* outputs);
+
+typedef struct {
+  uint64_t max_task_gates; /* 0 = default (600000) */
+  uint32_t max_task_slots; /* 0 = default (1536 shared-memory label slots per instance) */
+  uint32_t reserved;
+} gsv_plan_options;
+
+/* Records `root(ctx, user, inputs[n_inputs], outputs[n_outputs])` (CircuitBuilder::run_streaming,
+ * src/circuit/mod.rs:253-301) and plans it into a levelised task program. */
+gsv_program* gsv_program_record(const char* name, uint32_t n_inputs, uint32_t n_outputs,
+                                gsv_body_fn root, void* user, const gsv_plan_options* opt);
+/* The named workload circuits built by the library's own C++ gadget restatement
+ * (src/gadgets/**): "fq12_mul", "fq6_mul", "fq2_mul", "fq_mul", "fq_add", "fq_expr",
+ * "gate_zoo", "bn_mul<N>". */
+gsv_program* gsv_program_build(const char* circuit, const gsv_plan_options* opt);
+void gsv_program_destroy(gsv_program* p);
+
+typedef struct {
+  uint64_t n_gates;       /* every add_gate call (dead ones included), = GateCount total     */
+  uint64_t n_live_gates;
+  uint64_t n_ciphertexts; /* live non-free gates                                            */
+  uint64_t type_count[11];
+  uint32_t n_inputs;
+  uint32_t n_outputs;
+  uint32_t n_tasks;
+  uint32_t n_calls;
+  uint32_t n_global_slots;
+  uint32_t max_task_slots;
+  uint32_t max_task_levels;
+  uint32_t max_call_deps;
+  uint64_t sum_call_levels; /* sum over calls of their task's level count */
+} gsv_program_info;
+int gsv_program_get_info(const gsv_program* p, gsv_program_info* out);
+
+/* Flat emission-order gate stream (SSA wire ids: 0/1 constants, 2.. inputs, then one id per
+ * written wire; c = GSV_WIRE_UNREACHABLE for dead gates).  Checkers feed this to the CPU
+ * oracle.  Pass NULL arrays to query sizes.  Returns the gate count or a negative status. */
+int64_t gsv_program_flat_stream(const gsv_program* p, uint8_t* type, uint32_t* a, uint32_t* b,
+                                uint32_t* c, uint64_t capacity, uint32_t* outputs,
+                                uint32_t* n_wires);
+
+/* ------------------------------------------------------------------------------------------
+ * Execution.  A session owns the device state of `n_instances` instances of one program on
+ * one GPU: per-instance global label slots, deltas, the interleaved ciphertext buffer.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int device;             /* CUDA device ordinal */
+  uint32_t n_instances;   /* batch size B (cut-and-choose instances on this GPU) */
+  uint32_t group;         /* instances per work item: 1,2,4,8; 0 = auto */
+  uint32_t worker_threads;/* threads per worker: 128/256/512; 0 = auto */
+  uint32_t ct_mode;       /* enum gsv_ct_mode */
+  uint32_t reserved[3];
+} gsv_session_options;
+
+gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options* opt);
+void gsv_session_destroy(gsv_session* s);
+
+typedef struct {
+  /* all optional (NULL = not wanted); host pointers */
+  uint8_t* delta;         /* B * 16        secret                                        */
+  uint8_t* false_label0;  /* B * 16        GarbleMode::false_value().label0              */
+  uint8_t* true_label0;   /* B * 16                                                      */
+  uint8_t* input_label0;  /* B * n_inputs * 16, EncodeInput order                        */
+  uint8_t* output_label0; /* B * n_outputs * 16                                          */
+  uint8_t* ct_commit;     /* B * 16        AESAccumulatingHash::finalize                 */
+  /* filled by the call */
+  uint64_t n_ciphertexts; /* per instance */
+  float ms_seed;          /* device time of the seed-expansion kernel (CUDA events)      */
+  float ms_garble;        /* device time of the garbling kernel                          */
+  float ms_commit;        /* device time of the chain-commitment kernel                  */
+  float ms_total;         /* first launch -> last kernel done                            */
+  uint32_t n_launches;    /* kernels launched by this call                               */
+  uint32_t reserved;
+} gsv_garble_result;
+
+/* streaming_garbling for B instances: instance i uses seeds[i] (garble_mode.rs:80-97). */
+int gsv_garble_batch(gsv_session* s, int hasher, const uint64_t* seeds, gsv_garble_result* res);
+
+/* Copies ciphertexts [first, first+count) of `instance` to `out` in the reference stream
+ * format (count * 16 bytes, emission order = gc_{i}.bin, ciphertext_source.rs:95-101).
+ * Requires GSV_CT_KEEP. */
+int gsv_session_read_ciphertexts(gsv_session* s, uint32_t instance, uint64_t first, uint64_t count,
+                                 uint8_t* out);
+
+typedef struct {
+  /* inputs (host pointers) */
+  const uint8_t* true_label;    /* B * 16   true constant's label1  (mod.rs:278-279)            */
+  const uint8_t* false_label;   /* B * 16   false constant's label0                              */
+  const uint8_t* input_active;  /* B * n_inputs * 16                                             */
+  const uint8_t* input_bits;    /* B * n_inputs (0/1)                                            */
+  /* ciphertext source: NULL = the session's own kept stream (garbler and evaluator share the
+   * GPU); otherwise B host streams of n_ciphertexts*16 bytes each (FileSource layout).           */
+  const uint8_t* const* ct_streams;
+  uint64_t ct_stream_len;       /* ciphertexts available per host stream                         */
+  /* outputs (host pointers, optional) */
+  uint8_t* output_active;       /* B * n_outputs * 16                                            */
+  uint8_t* output_bits;         /* B * n_outputs                                                 */
+  uint8_t* ct_commit;           /* B * 16  chain hash of the consumed ciphertexts                */
+  float ms_evaluate;
+  float ms_commit;
+  float ms_total;
+  uint32_t n_launches;
+  uint32_t reserved;
+} gsv_evaluate_io;
+
+/* streaming_evaluation for B instances (evaluate_mode.rs:70-158). */
+int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io);
+
+/* commit(label) = AES128_K(label) for n labels (src/cut_and_choose/mod.rs:41-48). */
+int gsv_commit_labels(int device, const uint8_t* labels, uint64_t n, uint8_t* out);
+
+/* Raw AES / BLAKE3 gate-hash micro-kernels: n blocks, register resident; returns blocks/s in
+ * *rate (the integer-ALU roof of SURVEY.md section 8d).  out (n*16, optional) gets H(x_i, gid_i)
+ * for x_i = counter pattern -- used by the parity tests of the device primitives. */
+int gsv_hash_blocks(int device, int hasher, const uint8_t* x, const uint64_t* gid, uint64_t n,
+                    uint8_t* out);
+int gsv_bench_hash(int device, int hasher, uint64_t n_blocks, int iters, double* blocks_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSV_CUDA_H */

@@ -1,0 +1,165 @@
+"""Host-side logic: the C++ gadget restatement, the credits/liveness pass, the planner, and the
+oracle's whole-stream garble/evaluate -- everything that runs without a GPU."""
+import random
+
+import numpy as np
+import pytest
+
+import bn254_ref as bn
+
+WIRE_DEAD = 0xFFFFFFFF
+
+
+# gate counts derived at survey time with an independent re-statement
+MODEL = {
+    "fq_add": (3298, 1523, 1522),
+    "bn_mul254": (183326, 55602, 55602),
+    "fq_mul": (414284, 102093, 102093),
+    "fq12_mul": (20284982, 5439790, 5439206),
+}
+
+
+@pytest.mark.parametrize("name", list(MODEL))
+def test_gate_counts_match_model(circuit, name):
+    p, st = circuit(name)
+    gates, nonfree, cts = MODEL[name]
+    assert p.n_gates == gates
+    assert sum(p.type_count[:8]) == nonfree
+    assert p.n_ciphertexts == cts
+    assert st.n_gates == gates
+    # #ciphertexts == #live non-free gates (garble_test.rs:82,129-133)
+    assert int(((st.type < 8) & (st.c != WIRE_DEAD)).sum()) == cts
+
+
+def test_fq12_mul_type_mix(circuit):
+    p, _ = circuit("fq12_mul")
+    # Xor 14.69 M, And 4.83 M, Nand 297 k, Xnor 151 k, Or 156 k, Cimp 148 k
+    assert p.type_count == [4831858, 296672, 4572, 0, 2420, 148336, 0, 155932, 14693832, 151360, 0]
+    assert p.n_inputs == 6096 and p.n_outputs == 3048
+
+
+def test_stream_is_well_formed(circuit):
+    for name in ("gate_zoo", "fq_add", "fq_mul"):
+        p, st = circuit(name)
+        defined = np.zeros(st.n_wires, bool)
+        defined[: 2 + st.n_inputs] = True
+        live = st.c != WIRE_DEAD
+        # SSA: every live gate defines a fresh, increasing id
+        ids = st.c[live]
+        assert np.all(np.diff(ids.astype(np.int64)) == 1) and ids[0] == 2 + st.n_inputs
+        # reads only of earlier definitions
+        pos = np.full(st.n_wires, -1, np.int64)
+        pos[ids] = np.nonzero(live)[0]
+        g = np.arange(st.n_gates)
+        assert np.all(pos[st.a] < g) and np.all(pos[st.b] < g)
+        assert np.all(st.outputs < st.n_wires)
+
+
+def test_gate_zoo_dead_gate(circuit):
+    p, st = circuit("gate_zoo")
+    assert p.n_gates == 14 and p.n_live_gates == 13
+    assert int((st.c == WIRE_DEAD).sum()) == 1
+    assert p.n_ciphertexts == 8 + 2  # 8 AND-family + Or/Nimp on constants; the dead And emits none
+    for a in (0, 1):
+        for b in (0, 1):
+            out = st.execute([a, b])
+            want = [a & b, 1 - (a & b), a & (1 - b), (1 - a) | b, (1 - a) & b, (1 - b) | a, 1 - (a | b), a | b,
+                    a ^ b, 1 - (a ^ b), 1 - a, 1]
+            assert list(out) == want
+
+
+def _fq_bits(x):
+    return bn.bits_le(bn.to_mont(x))
+
+
+def test_fq_add_functional(circuit):
+    _, st = circuit("fq_add")
+    rng = random.Random(11)
+    for _ in range(10):
+        a, b = bn.rand_fq(rng), bn.rand_fq(rng)
+        out = st.execute(bn.bits_le(a) + bn.bits_le(b))
+        assert bn.from_bits(out) == (a + b) % bn.P
+
+
+def test_fq_mul_functional(circuit):
+    _, st = circuit("fq_mul")
+    rng = random.Random(12)
+    for a, b in [(0, 0), (1, 1), (bn.P - 1, bn.P - 1)] + [(bn.rand_fq(rng), bn.rand_fq(rng)) for _ in range(5)]:
+        out = st.execute(_fq_bits(a) + _fq_bits(b))
+        assert bn.from_bits(out) == bn.to_mont(a * b % bn.P)
+
+
+def test_fq_expr_functional(circuit):
+    # tests/streaming_evaluate.rs:392-447: ((a^2) b) + a with a = 13, b = 7
+    _, st = circuit("fq_expr")
+    for a, b in [(13, 7), (bn.P - 2, 12345)]:
+        out = st.execute(_fq_bits(a) + _fq_bits(b))
+        assert bn.from_bits(out) == bn.to_mont((a * a * b + a) % bn.P)
+
+
+def test_fq12_mul_functional(circuit):
+    _, st = circuit("fq12_mul")
+    rng = random.Random(13)
+    for _ in range(2):
+        a, b = bn.rand_fq12(rng), bn.rand_fq12(rng)
+        out = st.execute(bn.fq12_bits_mont(a) + bn.fq12_bits_mont(b))
+        assert list(out) == bn.fq12_bits_mont(bn.fq12_mul(a, b))
+
+
+def _labels_for(res, bits):
+    delta = np.frombuffer(res["delta"], np.uint8)
+    act = res["input_label0"].copy()
+    act[np.asarray(bits, bool)] ^= delta
+    return act
+
+
+@pytest.mark.parametrize("hasher", [0, 1])
+@pytest.mark.parametrize("name", ["gate_zoo", "fq_add", "fq_mul"])
+def test_oracle_garble_evaluate_consistency(circuit, orc, name, hasher):
+    """tests/streaming_evaluate.rs:125-132 / fq12_mul_e2e.rs:217-235: gw.select(value) == active."""
+    p, st = circuit(name)
+    rng = random.Random(21)
+    for seed in (0, 42):
+        g = st.garble(hasher, seed)
+        assert g["n_ct"] == p.n_ciphertexts == g["cts"].shape[0]
+        assert orc.chain([bytes(c) for c in g["cts"][:64]]) is not None
+        bits = [rng.randrange(2) for _ in range(st.n_inputs)]
+        delta = np.frombuffer(g["delta"], np.uint8)
+        true1 = bytes(np.frombuffer(g["true_label0"], np.uint8) ^ delta)
+        ev = st.evaluate(hasher, true1, g["false_label0"], _labels_for(g, bits), bits, g["cts"])
+        assert ev["rc"] == 0 and ev["n_ct_used"] == g["n_ct"]
+        assert ev["ct_commit"] == g["ct_commit"]  # evaluator's hash == committed hash
+        assert list(ev["output_bits"]) == list(st.execute(bits))
+        want = g["output_label0"].copy()
+        want[ev["output_bits"].astype(bool)] ^= delta
+        assert np.array_equal(ev["output_active"], want)
+
+
+def test_oracle_ciphertext_exhaustion(circuit):
+    _, st = circuit("fq_add")
+    g = st.garble(0, 1)
+    bits = [0] * st.n_inputs
+    delta = np.frombuffer(g["delta"], np.uint8)
+    true1 = bytes(np.frombuffer(g["true_label0"], np.uint8) ^ delta)
+    ev = st.evaluate(0, true1, g["false_label0"], g["input_label0"], bits, g["cts"][:-1])
+    assert ev["rc"] == -2  # "Ciphertext source exhausted", evaluate_mode.rs:140-142
+
+
+def test_seed_draw_order(circuit, orc):
+    """garble_mode.rs:80-97,116-118: delta, false.label0, true.label0, then the input label0s."""
+    _, st = circuit("fq_add")
+    g = st.garble(0, 777)
+    r = orc.Rng(777)
+    assert r.label() == g["delta"] and r.label() == g["false_label0"] and r.label() == g["true_label0"]
+    for i in range(st.n_inputs):
+        assert r.label() == bytes(g["input_label0"][i])
+
+
+def test_planner_invariants(gsv):
+    p = gsv.Program("fq12_mul")
+    assert p.n_calls == 867 and p.n_tasks == 13
+    assert p.max_task_slots <= 1536
+    small = gsv.Program("fq12_mul", max_task_slots=4096)
+    assert small.n_calls == 507 and small.n_gates == p.n_gates and small.n_ciphertexts == p.n_ciphertexts
+    one = gsv.Program("fq_mul", max_task_slots=8192, max_task_gates=10**7)
+    assert one.n_calls == 1  # whole circuit as a single task

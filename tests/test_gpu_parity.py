@@ -1,0 +1,159 @@
+"""GPU parity: every ciphertext, label, commitment and decoded bit produced through the C ABI on
+the B200 must equal the CPU oracle's on the same seeds (bit-exact; integer/byte work)."""
+import random
+
+import numpy as np
+import pytest
+
+import bn254_ref as bn
+
+pytestmark = pytest.mark.gpu
+
+
+def test_native_library_on_gpu(gsv):
+    assert gsv.device_count() >= 1
+
+
+@pytest.mark.parametrize("hasher", [0, 1])
+def test_device_gate_hash(gsv, orc, hasher):
+    rng = np.random.default_rng(1)
+    n = 4096
+    x = rng.integers(0, 256, (n, 16), dtype=np.uint8)
+    gid = rng.integers(0, 2**63, n, dtype=np.uint64)
+    gid[:8] = [0, 1, 7, 2**32 - 1, 2**32, 2**32 + 5, 11_174_708_820, 2**63 + 17]
+    got = gsv.hash_blocks(hasher, x, gid)
+    for i in range(0, n, 7):
+        assert bytes(got[i]) == orc.hash_gate(hasher, bytes(x[i]), int(gid[i])), i
+
+
+def test_device_label_commit(gsv, orc):
+    rng = np.random.default_rng(2)
+    lab = rng.integers(0, 256, (1000, 16), dtype=np.uint8)
+    got = gsv.commit_labels(lab)
+    for i in range(0, 1000, 13):
+        assert bytes(got[i]) == orc.commit_label(bytes(lab[i]))
+
+
+def _check_garble(gsv, orc, circuit, name, hasher, seeds, group, worker_threads=0, every_ct=True):
+    p, st = circuit(name)
+    sess = gsv.Session(p, len(seeds), group=group, worker_threads=worker_threads, ct_mode=gsv.CT_KEEP)
+    res = sess.garble(seeds, hasher)
+    assert res.n_ciphertexts == p.n_ciphertexts
+    refs = []
+    for i, seed in enumerate(seeds):
+        ref = st.garble(hasher, seed)
+        refs.append(ref)
+        assert bytes(res.delta[i]) == ref["delta"]
+        assert bytes(res.false_label0[i]) == ref["false_label0"]
+        assert bytes(res.true_label0[i]) == ref["true_label0"]
+        assert np.array_equal(res.input_label0[i], ref["input_label0"])
+        assert np.array_equal(res.output_label0[i], ref["output_label0"]), (name, hasher, seed)
+        assert bytes(res.ct_commit[i]) == ref["ct_commit"], (name, hasher, seed)
+        if every_ct:
+            assert np.array_equal(sess.read_ciphertexts(i), ref["cts"])
+    return p, st, sess, res, refs
+
+
+@pytest.mark.parametrize("hasher", [0, 1])
+@pytest.mark.parametrize("name", ["gate_zoo", "fq_add", "fq_mul", "fq_expr"])
+def test_garble_matches_oracle(gsv, orc, circuit, name, hasher):
+    # the reference tests' seeds
+    _check_garble(gsv, orc, circuit, name, hasher, [0, 42, 99, 777], group=2)
+
+
+@pytest.mark.parametrize("group,wt", [(1, 256), (4, 256), (8, 128), (2, 512), (1, 64)])
+def test_garble_group_and_worker_shapes(gsv, orc, circuit, group, wt):
+    seeds = [1234, 12345, 2**64 - 1, 5, 6, 7, 8, 9]
+    _check_garble(gsv, orc, circuit, "fq_mul", 0, seeds, group=group, worker_threads=wt)
+
+
+def test_garble_ragged_batch(gsv, orc, circuit):
+    # odd instance count forces group 1; single instance
+    _check_garble(gsv, orc, circuit, "fq_add", 0, [3, 4, 5], group=0)
+    _check_garble(gsv, orc, circuit, "fq_add", 1, [9], group=0)
+
+
+@pytest.mark.parametrize("hasher", [0, 1])
+def test_fq12_mul_garble_matches_oracle(gsv, orc, circuit, hasher):
+    """config 1 (tests/fq12_mul_e2e.rs, seed 0): all 5.44 M ciphertexts, 3048 output labels,
+    the chain commitment."""
+    _check_garble(gsv, orc, circuit, "fq12_mul", hasher, [0, 42], group=2)
+
+
+def _eval_inputs(res, bits):
+    """EvaluatedWire::new_from_garbled for every input (evaluate_mode.rs:33-38)."""
+    act = res.input_label0.copy()
+    act[np.asarray(bits, bool)] ^= np.broadcast_to(res.delta[:, None, :], act.shape)[np.asarray(bits, bool)]
+    return act
+
+
+@pytest.mark.parametrize("hasher", [0, 1])
+@pytest.mark.parametrize("name", ["gate_zoo", "fq_mul"])
+def test_evaluate_matches_oracle(gsv, orc, circuit, name, hasher):
+    seeds = [0, 42, 99, 777]
+    p, st, sess, res, refs = _check_garble(gsv, orc, circuit, name, hasher, seeds, group=2, every_ct=False)
+    rng = np.random.default_rng(3)
+    bits = rng.integers(0, 2, (len(seeds), p.n_inputs), dtype=np.uint8)
+    act = _eval_inputs(res, bits)
+    ev = sess.evaluate(hasher, res.true_label1, res.false_label0, act, bits)  # the session's own stream
+    streams = [sess.read_ciphertexts(i) for i in range(len(seeds))]
+    sess2 = gsv.Session(p, len(seeds), group=1, ct_mode=gsv.CT_KEEP)  # FileSource-style host streams
+    ev2 = sess2.evaluate(hasher, res.true_label1, res.false_label0, act, bits, ct_streams=streams)
+    for i in range(len(seeds)):
+        o = st.evaluate(hasher, bytes(res.true_label1[i]), bytes(res.false_label0[i]), act[i], bits[i], refs[i]["cts"])
+        assert o["rc"] == 0
+        for e in (ev, ev2):
+            assert np.array_equal(e.output_active[i], o["output_active"])
+            assert np.array_equal(e.output_bits[i], o["output_bits"])
+            assert bytes(e.ct_commit[i]) == o["ct_commit"] == refs[i]["ct_commit"]
+        # gw.select(value) == active_label (tests/fq12_mul_e2e.rs:217-235)
+        want = res.output_label0[i].copy()
+        want[ev.output_bits[i].astype(bool)] ^= res.delta[i]
+        assert np.array_equal(ev.output_active[i], want)
+
+
+def test_evaluate_ciphertext_exhaustion(gsv, circuit):
+    p, st = circuit("fq_add")
+    sess = gsv.Session(p, 2, ct_mode=gsv.CT_KEEP)
+    res = sess.garble([1, 2], 0)
+    bits = np.zeros((2, p.n_inputs), np.uint8)
+    streams = [sess.read_ciphertexts(i)[:-1] for i in range(2)]
+    with pytest.raises(gsv.GsvError) as e:
+        sess.evaluate(0, res.true_label1, res.false_label0, res.input_label0, bits, ct_streams=streams)
+    assert e.value.code == -5  # "Ciphertext source exhausted"
+
+
+def test_fq12_mul_e2e_batch_properties(gsv, circuit):
+    """Full-size, size-independent checks on a 32-instance batch: garble -> evaluate round trip,
+    decoded product == plain BN254 arithmetic, evaluator's stream hash == garbler's commitment,
+    distinct seeds give distinct commitments, same seed is reproducible."""
+    p, _ = circuit("fq12_mul")
+    B = 32
+    seeds = list(range(100, 100 + B - 1)) + [100]
+    sess = gsv.Session(p, B, group=2, ct_mode=gsv.CT_KEEP)
+    res = sess.garble(seeds, gsv.HASH_AES)
+    assert bytes(res.ct_commit[0]) == bytes(res.ct_commit[B - 1])
+    assert len({bytes(c) for c in res.ct_commit}) == B - 1
+    rng = random.Random(5)
+    bits = np.zeros((B, p.n_inputs), np.uint8)
+    want = []
+    for i in range(B):
+        a, b = bn.rand_fq12(rng), bn.rand_fq12(rng)
+        bits[i] = bn.fq12_bits_mont(a) + bn.fq12_bits_mont(b)
+        want.append(bn.fq12_bits_mont(bn.fq12_mul(a, b)))
+    ev = sess.evaluate(gsv.HASH_AES, res.true_label1, res.false_label0, _eval_inputs(res, bits), bits)
+    assert np.array_equal(ev.output_bits, np.array(want, np.uint8))
+    sel = res.output_label0.copy()
+    sel[ev.output_bits.astype(bool)] ^= np.broadcast_to(res.delta[:, None, :], sel.shape)[ev.output_bits.astype(bool)]
+    assert np.array_equal(ev.output_active, sel)
+    assert np.array_equal(ev.ct_commit, res.ct_commit)
+
+
+def test_commit_only_mode_matches_keep(gsv, circuit):
+    p, _ = circuit("fq_mul")
+    seeds = [7, 8, 9, 10]
+    a = gsv.Session(p, 4, ct_mode=gsv.CT_KEEP).garble(seeds, 0)
+    b = gsv.Session(p, 4, ct_mode=gsv.CT_COMMIT).garble(seeds, 0)
+    c = gsv.Session(p, 4, ct_mode=gsv.CT_NONE).garble(seeds, 0)
+    assert np.array_equal(a.ct_commit, b.ct_commit)
+    assert np.array_equal(a.output_label0, b.output_label0) and np.array_equal(a.output_label0, c.output_label0)
