@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py -- garbled gates/s of the B200 engine on the largest circuit the generator builds.
+
+A "step" garbles one batch of B cut-and-choose instances of the workload circuit per GPU from
+seeds (seed expansion -> garbling -> bit-exact ciphertext chain commitment), i.e. the first
+garbling stage of the reference's cut-and-choose (src/cut_and_choose/garbler.rs:191-242) with
+`AesNiHasher` + `AESAccumulatingHash`.
+
+  value : whole-job gates/s, device time (CUDA events inside the library, on its stream), seeds
+          already resident in HBM being the only input.
+  e2e   : same metric through the public API with HOST buffers (seeds H2D, commitments + input /
+          output labels D2H inside the timed region).
+  --impl reference : the CPU oracle (AES-NI restatement of the reference's per-gate loop; the
+          reference itself is Rust and cannot be built in this image) on all host cores.
+
+Launch: `python bench.py --gpus 1`, or under torchrun for N > 1 (one rank per GPU, instances
+sharded across ranks, NCCL used only to all-gather the per-instance commitments).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_GATE = 52.3   # 48 B free gate, 64 B non-free, 73.2/26.8 mix
+AES_BLOCKS_PER_GATE_GARBLE = 2.0  # per NON-FREE gate; + 1 chain block when committing
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        # median over samples under load (above 60 % of the maximum seen)
+        load = [x for x in sm if x >= 0.6 * (sm[-1] if sm else 0)] or sm
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_garble_rate(circuit, n_instances_per_core, cores, hasher=0):
+    """Oracle (CPU restatement, AES-NI when the host has it) on `cores` threads, one instance
+    at a time per core like the reference's pinned rayon pool (cut_and_choose/mod.rs:131-186)."""
+    import gsv_b200 as g
+    from oracle import oracle as o
+
+    prog = g.Program(circuit)
+    t, a, b, c, outs, nw = prog.flat_stream()
+    st = o.Stream(t, a, b, c, outs, nw, prog.n_inputs).compact()  # slab-sized live set, cache resident
+
+    def work(k):
+        for j in range(n_instances_per_core):
+            st.garble(hasher, 1000 * k + j, want_ct=False)  # ctypes releases the GIL
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(cores)]
+    t0 = time.perf_counter()
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    dt = time.perf_counter() - t0
+    gates = prog.n_gates * n_instances_per_core * cores
+    return gates / dt, dt, prog, o.have_aesni()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    rates = []
+    per_core = max(1, args.ref_instances_per_core)
+    for i in range(args.warmup + args.steps):
+        rate, dt, prog, aesni = cpu_garble_rate(args.circuit, per_core, cores)
+        if i >= args.warmup:
+            rates.append((rate, dt))
+    value = sum(r for r, _ in rates) / len(rates)
+    ms = 1e3 * sum(d for _, d in rates) / len(rates)
+    sample = (f"{per_core} instance(s) of {args.circuit} per core on {cores} threads per step, garble + chain "
+              f"commitment, {'AES-NI' if aesni else 'portable AES'}; oracle omits the reference's slab/credit "
+              f"bookkeeping (upper bound on the reference's CPU speed)")
+    line = {
+        "impl": "reference", "metric": "garbled_gates_per_s", "value": value, "unit": "gates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{args.circuit} garble+commit, AES hasher (CPU oracle, bounded sample)",
+                   "gates_per_instance": prog.n_gates},
+        "cpu_baseline": {"value": value, "unit": "gates/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gsv", choices=["gsv", "reference"])
+    ap.add_argument("--circuit", default="fq12_mul")
+    ap.add_argument("--instances", type=int, default=512, help="cut-and-choose instances per GPU")
+    ap.add_argument("--group", type=int, default=0)
+    ap.add_argument("--worker-threads", type=int, default=0)
+    ap.add_argument("--hasher", default="aes", choices=["aes", "blake3"])
+    ap.add_argument("--no-commit", action="store_true", help="drop ciphertexts (the `()` handler)")
+    ap.add_argument("--ref-instances-per-core", type=int, default=2)
+    ap.add_argument("--cpu-baseline-instances", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import gsv_b200 as g
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    hasher = g.HASH_AES if args.hasher == "aes" else g.HASH_BLAKE3
+    ct_mode = g.CT_NONE if args.no_commit else g.CT_COMMIT
+    prog = g.Program(args.circuit)
+    B = args.instances
+    sess = g.Session(prog, B, device=local, group=args.group, worker_threads=args.worker_threads, ct_mode=ct_mode)
+    # cut-and-choose seeds: instance i of rank r (garbler.rs:201-203 draws them from one RNG;
+    # here a fixed arithmetic pattern so every rank/step is reproducible)
+    def seeds_for(step):
+        base = np.uint64(0x9E3779B97F4A7C15)
+        idx = np.arange(B, dtype=np.uint64) + np.uint64((rank * 1_000_003 + step) * B)
+        return idx * base + np.uint64(12345)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    commits_dev = torch.empty((B, 16), dtype=torch.uint8, device="cuda")
+    gathered = torch.empty((world * B, 16), dtype=torch.uint8, device="cuda") if world > 1 else None
+
+    def step(i, want_labels):
+        res = sess.garble(seeds_for(i), hasher, want_inputs=want_labels, want_outputs=want_labels)
+        if world > 1:
+            # the only collective of the path: gather the per-instance commitments
+            commits_dev.copy_(torch.from_numpy(res.ct_commit))
+            dist.all_gather_into_tensor(gathered, commits_dev)
+        return res
+
+    for i in range(args.warmup):
+        step(i, True)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms = garble_ms = commit_ms = seed_ms = 0.0
+    launches = 0
+    for i in range(args.steps):
+        res = step(args.warmup + i, True)
+        dev_ms += res.ms_total
+        garble_ms += res.ms_garble
+        commit_ms += res.ms_commit
+        seed_ms += res.ms_seed
+        launches += res.n_launches
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    # max over ranks, on-device time for `value`, wall (incl. copies) for e2e
+    tt = torch.tensor([dev_ms, wall * 1e3, garble_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max, garble_ms_max = [float(x) for x in tt.tolist()]
+
+    gates_per_step = prog.n_gates * B * world
+    value = gates_per_step * args.steps / (dev_ms_max * 1e-3)
+    e2e = gates_per_step * args.steps / (wall_ms_max * 1e-3)
+    h2d = 8 * B
+    d2h = B * 16 * (4 + prog.n_inputs + prog.n_outputs)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        # dominant kernel = k_engine (garbling); its per-launch device time from the library's events
+        k_ms = garble_ms / args.steps
+        k_gates = prog.n_gates * B
+        achieved = k_gates * ALGO_BYTES_PER_GATE / (k_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "kernel": "k_engine", "kernel_ms": k_ms, "peak_source": peak_src,
+                    "algorithmic_bytes_per_gate": ALGO_BYTES_PER_GATE}
+        try:
+            blocks = g.bench_hash(hasher, 1 << 28, 2, device=local)
+            nonfree = sum(prog.type_count[:8]) / prog.n_gates
+            need = nonfree * AES_BLOCKS_PER_GATE_GARBLE * k_gates / (k_ms * 1e-3)
+            roofline["alu"] = {"hash_blocks_per_s_peak": blocks, "hash_blocks_per_s_achieved": need,
+                               "frac": need / blocks, "note": "register-resident 2-block gate-hash micro-kernel"}
+        except Exception as e:  # pragma: no cover
+            roofline["alu"] = {"error": str(e)}
+        line = {
+            "metric": "garbled_gates_per_s", "value": value, "unit": "gates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {
+                "workload": f"{args.circuit} x {B} cut-and-choose instances per GPU, garble + "
+                            f"{'no commitment' if args.no_commit else 'bit-exact AES chain commitment'}, "
+                            f"{args.hasher} gate hasher (largest circuit the generator builds; the k=6 "
+                            f"verifier generator is not built yet)",
+                "gates_per_instance": prog.n_gates, "ciphertexts_per_instance": prog.n_ciphertexts,
+                "instances_per_gpu": B, "l2": "inputs larger than L2 (label + ciphertext state >> 126 MB)",
+                "parallelism": f"instances sharded over {world} GPU(s); NCCL all-gather of commitments only",
+            },
+            "phases_ms_per_step": {"seed_expand": seed_ms / args.steps, "garble": garble_ms / args.steps,
+                                   "chain_commit": commit_ms / args.steps},
+            "e2e": {"value": e2e, "unit": "gates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            rate, dt, _, aesni = cpu_garble_rate(args.circuit, args.cpu_baseline_instances, cores)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": "gates/s", "cores": cores, "kind": "port",
+                "sample": f"{args.cpu_baseline_instances} instance(s) of {args.circuit} per core on {cores} threads "
+                          f"({dt:.1f} s), garble + chain commitment, {'AES-NI' if aesni else 'portable AES'} oracle",
+            }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

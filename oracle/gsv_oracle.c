@@ -595,3 +595,37 @@ int gsvo_execute_stream(const gsvo_stream* s, const uint8_t* input_bits, uint8_t
   free(val);
   return 0;
 }
+
+int gsvo_compact_stream(const gsvo_stream* s, uint32_t* a2, uint32_t* b2, uint32_t* c2,
+                        uint32_t* outputs2, uint32_t* n_slots) {
+  const uint64_t NEVER = ~0ull;
+  uint64_t* last = (uint64_t*)malloc((size_t)s->n_wires * sizeof(uint64_t));
+  uint32_t* slot = (uint32_t*)malloc((size_t)s->n_wires * sizeof(uint32_t));
+  uint32_t* free_list = (uint32_t*)malloc((size_t)s->n_wires * sizeof(uint32_t));
+  if (!last || !slot || !free_list) { free(last); free(slot); free(free_list); return -3; }
+  for (uint32_t w = 0; w < s->n_wires; w++) { last[w] = 0; slot[w] = GSVO_WIRE_DEAD; }
+  for (uint64_t g = 0; g < s->n_gates; g++) {
+    last[s->a[g]] = g + 1;
+    last[s->b[g]] = g + 1;
+  }
+  for (uint32_t i = 0; i < s->n_outputs; i++) last[s->outputs[i]] = NEVER;
+  last[0] = last[1] = NEVER;
+  uint32_t next = 2 + s->n_inputs, n_free = 0;
+  for (uint32_t w = 0; w < next; w++) slot[w] = w;
+  for (uint64_t g = 0; g < s->n_gates; g++) {
+    uint32_t a = s->a[g], b = s->b[g], c = s->c[g];
+    a2[g] = slot[a];
+    b2[g] = slot[b];
+    if (last[a] == g + 1) free_list[n_free++] = slot[a];
+    if (b != a && last[b] == g + 1) free_list[n_free++] = slot[b];
+    if (c == GSVO_WIRE_DEAD) { c2[g] = GSVO_WIRE_DEAD; continue; }
+    uint32_t sl = n_free ? free_list[--n_free] : next++;
+    slot[c] = sl;
+    c2[g] = sl;
+    if (last[c] == 0) free_list[n_free++] = sl; /* written, never read, not an output */
+  }
+  for (uint32_t i = 0; i < s->n_outputs; i++) outputs2[i] = slot[s->outputs[i]];
+  *n_slots = next;
+  free(last); free(slot); free(free_list);
+  return 0;
+}

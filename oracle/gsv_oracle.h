@@ -142,6 +142,15 @@ int gsvo_evaluate_stream(int hasher, const gsvo_stream* s, const uint8_t true_la
                          uint8_t* output_active_out, uint8_t* output_bits_out,
                          uint8_t ct_commit_out[16], uint64_t* n_ct_used);
 
+/*
+ * Renames the SSA wire ids of a stream to recycled slot ids (a wire's slot is freed after its
+ * last read, outputs stay pinned) -- the static equivalent of the reference's credits slab
+ * (src/storage.rs:119-198), which keeps the live set cache resident.  The result is again a
+ * valid stream (n_wires = *n_slots).  Arrays a2/b2/c2 have n_gates entries, outputs2 n_outputs.
+ */
+int gsvo_compact_stream(const gsvo_stream* s, uint32_t* a2, uint32_t* b2, uint32_t* c2,
+                        uint32_t* outputs2, uint32_t* n_slots);
+
 /* ExecuteMode: plain boolean evaluation of the stream (execute_mode.rs). */
 int gsvo_execute_stream(const gsvo_stream* s, const uint8_t* input_bits, uint8_t* output_bits_out);
 

@@ -62,6 +62,7 @@ def lib() -> C.CDLL:
         L.gsvo_garble_stream.argtypes = [C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.gsvo_evaluate_stream.argtypes = [C.c_int, C.c_void_p] + [C.c_void_p] * 5 + [C.c_uint64] + [C.c_void_p] * 4
         L.gsvo_execute_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gsvo_compact_stream.argtypes = [C.c_void_p] * 6
         _lib = L
     return _lib
 
@@ -186,6 +187,16 @@ class Stream:
         self._s = _Stream(self.n_gates, self.type.ctypes.data, self.a.ctypes.data, self.b.ctypes.data,
                           self.c.ctypes.data, self.n_wires, self.n_inputs, self.n_outputs,
                           self.outputs.ctypes.data)
+
+    def compact(self) -> "Stream":
+        """Same stream with recycled slot ids (cache-resident live set, like the reference's slab)."""
+        a2, b2, c2 = (np.zeros(self.n_gates, np.uint32) for _ in range(3))
+        o2 = np.zeros(max(self.n_outputs, 1), np.uint32)
+        ns = C.c_uint32(0)
+        rc = lib().gsvo_compact_stream(C.byref(self._s), a2.ctypes.data, b2.ctypes.data, c2.ctypes.data,
+                                       o2.ctypes.data, C.byref(ns))
+        assert rc == 0
+        return Stream(self.type, a2, b2, c2, o2[: self.n_outputs], ns.value, self.n_inputs)
 
     def garble(self, hasher: int, seed: int, want_ct: bool = True):
         n_nonfree = int(((self.type < 8) & (self.c != WIRE_DEAD)).sum())
