@@ -24,40 +24,52 @@ __device__ __forceinline__ uint4 and4(uint4 a, uint32_t m) {
   return make_uint4(a.x & m, a.y & m, a.z & m, a.w & m);
 }
 
-// Shared-memory table block: te[0..255] = Te0, +256 = Te1, +512 = Te2, +768 = Te3.
+// Shared-memory table block, 64 KB, bank-conflict free by construction:
+//   row r (256 bytes, r = 0..255): bytes [0,128)   = Te0[r] replicated for the 32 lanes,
+//                                  bytes [128,256) = Te2[r] = rotl(Te0[r], 16) replicated.
+// Lane l only ever touches word l (or 32 + l) of a row, i.e. bank l: every LDS is a single
+// wavefront whatever the 32 indices are (the plain 4 KB layout measured 57 % conflict replays,
+// profiles/r01_first_engine.md).  The byte address (r << 8) | (tbl << 7) | (l << 2) is formed by
+// ONE PRMT from the state word and a per-lane constant, so a lookup costs PRMT + LDS.
+// Te1 / Te3 are rotl8 of Te0 / Te2; rotation is linear, so one PRMT rotates the XOR of both.
+constexpr int AES_TABLE_BYTES = 65536;
+
 __device__ __forceinline__ void load_tables(uint32_t* te, int tid, int nthreads) {
-  for (int i = tid; i < 256; i += nthreads) {
-    uint32_t v = c_te0[i];
-    te[i] = v;
-    te[256 + i] = (v << 8) | (v >> 24);
-    te[512 + i] = (v << 16) | (v >> 16);
-    te[768 + i] = (v << 24) | (v >> 8);
+  for (int i = tid; i < 256 * 64; i += nthreads) {
+    const uint32_t v = c_te0[i >> 6];
+    te[i] = (i & 32) ? ((v << 16) | (v >> 16)) : v;
   }
 }
+// per-lane PRMT operands: byte 0 = lane*4 (+128 for the Te2 half), other bytes zero
+__device__ __forceinline__ uint32_t lane_sel0() { return (threadIdx.x & 31u) << 2; }
 
-#define GSV_AES_ROUND(T, S, R)                                                                    \
-  T.x = te[S.x & 255] ^ te[256 + ((S.y >> 8) & 255)] ^ te[512 + ((S.z >> 16) & 255)] ^            \
-        te[768 + (S.w >> 24)] ^ c_rk[4 * (R) + 0];                                                \
-  T.y = te[S.y & 255] ^ te[256 + ((S.z >> 8) & 255)] ^ te[512 + ((S.w >> 16) & 255)] ^            \
-        te[768 + (S.x >> 24)] ^ c_rk[4 * (R) + 1];                                                \
-  T.z = te[S.z & 255] ^ te[256 + ((S.w >> 8) & 255)] ^ te[512 + ((S.x >> 16) & 255)] ^            \
-        te[768 + (S.y >> 24)] ^ c_rk[4 * (R) + 2];                                                \
-  T.w = te[S.w & 255] ^ te[256 + ((S.x >> 8) & 255)] ^ te[512 + ((S.y >> 16) & 255)] ^            \
-        te[768 + (S.z >> 24)] ^ c_rk[4 * (R) + 3];
+#define GSV_LK(S, J, LB) \
+  (*reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(te) + __byte_perm((S), (LB), 0x5504 | ((J) << 4))))
+#define GSV_ROT8(V) __byte_perm((V), 0, 0x2103)
 
-// last round: SubBytes+ShiftRows only; S-box bytes are picked out of the T tables
-// (Te2 byte0 = s, Te3 byte1 = s, Te0 byte2 = s, Te1 byte3 = s).
-#define GSV_AES_LAST(T, S)                                                                        \
-  T.x = (te[512 + (S.x & 255)] & 0x000000ffu) ^ (te[768 + ((S.y >> 8) & 255)] & 0x0000ff00u) ^    \
-        (te[((S.z >> 16) & 255)] & 0x00ff0000u) ^ (te[256 + (S.w >> 24)] & 0xff000000u) ^ c_rk[40]; \
-  T.y = (te[512 + (S.y & 255)] & 0x000000ffu) ^ (te[768 + ((S.z >> 8) & 255)] & 0x0000ff00u) ^    \
-        (te[((S.w >> 16) & 255)] & 0x00ff0000u) ^ (te[256 + (S.x >> 24)] & 0xff000000u) ^ c_rk[41]; \
-  T.z = (te[512 + (S.z & 255)] & 0x000000ffu) ^ (te[768 + ((S.w >> 8) & 255)] & 0x0000ff00u) ^    \
-        (te[((S.x >> 16) & 255)] & 0x00ff0000u) ^ (te[256 + (S.y >> 24)] & 0xff000000u) ^ c_rk[42]; \
-  T.w = (te[512 + (S.w & 255)] & 0x000000ffu) ^ (te[768 + ((S.x >> 8) & 255)] & 0x0000ff00u) ^    \
-        (te[((S.y >> 16) & 255)] & 0x00ff0000u) ^ (te[256 + (S.z >> 24)] & 0xff000000u) ^ c_rk[43];
+// one column: Te0[b0(A)] ^ Te1[b1(B)] ^ Te2[b2(C)] ^ Te3[b3(D)] ^ rk
+#define GSV_AES_COL(A, B, C, D, RK) \
+  (GSV_LK(A, 0, lb0) ^ GSV_LK(C, 2, lb2) ^ (RK) ^ GSV_ROT8(GSV_LK(B, 1, lb0) ^ GSV_LK(D, 3, lb2)))
+
+#define GSV_AES_ROUND(T, S, R)                          \
+  T.x = GSV_AES_COL(S.x, S.y, S.z, S.w, c_rk[4 * (R) + 0]); \
+  T.y = GSV_AES_COL(S.y, S.z, S.w, S.x, c_rk[4 * (R) + 1]); \
+  T.z = GSV_AES_COL(S.z, S.w, S.x, S.y, c_rk[4 * (R) + 2]); \
+  T.w = GSV_AES_COL(S.w, S.x, S.y, S.z, c_rk[4 * (R) + 3]);
+
+// last round: SubBytes + ShiftRows only.  S-box bytes sit in Te2 byte 0 / byte 3 and Te0
+// byte 1 / byte 2, so three PRMTs assemble the column.
+#define GSV_AES_LASTCOL(A, B, C, D, RK)                                                     \
+  (__byte_perm(__byte_perm(GSV_LK(A, 0, lb2), GSV_LK(B, 1, lb0), 0x7650),                    \
+               __byte_perm(GSV_LK(C, 2, lb0), GSV_LK(D, 3, lb2), 0x7210), 0x7610) ^ (RK))
+#define GSV_AES_LAST(T, S)                              \
+  T.x = GSV_AES_LASTCOL(S.x, S.y, S.z, S.w, c_rk[40]); \
+  T.y = GSV_AES_LASTCOL(S.y, S.z, S.w, S.x, c_rk[41]); \
+  T.z = GSV_AES_LASTCOL(S.z, S.w, S.x, S.y, c_rk[42]); \
+  T.w = GSV_AES_LASTCOL(S.w, S.x, S.y, S.z, c_rk[43]);
 
 __device__ __forceinline__ uint4 aes_fixed(const uint32_t* __restrict__ te, uint4 in) {
+  const uint32_t lb0 = lane_sel0(), lb2 = lb0 | 128u;
   uint4 s = make_uint4(in.x ^ c_rk[0], in.y ^ c_rk[1], in.z ^ c_rk[2], in.w ^ c_rk[3]);
   uint4 t;
 #pragma unroll
@@ -73,6 +85,7 @@ __device__ __forceinline__ uint4 aes_fixed(const uint32_t* __restrict__ te, uint
 // two independent blocks, rounds interleaved for ILP (the GPU analogue of encrypt2_blocks,
 // src/hashers/aes_ni.rs:~120-160)
 __device__ __forceinline__ void aes_fixed2(const uint32_t* __restrict__ te, uint4& a, uint4& b) {
+  const uint32_t lb0 = lane_sel0(), lb2 = lb0 | 128u;
   uint4 s = make_uint4(a.x ^ c_rk[0], a.y ^ c_rk[1], a.z ^ c_rk[2], a.w ^ c_rk[3]);
   uint4 u = make_uint4(b.x ^ c_rk[0], b.y ^ c_rk[1], b.z ^ c_rk[2], b.w ^ c_rk[3]);
   uint4 t, v;

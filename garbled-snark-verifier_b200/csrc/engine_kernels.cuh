@@ -1,14 +1,20 @@
 // engine_kernels.cuh -- the persistent task-dataflow kernels of the garbling engine (sm_100a).
 //
 // Execution model:
-//   grid  = one CTA per SM (persistent), CTA = NW workers of NT threads;
+//   grid  = one CTA per SM (persistent); a CTA = NW garble workers of NT threads
+//           + NC chain warps (commitment consumers);
 //   work  = items (call, instance-group) claimed in emission order by an atomic ticket;
 //           a worker spins on the done-flags of the call's producer calls (RAW) before it
 //           starts, so independent calls of one instance and all instances run concurrently;
 //   task  = gather the call's input labels from the instance's global slot array into shared
 //           memory, run the task level by level (named barrier per level, labels never leave
-//           shared memory), write ciphertexts straight to their stream position, scatter the
-//           produced labels back, publish the done-flag.
+//           shared memory), write ciphertexts straight to their stream position (a ring when
+//           the stream is not kept), scatter the produced labels back, publish the done-flag;
+//   chain = each chain warp owns 32 instances (one per lane) and folds their ciphertext
+//           streams into the bit-exact commitment h <- AES_K(h ^ ct) in emission order, call by
+//           call, as soon as the producing items are done; its progress counter is the ring's
+//           back-pressure.  This is the "commitment fused into the garbling kernel" of the
+//           north star: the serial chain runs concurrently with garbling instead of after it.
 // Thread mapping inside a level: idx -> (gate = idx / G, instance = idx % G); G instances of a
 // gate sit in adjacent lanes so label accesses are contiguous 16-byte vectors and the gate
 // record load is a broadcast.
@@ -17,15 +23,9 @@
 
 namespace gsvdev {
 
-struct DevGateD {  // mirrors gsv::DevGate (program.h)
-  uint16_t a, b, c;
-  uint8_t type;
-  uint8_t flags;
-  uint32_t gid_off;
-  uint32_t ct_off;
-};
 struct DevTaskD {
   uint32_t gate_off, level_off, n_levels, n_in, n_out, n_slots, in_slot_off, out_slot_off;
+  uint32_t n_ct, pad0, pad1, pad2;
 };
 struct DevCallD {
   uint32_t task, in_off, out_off, dep_off, n_deps, pad;
@@ -33,7 +33,7 @@ struct DevCallD {
 };
 
 struct EngineParams {
-  const uint4* gates;  // DevGateD as uint4
+  const uint4* gates;  // gsv::DevGate records as uint4
   const uint32_t* level_off;
   const uint16_t* in_slot;
   const uint16_t* out_slot;
@@ -44,16 +44,20 @@ struct EngineParams {
   uint4* labels;        // [group][global slot][G]
   uint8_t* vals;        // evaluate: plaintext bit per label, same indexing
   const uint4* delta;   // [B]
-  uint4* ct;            // [ct index][B]  (garble: written, evaluate: read)
+  uint4* ct;            // [ct position][B]  (garble: written, evaluate: read)
   uint32_t* flags;      // [call][group] == epoch when done
   uint32_t* next_item;
+  uint32_t* error_flag;       // evaluate: set to 1 on ciphertext exhaustion
+  unsigned long long* chain_progress;  // [chain warp] ciphertexts folded so far
+  uint4* commit;        // [B] chain result
+  unsigned long long ct_mask;      // ring: position = index & ct_mask (all ones: no wrap)
+  unsigned long long ct_ring;      // ring capacity in ciphertexts (0: no back-pressure needed)
+  unsigned long long ct_capacity;  // evaluate: ciphertexts available per instance
   uint32_t n_calls, n_groups, n_global_slots, B;
   uint32_t slots_per_worker;  // shared-memory label slots per instance reserved per worker
-  uint32_t worker_threads;
+  uint32_t worker_threads, n_workers, n_chain_warps;
   uint32_t epoch;
   uint32_t write_ct;          // garble: store ciphertexts
-  unsigned long long ct_capacity;  // evaluate: ciphertexts available per instance
-  uint32_t* error_flag;       // evaluate: set to 1 on ciphertext exhaustion
 };
 
 __device__ __forceinline__ void named_bar(uint32_t id, uint32_t nthreads) {
@@ -67,27 +71,81 @@ __device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
 __device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long ld_acquire64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---- commitment consumer: one warp, 32 instances, runs until every call is folded
+__device__ __forceinline__ void chain_warp(const EngineParams& p, const uint32_t* te, uint32_t cw) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t first = cw * 32u;
+  if (first >= p.B) return;
+  const uint32_t n_inst = min(32u, p.B - first);
+  const uint32_t G = p.B / p.n_groups;
+  const uint32_t g0 = first / G, ng = n_inst / G;
+  const bool active = lane < n_inst;
+  const uint4* base = p.ct + first + (active ? lane : 0u);
+  uint4 h = make_uint4(0, 0, 0, 0);
+  for (uint32_t c = 0; c < p.n_calls; ++c) {
+    const DevCallD call = p.calls[c];
+    const uint32_t n = p.tasks[call.task].n_ct;
+    if (n == 0) continue;
+    if (lane < ng) {
+      const uint32_t* f = p.flags + (size_t)c * p.n_groups + g0 + lane;
+      while (ld_acquire(f) != p.epoch) __nanosleep(200);
+    }
+    __syncwarp();
+    unsigned long long k = call.ct_base;
+    const unsigned long long end = k + n;
+    constexpr int U = 8;
+    for (; k + U <= end; k += U) {
+      uint4 v[U];
+#pragma unroll
+      for (int j = 0; j < U; j++) v[j] = __ldcg(base + (size_t)((k + j) & p.ct_mask) * p.B);
+#pragma unroll
+      for (int j = 0; j < U; j++) h = aes_fixed(te, xor4(h, v[j]));
+    }
+    for (; k < end; k++) h = aes_fixed(te, xor4(h, __ldcg(base + (size_t)(k & p.ct_mask) * p.B)));
+    __syncwarp();
+    if (lane == 0) st_release64(p.chain_progress + cw, end);
+  }
+  if (active) p.commit[first + lane] = h;
+}
 
 // MODE 0 = garble (labels are label0, ciphertexts produced), MODE 1 = evaluate.
 template <int G, int HASH, int MODE>
 __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
   extern __shared__ uint4 smem[];
-  uint32_t* te = reinterpret_cast<uint32_t*>(smem);  // 1024 words
+  uint32_t* te = reinterpret_cast<uint32_t*>(smem);  // 64 KB table block
+  constexpr uint32_t TE_Q = AES_TABLE_BYTES / 16;    // in uint4 units
   const uint32_t NT = p.worker_threads;
+  const uint32_t n_workers = p.n_workers;
+  load_tables(te, threadIdx.x, blockDim.x);
+  __syncthreads();
+
+  if (threadIdx.x >= n_workers * NT) {
+    // ---- chain role
+    if (MODE == 0) {
+      const uint32_t k = (threadIdx.x - n_workers * NT) >> 5;
+      chain_warp(p, te, blockIdx.x * p.n_chain_warps + k);
+    }
+    return;
+  }
+
   const uint32_t worker = threadIdx.x / NT;
   const uint32_t wt = threadIdx.x - worker * NT;
-  const uint32_t n_workers = blockDim.x / NT;
   const uint32_t bar_id = worker + 1;
   // per-worker regions
   const uint32_t lab_words = p.slots_per_worker * G;  // uint4 entries
-  uint4* lab = smem + 256 + worker * lab_words;
-  uint8_t* sval = reinterpret_cast<uint8_t*>(smem + 256 + n_workers * lab_words) + worker * lab_words;
-  volatile uint32_t* ctrl =
-      reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint8_t*>(smem + 256 + n_workers * lab_words) +
-                                           (MODE == 1 ? n_workers * lab_words : 0)) + worker;
-
-  load_tables(te, threadIdx.x, blockDim.x);
-  __syncthreads();
+  uint4* lab = smem + TE_Q + worker * lab_words;
+  uint8_t* tail = reinterpret_cast<uint8_t*>(smem + TE_Q + n_workers * lab_words);
+  uint8_t* sval = tail + worker * lab_words;
+  volatile uint32_t* ctrl = reinterpret_cast<volatile uint32_t*>(tail + (MODE == 1 ? n_workers * lab_words : 0)) + worker;
 
   const uint32_t inst = wt % G;  // NT % G == 0, so a thread always serves the same instance lane
   const uint32_t n_items = p.n_calls * p.n_groups;
@@ -102,10 +160,17 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
     const DevCallD call = p.calls[call_i];
     const DevTaskD task = p.tasks[call.task];
 
-    // ---- wait for producer calls of this instance group
+    // ---- wait for producer calls of this instance group, and for ring space
     for (uint32_t d = wt; d < call.n_deps; d += NT) {
       const uint32_t* f = p.flags + (size_t)p.deps[call.dep_off + d] * p.n_groups + grp;
       while (ld_acquire(f) != p.epoch) __nanosleep(64);
+    }
+    if (MODE == 0 && p.ct_ring && wt == NT - 1) {
+      const unsigned long long need = call.ct_base + task.n_ct;
+      if (need > p.ct_ring) {
+        const unsigned long long* pr = p.chain_progress + (grp * G) / 32u;
+        while (ld_acquire64(pr) + p.ct_ring < need) __nanosleep(256);
+      }
     }
     named_bar(bar_id, NT);
 
@@ -160,7 +225,8 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
             const unsigned long long gid = call.gid_base + graw.z;
             uint4 ct;
             lc = garble_nonfree<HASH>(te, type, la, lb, delta, gid, ct);
-            if (p.write_ct) __stcs(p.ct + (size_t)(call.ct_base + graw.w) * p.B + grp * G + inst, ct);
+            if (p.write_ct)
+              __stcg(p.ct + (size_t)((call.ct_base + graw.w) & p.ct_mask) * p.B + grp * G + inst, ct);
           }
         } else {
           const uint32_t va = sval[sa * G + inst], vb = sval[sb * G + inst];
@@ -258,12 +324,13 @@ __global__ void k_seed_expand(const unsigned long long* seeds, uint32_t B, uint3
   }
 }
 
-// ---- serial ciphertext commitment: h <- AES_K(h ^ ct_k), one lane per instance
-// (src/ciphertext_hasher.rs:23-29).  Inherently sequential per instance; lanes = instances.
+// ---- stand-alone serial commitment (evaluator side: FileSource hashes what it consumed,
+// src/circuit/ciphertext_source.rs:35-106).  One lane per instance.
 template <int DUMMY>
 __global__ void __launch_bounds__(32) k_chain(const uint4* __restrict__ ct, unsigned long long n_ct, uint32_t B,
                                               uint4* __restrict__ out) {
-  __shared__ uint32_t te[1024];
+  extern __shared__ uint4 smem[];
+  uint32_t* te = reinterpret_cast<uint32_t*>(smem);
   load_tables(te, threadIdx.x, blockDim.x);
   __syncthreads();
   const uint32_t instance = blockIdx.x * blockDim.x + threadIdx.x;
@@ -328,26 +395,29 @@ __global__ void k_ct_insert(uint4* ct, uint32_t B, uint32_t instance, unsigned l
 // commit(label) = AES_K(label)
 template <int DUMMY>
 __global__ void k_commit_labels(const uint4* in, unsigned long long n, uint4* out) {
-  __shared__ uint32_t te[1024];
+  extern __shared__ uint4 smem[];
+  uint32_t* te = reinterpret_cast<uint32_t*>(smem);
   load_tables(te, threadIdx.x, blockDim.x);
   __syncthreads();
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = aes_fixed(te, in[i]);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = aes_fixed(te, in[i]);
 }
 // H(x_i, gid_i) for the primitive parity tests
 template <int HASH>
 __global__ void k_hash_blocks(const uint4* x, const unsigned long long* gid, unsigned long long n, uint4* out) {
-  __shared__ uint32_t te[1024];
+  extern __shared__ uint4 smem[];
+  uint32_t* te = reinterpret_cast<uint32_t*>(smem);
   load_tables(te, threadIdx.x, blockDim.x);
   __syncthreads();
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = hash1<HASH>(te, x[i], gid[i]);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = hash1<HASH>(te, x[i], gid[i]);
 }
 // register-resident hash throughput probe (the integer-ALU roof): each thread chains
 // `per_thread` two-block hashes, like a stream of AND gates with no memory traffic.
 template <int HASH>
-__global__ void __launch_bounds__(256) k_bench_hash(unsigned long long per_thread, uint4* sink) {
-  __shared__ uint32_t te[1024];
+__global__ void __launch_bounds__(1024, 1) k_bench_hash(unsigned long long per_thread, uint4* sink) {
+  extern __shared__ uint4 smem[];
+  uint32_t* te = reinterpret_cast<uint32_t*>(smem);
   load_tables(te, threadIdx.x, blockDim.x);
   __syncthreads();
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -271,6 +271,8 @@ struct gsv_session {
   uint32_t ct_mode = GSV_CT_COMMIT;
   int sm_count = 0;
   size_t smem_garble = 0, smem_eval = 0;
+  uint32_t n_chain_warps = 0;      // per CTA
+  uint64_t ct_ring = 0, ct_mask = ~0ull;  // ring capacity (0 = whole stream kept) / position mask
   uint32_t epoch = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -285,6 +287,7 @@ struct gsv_session {
   DevBuf<uint4> d_labels, d_delta, d_ct, d_commit, d_io, d_stage;
   DevBuf<uint8_t> d_vals, d_io_bits;
   DevBuf<uint32_t> d_flags, d_ctrl;  // d_ctrl[0] = next_item, [1] = error flag
+  DevBuf<unsigned long long> d_progress;
   DevBuf<unsigned long long> d_seeds;
   bool ct_valid = false;
   ~gsv_session() {
@@ -312,6 +315,8 @@ void upload_program(gsv_session* s) {
     d.n_slots = t.n_slots;
     d.in_slot_off = (uint32_t)in_slot.size();
     d.out_slot_off = (uint32_t)out_slot.size();
+    d.n_ct = (uint32_t)t.n_ct;
+    d.pad0 = d.pad1 = d.pad2 = 0;
     for (const gsv::DevGate& dg : t.gates) {
       uint4 v;
       memcpy(&v, &dg, 16);
@@ -373,6 +378,12 @@ EngineParams make_params(gsv_session* s) {
   p.flags = s->d_flags.p;
   p.next_item = s->d_ctrl.p;
   p.error_flag = s->d_ctrl.p + 1;
+  p.chain_progress = s->d_progress.p;
+  p.commit = s->d_commit.p;
+  p.ct_mask = s->ct_mask;
+  p.ct_ring = s->ct_ring;
+  p.n_workers = s->n_workers;
+  p.n_chain_warps = 0;
   p.n_calls = (uint32_t)s->prog->prog.calls.size();
   p.n_groups = s->n_groups;
   p.n_global_slots = s->prog->prog.n_global_slots;
@@ -386,7 +397,7 @@ EngineParams make_params(gsv_session* s) {
 template <int MODE>
 void launch_engine(gsv_session* s, int hasher, const EngineParams& p) {
   const size_t smem = MODE == 0 ? s->smem_garble : s->smem_eval;
-  dim3 grid(s->sm_count), block(s->n_workers * s->NT);
+  dim3 grid(s->sm_count), block(s->n_workers * s->NT + 32 * p.n_chain_warps);
 #define GSV_LAUNCH(GG, HH)                                                                              \
   do {                                                                                                  \
     CUDA_TRY(cudaFuncSetAttribute(k_engine<GG, HH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
@@ -437,11 +448,14 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
     s->NT = opt->worker_threads ? opt->worker_threads : 256;
     if (s->NT != 64 && s->NT != 128 && s->NT != 256 && s->NT != 512 && s->NT != 1024)
       throw std::runtime_error("worker_threads must be 64/128/256/512/1024");
-    uint32_t n_workers = 1024 / s->NT;
+    uint32_t n_chain = (s->ct_mode != GSV_CT_NONE) ? ((s->B + 31) / 32 + s->sm_count - 1) / s->sm_count : 0;
+    if (n_chain > 8) throw std::runtime_error("too many instances for one GPU (chain warps)");
+    uint32_t n_workers = (1024 - 32 * n_chain) / s->NT;
+    if (n_workers == 0) throw std::runtime_error("worker_threads too large");
     // largest G (power of two dividing B, <= 8) whose label working set fits next to the tables
     auto smem_for = [&](uint32_t G, uint32_t nw, bool eval) {
       size_t lab = (size_t)slots * G;
-      return (size_t)4096 + nw * lab * 16 + (eval ? nw * lab : 0) + nw * 4 + 16;
+      return (size_t)AES_TABLE_BYTES + nw * lab * 16 + (eval ? nw * lab : 0) + nw * 4 + 16;
     };
     uint32_t G = opt->group;
     if (G == 0) {
@@ -450,11 +464,12 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
     }
     if (G != 1 && G != 2 && G != 4 && G != 8) throw std::runtime_error("group must be 1/2/4/8");
     if (s->B % G) throw std::runtime_error("n_instances must be a multiple of group");
-    while (n_workers > 1 && smem_for(G, n_workers, true) > smem_max) n_workers >>= 1;
+    while (n_workers > 1 && smem_for(G, n_workers, true) > smem_max) n_workers--;
     if (smem_for(G, n_workers, true) > smem_max)
       throw std::runtime_error("task working set does not fit shared memory; lower group or max_task_slots");
     s->G = G;
     s->n_workers = n_workers;
+    s->n_chain_warps = n_chain;
     s->n_groups = s->B / G;
     s->smem_garble = smem_for(G, n_workers, false);
     s->smem_eval = smem_for(G, n_workers, true);
@@ -468,8 +483,32 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
     s->d_flags.alloc((size_t)g.calls.size() * s->n_groups + 1);
     CUDA_TRY(cudaMemset(s->d_flags.p, 0, s->d_flags.n * 4));
     s->d_ctrl.alloc(4);
+    s->d_progress.alloc((size_t)s->sm_count * std::max<uint32_t>(n_chain, 1));
     CUDA_TRY(cudaMemset(s->d_ctrl.p, 0, 16));
-    if (s->ct_mode != GSV_CT_NONE) s->d_ct.alloc((size_t)std::max<uint64_t>(g.total_ct, 1) * s->B);
+    if (s->ct_mode != GSV_CT_NONE) {
+      // GSV_CT_KEEP: the whole interleaved stream stays resident.  GSV_CT_COMMIT: a power-of-two
+      // ring the chain warps drain (back-pressure through chain_progress).
+      uint64_t total = std::max<uint64_t>(g.total_ct, 1);
+      uint64_t max_task_ct = 1;
+      for (const auto& t : g.tasks) max_task_ct = std::max<uint64_t>(max_task_ct, t.n_ct);
+      size_t free_b = 0, total_b = 0;
+      CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+      const uint64_t budget = std::min<uint64_t>((uint64_t)(free_b * 0.6), 48ull << 30);
+      uint64_t ring = 1;
+      while (ring * 2 * s->B * 16 <= budget) ring *= 2;
+      if (opt->ct_ring_log2) ring = std::min<uint64_t>(ring, 1ull << opt->ct_ring_log2);
+      if (s->ct_mode == GSV_CT_KEEP || ring >= total) {
+        if (total * s->B * 16 > (uint64_t)(free_b * 0.9)) throw std::runtime_error("ciphertext stream does not fit in HBM; use GSV_CT_COMMIT");
+        s->ct_ring = 0;
+        s->ct_mask = ~0ull;
+        s->d_ct.alloc((size_t)total * s->B);
+      } else {
+        if (ring < 2 * max_task_ct) throw std::runtime_error("ciphertext ring smaller than two tasks; fewer instances needed");
+        s->ct_ring = ring;
+        s->ct_mask = ring - 1;
+        s->d_ct.alloc((size_t)ring * s->B);
+      }
+    }
     return s.release();
   } catch (const std::exception& e) {
     fail(std::string(e.what()).find("no CUDA device") != std::string::npos ? GSV_ERR_NO_DEVICE : GSV_ERR_CUDA, e.what());
@@ -504,14 +543,12 @@ int gsv_garble_batch(gsv_session* s, int hasher, const uint64_t* seeds, gsv_garb
     CUDA_TRY(cudaEventRecord(s->ev[1], s->stream));
     EngineParams p = make_params(s);
     p.write_ct = (s->ct_mode != GSV_CT_NONE) ? 1u : 0u;
+    p.n_chain_warps = s->n_chain_warps;
+    if (s->n_chain_warps) CUDA_TRY(cudaMemsetAsync(s->d_progress.p, 0, s->d_progress.n * 8, s->stream));
     launch_engine<0>(s, hasher, p);
     launches++;
     CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
-    if (s->ct_mode != GSV_CT_NONE) {
-      k_chain<0><<<(B + 31) / 32, 32, 0, s->stream>>>(s->d_ct.p, g.total_ct, B, s->d_commit.p);
-      CUDA_TRY(cudaGetLastError());
-      launches++;
-    }
+    // the chain commitment is folded inside k_engine by the chain warps (no separate launch)
     CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
     // ---- results
     if (res->delta) CUDA_TRY(cudaMemcpyAsync(res->delta, s->d_delta.p, (size_t)B * 16, cudaMemcpyDeviceToHost, s->stream));
@@ -557,7 +594,7 @@ int gsv_session_read_ciphertexts(gsv_session* s, uint32_t instance, uint64_t fir
   try {
     CUDA_TRY(cudaSetDevice(s->device));
     const gsv::Program& g = s->prog->prog;
-    if (!s->ct_valid || s->ct_mode == GSV_CT_NONE) return fail(GSV_ERR_INVALID, "no ciphertext stream kept");
+    if (!s->ct_valid || s->ct_mode == GSV_CT_NONE || s->ct_ring) return fail(GSV_ERR_INVALID, "no ciphertext stream kept (use GSV_CT_KEEP)");
     if (instance >= s->B || first + count > g.total_ct) return fail(GSV_ERR_INVALID, "range out of bounds");
     if (count == 0) return GSV_OK;
     if (s->d_stage.n < count) s->d_stage.alloc(count);
@@ -595,7 +632,7 @@ int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io) {
         }
       }
       ct_avail = io->ct_stream_len;
-    } else if (!s->ct_valid) {
+    } else if (!s->ct_valid || s->ct_ring) {
       return fail(GSV_ERR_INVALID, "no ciphertext stream in the session (garble with GSV_CT_KEEP first)");
     }
     if (s->d_vals.n < (size_t)B * g.n_global_slots) s->d_vals.alloc((size_t)B * g.n_global_slots);
@@ -630,7 +667,8 @@ int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io) {
     CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
     // the evaluator's own chain hash over what it consumed (FileSource hashes while reading)
     const uint64_t used = std::min<uint64_t>(ct_avail, g.total_ct);
-    k_chain<0><<<(B + 31) / 32, 32, 0, s->stream>>>(s->d_ct.p, used, B, s->d_commit.p);
+    CUDA_TRY(cudaFuncSetAttribute(k_chain<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
+    k_chain<0><<<(B + 31) / 32, 32, AES_TABLE_BYTES, s->stream>>>(s->d_ct.p, used, B, s->d_commit.p);
     CUDA_TRY(cudaGetLastError());
     launches++;
     CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
@@ -669,7 +707,8 @@ int gsv_commit_labels(int device, const uint8_t* labels, uint64_t n, uint8_t* ou
     d_in.alloc(n);
     d_out.alloc(n);
     CUDA_TRY(cudaMemcpy(d_in.p, labels, n * 16, cudaMemcpyHostToDevice));
-    k_commit_labels<0><<<(unsigned)((n + 255) / 256), 256>>>(d_in.p, n, d_out.p);
+    CUDA_TRY(cudaFuncSetAttribute(k_commit_labels<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
+    k_commit_labels<0><<<(unsigned)std::min<uint64_t>((n + 255) / 256, 296), 256, AES_TABLE_BYTES>>>(d_in.p, n, d_out.p);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(out, d_out.p, n * 16, cudaMemcpyDeviceToHost));
     return GSV_OK;
@@ -690,8 +729,11 @@ int gsv_hash_blocks(int device, int hasher, const uint8_t* x, const uint64_t* gi
     d_gid.alloc(n);
     CUDA_TRY(cudaMemcpy(d_in.p, x, n * 16, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_gid.p, gid, n * 8, cudaMemcpyHostToDevice));
-    if (hasher == GSV_HASH_AES) k_hash_blocks<HASH_AES><<<(unsigned)((n + 255) / 256), 256>>>(d_in.p, d_gid.p, n, d_out.p);
-    else k_hash_blocks<HASH_BLAKE3><<<(unsigned)((n + 255) / 256), 256>>>(d_in.p, d_gid.p, n, d_out.p);
+    const unsigned hb_grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 296);
+    CUDA_TRY(cudaFuncSetAttribute(k_hash_blocks<HASH_AES>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_hash_blocks<HASH_BLAKE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
+    if (hasher == GSV_HASH_AES) k_hash_blocks<HASH_AES><<<hb_grid, 256, AES_TABLE_BYTES>>>(d_in.p, d_gid.p, n, d_out.p);
+    else k_hash_blocks<HASH_BLAKE3><<<hb_grid, 256, AES_TABLE_BYTES>>>(d_in.p, d_gid.p, n, d_out.p);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(out, d_out.p, n * 16, cudaMemcpyDeviceToHost));
     return GSV_OK;
@@ -706,7 +748,9 @@ int gsv_bench_hash(int device, int hasher, uint64_t n_blocks, int iters, double*
     ensure_device(device);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    const unsigned grid = (unsigned)prop.multiProcessorCount * 8, block = 256;
+    const unsigned grid = (unsigned)prop.multiProcessorCount * 2, block = 512;
+    CUDA_TRY(cudaFuncSetAttribute(k_bench_hash<HASH_AES>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_bench_hash<HASH_BLAKE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
     const unsigned long long threads = (unsigned long long)grid * block;
     unsigned long long per_thread = std::max<unsigned long long>(1, n_blocks / (2 * threads));
     DevBuf<uint4> sink;
@@ -717,8 +761,8 @@ int gsv_bench_hash(int device, int hasher, uint64_t n_blocks, int iters, double*
     float best = 1e30f;
     for (int it = 0; it < std::max(iters, 1) + 1; it++) {
       CUDA_TRY(cudaEventRecord(e0));
-      if (hasher == GSV_HASH_AES) k_bench_hash<HASH_AES><<<grid, block>>>(per_thread, sink.p);
-      else k_bench_hash<HASH_BLAKE3><<<grid, block>>>(per_thread, sink.p);
+      if (hasher == GSV_HASH_AES) k_bench_hash<HASH_AES><<<grid, block, AES_TABLE_BYTES>>>(per_thread, sink.p);
+      else k_bench_hash<HASH_BLAKE3><<<grid, block, AES_TABLE_BYTES>>>(per_thread, sink.p);
       CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaEventRecord(e1));
       CUDA_TRY(cudaEventSynchronize(e1));

@@ -149,6 +149,31 @@ def test_fq12_mul_e2e_batch_properties(gsv, circuit):
     assert np.array_equal(ev.ct_commit, res.ct_commit)
 
 
+def test_commit_ring_backpressure(gsv, orc, circuit):
+    """GSV_CT_COMMIT with a ring far smaller than the stream (2^17 of 5.44 M ciphertexts): the
+    garbling workers must stall on the chain warps' progress and the commitment stay bit-exact."""
+    p, st = circuit("fq12_mul")
+    seeds = [0, 42, 99, 777, 1, 2, 3, 4]
+    sess = gsv.Session(p, len(seeds), group=2, ct_mode=gsv.CT_COMMIT, ct_ring_log2=17)
+    res = sess.garble(seeds, gsv.HASH_AES)
+    for i in (0, 1, 7):
+        ref = st.garble(orc.HASH_AES, seeds[i], want_ct=False)
+        assert bytes(res.ct_commit[i]) == ref["ct_commit"]
+        assert np.array_equal(res.output_label0[i], ref["output_label0"])
+    with pytest.raises(gsv.GsvError):
+        sess.read_ciphertexts(0)  # a ring keeps no stream
+
+
+def test_many_instances_chain_warps(gsv, orc, circuit):
+    """More than 32 instances per SM-resident chain warp set: 96 instances, odd chain-warp fill."""
+    p, st = circuit("fq_mul")
+    B = 96 + 8
+    seeds = list(range(5000, 5000 + B))
+    res = gsv.Session(p, B, group=4, ct_mode=gsv.CT_COMMIT).garble(seeds, gsv.HASH_AES)
+    for i in (0, 31, 32, 95, 96, B - 1):
+        assert bytes(res.ct_commit[i]) == st.garble(orc.HASH_AES, seeds[i], want_ct=False)["ct_commit"]
+
+
 def test_commit_only_mode_matches_keep(gsv, circuit):
     p, _ = circuit("fq_mul")
     seeds = [7, 8, 9, 10]
