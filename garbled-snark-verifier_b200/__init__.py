@@ -66,7 +66,8 @@ class _SessionOptions(C.Structure):
         ("worker_threads", C.c_uint32),
         ("ct_mode", C.c_uint32),
         ("ct_ring_log2", C.c_uint32),
-        ("reserved", C.c_uint32 * 2),
+        ("exec_mode", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 
@@ -240,13 +241,14 @@ class Session:
     """Device state for a batch of instances of one program on one GPU."""
 
     def __init__(self, program: Program, n_instances: int, device: int = 0, group: int = 0,
-                 worker_threads: int = 0, ct_mode: int = CT_KEEP, ct_ring_log2: int = 0):
+                 worker_threads: int = 0, ct_mode: int = CT_KEEP, ct_ring_log2: int = 0,
+                 exec_mode: int = 0):
         lib = load_library()
         self.program = program
         self.n_instances = n_instances
         self.device = device
         self.ct_mode = ct_mode
-        opt = _SessionOptions(device, n_instances, group, worker_threads, ct_mode, ct_ring_log2)
+        opt = _SessionOptions(device, n_instances, group, worker_threads, ct_mode, ct_ring_log2, exec_mode)
         self._h = lib.gsv_session_create(program._h, C.byref(opt))
         if not self._h:
             msg = lib.gsv_last_error().decode()

@@ -25,7 +25,8 @@ namespace gsvdev {
 
 struct DevTaskD {
   uint32_t gate_off, level_off, n_levels, n_in, n_out, n_slots, in_slot_off, out_slot_off;
-  uint32_t n_ct, pad0, pad1, pad2;
+  uint32_t n_ct;
+  uint32_t seq_gate_off, n_seq_gates, n_seq_slots;  // lane-mode (emission order) form
 };
 struct DevCallD {
   uint32_t task, in_off, out_off, dep_off, n_deps, pad;
@@ -58,6 +59,14 @@ struct EngineParams {
   uint32_t worker_threads, n_workers, n_chain_warps;
   uint32_t epoch;
   uint32_t write_ct;          // garble: store ciphertexts
+  uint32_t G;                 // instances per group (32 in lane mode)
+  // lane mode
+  const uint4* seq_gates;
+  const uint16_t* seq_in_slot;
+  const uint16_t* seq_out_slot;
+  uint4* scratch;             // [worker warp][scratch slot][32]
+  uint8_t* scratch_vals;
+  uint32_t scratch_stride;    // scratch slots per worker warp
 };
 
 __device__ __forceinline__ void named_bar(uint32_t id, uint32_t nthreads) {
@@ -86,8 +95,8 @@ __device__ __forceinline__ void chain_warp(const EngineParams& p, const uint32_t
   const uint32_t first = cw * 32u;
   if (first >= p.B) return;
   const uint32_t n_inst = min(32u, p.B - first);
-  const uint32_t G = p.B / p.n_groups;
-  const uint32_t g0 = first / G, ng = n_inst / G;
+  const uint32_t G = p.G;
+  const uint32_t g0 = first / G, ng = (n_inst + G - 1) / G;
   const bool active = lane < n_inst;
   const uint4* base = p.ct + first + (active ? lane : 0u);
   uint4 h = make_uint4(0, 0, 0, 0);
@@ -258,6 +267,164 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
     __threadfence();
     named_bar(bar_id, NT);
     if (wt == 0) st_release(p.flags + (size_t)call_i * p.n_groups + grp, p.epoch);
+  }
+}
+
+// ---- lane mode: one WARP per work item, lane = instance (32 instances of the batch), the task's
+// gates run sequentially in emission order.  Control flow is warp-uniform (every lane executes
+// the same gate), every AES issue does 32 useful blocks, there are no barriers, and label /
+// ciphertext accesses are 512-byte coalesced rows.  Task-internal wires live in a per-warp
+// scratch array in global memory (L1/L2 resident: the active window of an emission-order walk is
+// small) whose slots are recycled by emission-order liveness.  This is the throughput mode for
+// cut-and-choose batches of hundreds to thousands of instances; k_engine (levelised, labels in
+// shared memory) is the latency mode for small batches.
+template <int HASH, int MODE>
+__global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
+  extern __shared__ uint4 smem[];
+  uint32_t* te = reinterpret_cast<uint32_t*>(smem);
+  load_tables(te, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  if (warp >= p.n_workers) {
+    if (MODE == 0) chain_warp(p, te, blockIdx.x * p.n_chain_warps + (warp - p.n_workers));
+    return;
+  }
+  const uint32_t wid = blockIdx.x * p.n_workers + warp;
+  uint4* my = p.scratch + (size_t)wid * p.scratch_stride * 32u + lane;
+  uint8_t* myv = p.scratch_vals + (size_t)wid * p.scratch_stride * 32u + lane;
+  const uint32_t n_items = p.n_calls * p.n_groups;
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
+
+  for (;;) {
+    uint32_t item = 0;
+    if (lane == 0) item = atomicAdd(p.next_item, 1u);
+    item = __shfl_sync(FULL, item, 0);
+    if (item >= n_items) break;
+    const uint32_t call_i = item / p.n_groups;
+    const uint32_t grp = item - call_i * p.n_groups;
+    const DevCallD call = p.calls[call_i];
+    const DevTaskD task = p.tasks[call.task];
+    const uint32_t instance = grp * 32u + lane;
+    const bool act = instance < p.B;
+
+    for (uint32_t d = lane; d < call.n_deps; d += 32) {
+      const uint32_t* f = p.flags + (size_t)p.deps[call.dep_off + d] * p.n_groups + grp;
+      while (ld_acquire(f) != p.epoch) __nanosleep(100);
+    }
+    if (MODE == 0 && p.ct_ring && lane == 31) {
+      const unsigned long long need = call.ct_base + task.n_ct;
+      if (need > p.ct_ring) {
+        const unsigned long long* pr = p.chain_progress + grp;  // chain warp == instance group
+        while (ld_acquire64(pr) + p.ct_ring < need) __nanosleep(256);
+      }
+    }
+    __syncwarp();
+
+    // ---- gather: constants + inputs -> scratch (rows of 32 labels, 512 B each)
+    const size_t gbase = (size_t)grp * p.n_global_slots;
+    const uint4* glab = p.labels + gbase * 32u + lane;
+    const uint8_t* gval = p.vals + gbase * 32u + lane;
+    uint4 delta = make_uint4(0, 0, 0, 0);
+    if (MODE == 0) delta = p.delta[instance];
+    my[0] = __ldcg(glab);
+    my[32] = __ldcg(glab + 32);
+    if (MODE == 1) { myv[0] = 0; myv[32] = 1; }
+    for (uint32_t base = 0; base < task.n_in; base += 32) {
+      const uint32_t cnt = min(32u, task.n_in - base);
+      uint32_t ms = 0xFFFFu, mg = 0;
+      if (lane < cnt) {
+        ms = p.seq_in_slot[task.in_slot_off + base + lane];
+        mg = p.call_slots[call.in_off + base + lane];
+      }
+      for (uint32_t j0 = 0; j0 < cnt; j0 += 8) {
+        uint4 v[8];
+        uint8_t vb[8];
+        uint32_t s[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          s[j] = __shfl_sync(FULL, ms, (j0 + j) & 31);
+          const uint32_t gs = __shfl_sync(FULL, mg, (j0 + j) & 31);
+          if (j0 + j < cnt && s[j] != 0xFFFFu) {
+            v[j] = __ldcg(glab + (size_t)gs * 32u);
+            if (MODE == 1) vb[j] = __ldcg(gval + (size_t)gs * 32u);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          if (j0 + j < cnt && s[j] != 0xFFFFu) {
+            my[s[j] * 32u] = v[j];
+            if (MODE == 1) myv[s[j] * 32u] = vb[j];
+          }
+      }
+    }
+
+    // ---- the task's gates, emission order, 32 records per coalesced fetch
+    const uint4* gates = p.seq_gates + task.seq_gate_off;
+    const uint32_t n = task.n_seq_gates;
+    uint4 rec_next = make_uint4(0, 0, 0, 0);
+    if (lane < n) rec_next = __ldg(gates + lane);
+    for (uint32_t g0 = 0; g0 < n; g0 += 32) {
+      const uint4 rec = rec_next;
+      if (g0 + 32 + lane < n) rec_next = __ldg(gates + g0 + 32 + lane);
+      const uint32_t cnt = min(32u, n - g0);
+      for (uint32_t j = 0; j < cnt; j++) {
+        const uint32_t rx = __shfl_sync(FULL, rec.x, j), ry = __shfl_sync(FULL, rec.y, j);
+        const uint32_t sa = rx & 0xFFFFu, sb = rx >> 16, sc = ry & 0xFFFFu;
+        const uint32_t type = (ry >> 16) & 0xFFu;
+        const uint4 la = my[sa * 32u];
+        const uint4 lb = my[sb * 32u];
+        uint4 lc;
+        if (MODE == 0) {
+          if (type >= 8) {
+            lc = (type == 10) ? xor4(la, delta) : xor4(la, lb);
+            if (type == 9) lc = xor4(lc, delta);
+          } else {
+            const unsigned long long gid = call.gid_base + __shfl_sync(FULL, rec.z, j);
+            const unsigned long long cti = call.ct_base + __shfl_sync(FULL, rec.w, j);
+            uint4 ct;
+            lc = garble_nonfree<HASH>(te, type, la, lb, delta, gid, ct);
+            if (p.write_ct && act) __stcg(p.ct + (size_t)(cti & p.ct_mask) * p.B + instance, ct);
+          }
+        } else {
+          const uint32_t va = myv[sa * 32u], vb = myv[sb * 32u];
+          if (type >= 8) {
+            lc = (type == 10) ? la : xor4(la, lb);
+          } else {
+            const unsigned long long gid = call.gid_base + __shfl_sync(FULL, rec.z, j);
+            const unsigned long long cti = call.ct_base + __shfl_sync(FULL, rec.w, j);
+            uint4 ct = make_uint4(0, 0, 0, 0);
+            if (cti < p.ct_capacity) {
+              if (act) ct = __ldcs(p.ct + (size_t)cti * p.B + instance);
+            } else if (lane == 0) {
+              *p.error_flag = 1u;
+            }
+            lc = degarble_nonfree<HASH>(te, type, ct, la, va, lb, gid);
+          }
+          myv[sc * 32u] = (uint8_t)gate_value(type, va, vb);
+        }
+        my[sc * 32u] = lc;
+      }
+    }
+
+    // ---- scatter produced labels to the instance group's global slots
+    uint4* wlab = p.labels + gbase * 32u + lane;
+    uint8_t* wval = p.vals + gbase * 32u + lane;
+    for (uint32_t base = 0; base < task.n_out; base += 32) {
+      const uint32_t cnt = min(32u, task.n_out - base);
+      uint32_t ms = 0, mg = 0;
+      if (lane < cnt) {
+        ms = p.seq_out_slot[task.out_slot_off + base + lane];
+        mg = p.call_slots[call.out_off + base + lane];
+      }
+      for (uint32_t j = 0; j < cnt; j++) {
+        const uint32_t s = __shfl_sync(FULL, ms, j), gs = __shfl_sync(FULL, mg, j);
+        wlab[(size_t)gs * 32u] = my[s * 32u];
+        if (MODE == 1) wval[(size_t)gs * 32u] = myv[s * 32u];
+      }
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release(p.flags + (size_t)call_i * p.n_groups + grp, p.epoch);
   }
 }
 

@@ -289,6 +289,13 @@ struct gsv_session {
   DevBuf<uint32_t> d_flags, d_ctrl;  // d_ctrl[0] = next_item, [1] = error flag
   DevBuf<unsigned long long> d_progress;
   DevBuf<unsigned long long> d_seeds;
+  // lane mode (one warp = 32 instances, emission-order tasks)
+  bool lane_mode = false;
+  uint32_t B_pad = 0;            // B rounded up to whole groups
+  uint32_t scratch_stride = 0;   // scratch slots per worker warp
+  DevBuf<uint4> d_seq_gates, d_scratch;
+  DevBuf<uint16_t> d_seq_in_slot, d_seq_out_slot;
+  DevBuf<uint8_t> d_scratch_vals;
   bool ct_valid = false;
   ~gsv_session() {
     if (stream) cudaStreamDestroy(stream);
@@ -304,6 +311,8 @@ void upload_program(gsv_session* s) {
   std::vector<uint4> gates;
   std::vector<uint32_t> level_off;
   std::vector<uint16_t> in_slot, out_slot;
+  std::vector<uint4> seq_gates;
+  std::vector<uint16_t> seq_in_slot, seq_out_slot;
   std::vector<DevTaskD> tasks;
   for (const gsv::Task& t : g.tasks) {
     DevTaskD d;
@@ -316,12 +325,21 @@ void upload_program(gsv_session* s) {
     d.in_slot_off = (uint32_t)in_slot.size();
     d.out_slot_off = (uint32_t)out_slot.size();
     d.n_ct = (uint32_t)t.n_ct;
-    d.pad0 = d.pad1 = d.pad2 = 0;
+    d.seq_gate_off = (uint32_t)seq_gates.size();
+    d.n_seq_gates = (uint32_t)t.seq_gates.size();
+    d.n_seq_slots = t.n_seq_slots;
     for (const gsv::DevGate& dg : t.gates) {
       uint4 v;
       memcpy(&v, &dg, 16);
       gates.push_back(v);
     }
+    for (const gsv::DevGate& dg : t.seq_gates) {
+      uint4 v;
+      memcpy(&v, &dg, 16);
+      seq_gates.push_back(v);
+    }
+    seq_in_slot.insert(seq_in_slot.end(), t.seq_in_slot.begin(), t.seq_in_slot.end());
+    seq_out_slot.insert(seq_out_slot.end(), t.seq_out_slot.begin(), t.seq_out_slot.end());
     level_off.insert(level_off.end(), t.level_off.begin(), t.level_off.end());
     if (t.level_off.empty()) level_off.push_back(0);
     in_slot.insert(in_slot.end(), t.in_slot.begin(), t.in_slot.end());
@@ -345,6 +363,16 @@ void upload_program(gsv_session* s) {
   if (gates.empty()) gates.push_back(make_uint4(0, 0, 0, 0));
   if (in_slot.empty()) in_slot.push_back(0);
   if (out_slot.empty()) out_slot.push_back(0);
+  if (s->lane_mode) {
+    // lane mode only needs the emission-order form
+    if (seq_gates.empty()) seq_gates.push_back(make_uint4(0, 0, 0, 0));
+    if (seq_in_slot.empty()) seq_in_slot.push_back(0);
+    if (seq_out_slot.empty()) seq_out_slot.push_back(0);
+    s->d_seq_gates.upload(seq_gates);
+    s->d_seq_in_slot.upload(seq_in_slot);
+    s->d_seq_out_slot.upload(seq_out_slot);
+    gates.assign(1, make_uint4(0, 0, 0, 0));
+  }
   s->d_gates.upload(gates);
   s->d_level_off.upload(level_off);
   s->d_in_slot.upload(in_slot);
@@ -391,11 +419,32 @@ EngineParams make_params(gsv_session* s) {
   p.slots_per_worker = s->slots_per_worker;
   p.worker_threads = s->NT;
   p.epoch = s->epoch;
+  p.G = s->G;
+  p.seq_gates = s->d_seq_gates.p;
+  p.seq_in_slot = s->d_seq_in_slot.p;
+  p.seq_out_slot = s->d_seq_out_slot.p;
+  p.scratch = s->d_scratch.p;
+  p.scratch_vals = s->d_scratch_vals.p;
+  p.scratch_stride = s->scratch_stride;
   return p;
 }
 
 template <int MODE>
 void launch_engine(gsv_session* s, int hasher, const EngineParams& p) {
+  if (s->lane_mode) {
+    dim3 lgrid(s->sm_count), lblock(32 * (s->n_workers + p.n_chain_warps));
+    if (hasher == GSV_HASH_AES) {
+      CUDA_TRY(cudaFuncSetAttribute(k_lane<HASH_AES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
+      k_lane<HASH_AES, MODE><<<lgrid, lblock, AES_TABLE_BYTES, s->stream>>>(p);
+    } else if (hasher == GSV_HASH_BLAKE3) {
+      CUDA_TRY(cudaFuncSetAttribute(k_lane<HASH_BLAKE3, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
+      k_lane<HASH_BLAKE3, MODE><<<lgrid, lblock, AES_TABLE_BYTES, s->stream>>>(p);
+    } else {
+      throw std::runtime_error("unknown hasher");
+    }
+    CUDA_TRY(cudaGetLastError());
+    return;
+  }
   const size_t smem = MODE == 0 ? s->smem_garble : s->smem_eval;
   dim3 grid(s->sm_count), block(s->n_workers * s->NT + 32 * p.n_chain_warps);
 #define GSV_LAUNCH(GG, HH)                                                                              \
@@ -457,27 +506,47 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
       size_t lab = (size_t)slots * G;
       return (size_t)AES_TABLE_BYTES + nw * lab * 16 + (eval ? nw * lab : 0) + nw * 4 + 16;
     };
+    // execution mode: lane mode (warp = 32 instances) for batches that fill warps, the levelised
+    // shared-memory mode otherwise
+    if (opt->exec_mode > 2) throw std::runtime_error("exec_mode must be 0 (auto), 1 (levelised) or 2 (lane)");
+    s->lane_mode = opt->exec_mode == 2 || (opt->exec_mode == 0 && opt->group == 0 && s->B >= 128);
     uint32_t G = opt->group;
-    if (G == 0) {
-      G = 2;
-      while (G > 1 && (s->B % G != 0)) G >>= 1;
+    if (s->lane_mode) {
+      G = 32;
+      s->NT = 32;
+      n_workers = 32 - n_chain;
+      s->B_pad = (s->B + 31) / 32 * 32;
+      s->n_groups = s->B_pad / 32;
+      s->scratch_stride = std::max<uint32_t>(g.max_task_seq_slots, 4);
+    } else {
+      if (G == 0) {
+        G = 2;
+        while (G > 1 && (s->B % G != 0)) G >>= 1;
+      }
+      if (G != 1 && G != 2 && G != 4 && G != 8) throw std::runtime_error("group must be 1/2/4/8");
+      if (s->B % G) throw std::runtime_error("n_instances must be a multiple of group");
+      while (n_workers > 1 && smem_for(G, n_workers, true) > smem_max) n_workers--;
+      if (smem_for(G, n_workers, true) > smem_max)
+        throw std::runtime_error("task working set does not fit shared memory; lower group or max_task_slots");
+      s->B_pad = s->B;
+      s->n_groups = s->B / G;
+      s->smem_garble = smem_for(G, n_workers, false);
+      s->smem_eval = smem_for(G, n_workers, true);
     }
-    if (G != 1 && G != 2 && G != 4 && G != 8) throw std::runtime_error("group must be 1/2/4/8");
-    if (s->B % G) throw std::runtime_error("n_instances must be a multiple of group");
-    while (n_workers > 1 && smem_for(G, n_workers, true) > smem_max) n_workers--;
-    if (smem_for(G, n_workers, true) > smem_max)
-      throw std::runtime_error("task working set does not fit shared memory; lower group or max_task_slots");
     s->G = G;
     s->n_workers = n_workers;
     s->n_chain_warps = n_chain;
-    s->n_groups = s->B / G;
-    s->smem_garble = smem_for(G, n_workers, false);
-    s->smem_eval = smem_for(G, n_workers, true);
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto& e : s->ev) CUDA_TRY(cudaEventCreate(&e));
     upload_program(s.get());
-    s->d_labels.alloc((size_t)s->B * g.n_global_slots);
-    s->d_delta.alloc(s->B);
+    s->d_labels.alloc((size_t)s->B_pad * g.n_global_slots);
+    s->d_delta.alloc(s->B_pad);
+    CUDA_TRY(cudaMemset(s->d_delta.p, 0, (size_t)s->B_pad * 16));
+    if (s->lane_mode) {
+      const size_t n = (size_t)s->sm_count * n_workers * s->scratch_stride * 32;
+      s->d_scratch.alloc(n);
+      s->d_scratch_vals.alloc(n);
+    }
     s->d_commit.alloc(s->B);
     s->d_seeds.alloc(s->B);
     s->d_flags.alloc((size_t)g.calls.size() * s->n_groups + 1);
@@ -635,7 +704,7 @@ int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io) {
     } else if (!s->ct_valid || s->ct_ring) {
       return fail(GSV_ERR_INVALID, "no ciphertext stream in the session (garble with GSV_CT_KEEP first)");
     }
-    if (s->d_vals.n < (size_t)B * g.n_global_slots) s->d_vals.alloc((size_t)B * g.n_global_slots);
+    if (s->d_vals.n < (size_t)s->B_pad * g.n_global_slots) s->d_vals.alloc((size_t)s->B_pad * g.n_global_slots);
     // inputs -> device
     DevBuf<uint4> d_true, d_false, d_in;
     DevBuf<uint8_t> d_bits;

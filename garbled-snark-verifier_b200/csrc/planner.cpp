@@ -145,6 +145,65 @@ Task compile_flat(const FlatStream& fs, const std::string& key, const PlanOption
     t.out_slot.push_back((uint16_t)slot[o]);
   }
   t.n_out = (uint32_t)t.out_pos.size();
+
+  // ---- lane-mode form: emission order, slots freed right after the last read (LIFO reuse)
+  {
+    std::vector<uint64_t> last(nw, 0);  // 1 + index of the last live gate reading the wire
+    const uint64_t NEVER = ~0ull;
+    for (size_t g = 0; g < ng; g++) {
+      if (fs.c[g] == WIRE_DEAD) continue;
+      last[fs.a[g]] = g + 1;
+      last[fs.b[g]] = g + 1;
+    }
+    for (size_t j = 0; j < fs.outputs.size(); j++) {
+      uint32_t o = fs.outputs[j];
+      if (o != WIRE_DEAD && o >= first_def) last[o] = NEVER;
+    }
+    std::vector<uint32_t> sl(nw, UNSET);
+    sl[0] = 0;
+    sl[1] = 1;
+    uint32_t next = 2;
+    std::vector<uint32_t> freed;
+    t.seq_in_slot.assign(fs.n_inputs, 0xFFFF);
+    for (uint32_t i = 0; i < fs.n_inputs; i++) {
+      uint32_t w = WIRE_MIN + i;
+      if (!last[w]) continue;
+      sl[w] = next++;
+      t.seq_in_slot[i] = (uint16_t)sl[w];
+    }
+    t.seq_gates.reserve(n_live);
+    for (size_t g = 0; g < ng; g++) {
+      if (fs.c[g] == WIRE_DEAD) continue;
+      const uint32_t a = fs.a[g], b = fs.b[g], c = fs.c[g];
+      DevGate dg;
+      dg.a = (uint16_t)sl[a];
+      dg.b = (uint16_t)sl[b];
+      if (a >= WIRE_MIN && last[a] == g + 1) freed.push_back(sl[a]);
+      if (b >= WIRE_MIN && b != a && last[b] == g + 1) freed.push_back(sl[b]);
+      uint32_t s;
+      if (!freed.empty()) {
+        s = freed.back();
+        freed.pop_back();
+      } else {
+        s = next++;
+      }
+      if (next > 0xFFFF) throw std::length_error("task needs more than 65535 scratch slots: " + key);
+      sl[c] = s;
+      if (last[c] == 0) freed.push_back(s);  // written, never read, not an output
+      dg.c = (uint16_t)s;
+      dg.type = fs.type[g];
+      dg.flags = is_free(fs.type[g]) ? 0 : 1;
+      dg.gid_off = (uint32_t)g;
+      dg.ct_off = ct_off[g];
+      t.seq_gates.push_back(dg);
+    }
+    t.n_seq_slots = next;
+    for (size_t j = 0; j < fs.outputs.size(); j++) {
+      uint32_t o = fs.outputs[j];
+      if (o == WIRE_DEAD || o < first_def) continue;
+      t.seq_out_slot.push_back((uint16_t)sl[o]);
+    }
+  }
   return t;
 }
 
@@ -175,6 +234,8 @@ struct Planner {
       e.in_slot.assign(t.n_in, 0xFFFF);
       e.n_slots = 2;
       e.level_off.assign(1, 0);
+      e.seq_in_slot.assign(t.n_in, 0xFFFF);
+      e.n_seq_slots = 2;
       prog.tasks.push_back(std::move(e));
       return kind[ti] = (int64_t)prog.tasks.size() - 1;
     }
@@ -420,6 +481,7 @@ Program plan_program(const Builder& b, uint32_t root, const PlanOptions& opt) {
   for (const Task& t : prog.tasks) {
     prog.max_task_slots = std::max(prog.max_task_slots, t.n_slots);
     prog.max_task_in = std::max(prog.max_task_in, t.n_in);
+    prog.max_task_seq_slots = std::max(prog.max_task_seq_slots, t.n_seq_slots);
   }
   if (prog.total_gates != rt.total_gates || prog.total_ct != rt.total_ct)
     throw std::logic_error("planner lost gates: " + std::to_string(prog.total_gates) + " vs " +

@@ -50,6 +50,12 @@ struct Task {
   std::vector<uint16_t> in_slot;     // per input position; 0xFFFF when the input is never read
   std::vector<uint16_t> out_slot;    // per produced output
   std::vector<uint32_t> out_pos;     // callee output position of each produced output
+  // Lane-mode form (one warp = 32 instances, gates in EMISSION order, no levels): slots are
+  // recycled by emission-order liveness -- exactly the reference's credits slab behaviour
+  // (src/storage.rs:158-179: freed on the last read) -- and index a per-worker scratch array.
+  std::vector<DevGate> seq_gates;
+  std::vector<uint16_t> seq_in_slot, seq_out_slot;
+  uint32_t n_seq_slots = 0;
 };
 
 struct Call {
@@ -74,6 +80,7 @@ struct Program {
   uint64_t total_ct = 0;
   uint64_t total_live = 0;
   uint32_t max_task_slots = 0;
+  uint32_t max_task_seq_slots = 0;
   uint32_t max_task_in = 0;
   uint32_t max_call_deps = 0;
   uint64_t type_count[11] = {0};

@@ -143,7 +143,9 @@ typedef struct {
   uint32_t worker_threads;/* threads per worker: 128/256/512; 0 = auto */
   uint32_t ct_mode;       /* enum gsv_ct_mode */
   uint32_t ct_ring_log2;  /* GSV_CT_COMMIT: cap the ciphertext ring at 2^n entries per instance; 0 = auto */
-  uint32_t reserved[2];
+  uint32_t exec_mode;     /* 0 = auto, 1 = levelised (labels in shared memory, small batches),
+                             2 = lane (one warp = 32 instances, emission order; large batches) */
+  uint32_t reserved;
 } gsv_session_options;
 
 gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options* opt);

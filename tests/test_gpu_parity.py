@@ -61,10 +61,60 @@ def test_garble_matches_oracle(gsv, orc, circuit, name, hasher):
     _check_garble(gsv, orc, circuit, name, hasher, [0, 42, 99, 777], group=2)
 
 
-@pytest.mark.parametrize("group,wt", [(1, 256), (4, 256), (8, 128), (2, 512), (1, 64)])
+@pytest.mark.parametrize("group,wt", [(1, 256), (4, 256), (4, 128), (2, 512), (1, 64)])
 def test_garble_group_and_worker_shapes(gsv, orc, circuit, group, wt):
     seeds = [1234, 12345, 2**64 - 1, 5, 6, 7, 8, 9]
     _check_garble(gsv, orc, circuit, "fq_mul", 0, seeds, group=group, worker_threads=wt)
+
+
+@pytest.mark.parametrize("hasher", [0, 1])
+@pytest.mark.parametrize("name,B", [("gate_zoo", 5), ("fq_add", 33), ("fq_mul", 64), ("fq_expr", 40)])
+def test_lane_mode_garble_matches_oracle(gsv, orc, circuit, name, B, hasher):
+    """Lane mode (one warp = 32 instances, emission order): full, partial and multiple groups."""
+    p, st = circuit(name)
+    seeds = [0, 42, 99, 777] + list(range(1000, 1000 + B - 4))
+    sess = gsv.Session(p, B, ct_mode=gsv.CT_KEEP, exec_mode=2)
+    res = sess.garble(seeds, hasher)
+    for i in sorted({0, 1, 2, 3, 31 % B, 32 % B, B - 1}):
+        ref = st.garble(hasher, seeds[i])
+        assert bytes(res.delta[i]) == ref["delta"]
+        assert np.array_equal(res.input_label0[i], ref["input_label0"])
+        assert np.array_equal(res.output_label0[i], ref["output_label0"]), (name, i)
+        assert bytes(res.ct_commit[i]) == ref["ct_commit"], (name, i)
+        assert np.array_equal(sess.read_ciphertexts(i), ref["cts"])
+
+
+def test_lane_mode_evaluate_and_ring(gsv, orc, circuit):
+    p, st = circuit("fq_mul")
+    B = 48
+    seeds = list(range(300, 300 + B))
+    sess = gsv.Session(p, B, ct_mode=gsv.CT_KEEP, exec_mode=2)
+    res = sess.garble(seeds, gsv.HASH_AES)
+    rng = np.random.default_rng(9)
+    bits = rng.integers(0, 2, (B, p.n_inputs), dtype=np.uint8)
+    act = _eval_inputs(res, bits)
+    ev = sess.evaluate(gsv.HASH_AES, res.true_label1, res.false_label0, act, bits)
+    assert np.array_equal(ev.ct_commit, res.ct_commit)
+    for i in (0, 31, 32, 47):
+        ref = st.garble(orc.HASH_AES, seeds[i])
+        o = st.evaluate(orc.HASH_AES, bytes(res.true_label1[i]), bytes(res.false_label0[i]), act[i], bits[i], ref["cts"])
+        assert np.array_equal(ev.output_active[i], o["output_active"])
+        assert np.array_equal(ev.output_bits[i], o["output_bits"])
+    # commitment through a small ring (2^15 of 102 093 ciphertexts) must not change
+    ring = gsv.Session(p, B, ct_mode=gsv.CT_COMMIT, exec_mode=2, ct_ring_log2=15).garble(seeds, gsv.HASH_AES)
+    assert np.array_equal(ring.ct_commit, res.ct_commit)
+    assert np.array_equal(ring.output_label0, res.output_label0)
+
+
+def test_lane_mode_fq12_mul(gsv, orc, circuit):
+    p, st = circuit("fq12_mul")
+    B = 64
+    seeds = [0, 42] + list(range(7000, 7000 + B - 2))
+    res = gsv.Session(p, B, ct_mode=gsv.CT_COMMIT, exec_mode=2).garble(seeds, gsv.HASH_AES)
+    for i in (0, 1, 63):
+        ref = st.garble(orc.HASH_AES, seeds[i], want_ct=False)
+        assert bytes(res.ct_commit[i]) == ref["ct_commit"]
+        assert np.array_equal(res.output_label0[i], ref["output_label0"])
 
 
 def test_garble_ragged_batch(gsv, orc, circuit):
