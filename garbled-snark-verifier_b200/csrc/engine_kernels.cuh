@@ -89,17 +89,48 @@ __device__ __forceinline__ void st_release64(unsigned long long* p, unsigned lon
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// ---- commitment consumer: one warp, 32 instances, runs until every call is folded
+// ---- commitment consumer.  The chain h <- AES_K(h ^ ct) is strictly serial per instance, so
+// its LATENCY is the floor of a committed garbling run.  One AES is therefore spread over a
+// quad of lanes: lane (i, c) owns column c of instance i's state, exchanges the other three
+// columns with its quad by shuffle each round and does 4 table lookups instead of 16.  A chain
+// warp serves CHAIN_INST = 8 instances.  It folds the stream call by call in emission order as
+// soon as the producing work items are flagged done; its progress counter is the ring's
+// back-pressure.
+constexpr uint32_t CHAIN_INST = 8;
+
+__device__ __forceinline__ uint32_t quad_aes(const uint32_t* __restrict__ te, uint32_t s, const uint32_t (&rk)[11],
+                                             uint32_t src1, uint32_t src2, uint32_t src3, uint32_t lb0,
+                                             uint32_t lb2) {
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
+  s ^= rk[0];
+#pragma unroll
+  for (int r = 1; r < 10; r++) {
+    const uint32_t s1 = __shfl_sync(FULL, s, src1), s2 = __shfl_sync(FULL, s, src2), s3 = __shfl_sync(FULL, s, src3);
+    s = GSV_AES_COL(s, s1, s2, s3, rk[r]);
+  }
+  const uint32_t s1 = __shfl_sync(FULL, s, src1), s2 = __shfl_sync(FULL, s, src2), s3 = __shfl_sync(FULL, s, src3);
+  return GSV_AES_LASTCOL(s, s1, s2, s3, rk[10]);
+}
+
 __device__ __forceinline__ void chain_warp(const EngineParams& p, const uint32_t* te, uint32_t cw) {
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t first = cw * 32u;
+  const uint32_t first = cw * CHAIN_INST;
   if (first >= p.B) return;
-  const uint32_t n_inst = min(32u, p.B - first);
+  const uint32_t n_inst = min(CHAIN_INST, p.B - first);
   const uint32_t G = p.G;
-  const uint32_t g0 = first / G, ng = (n_inst + G - 1) / G;
-  const bool active = lane < n_inst;
-  const uint4* base = p.ct + first + (active ? lane : 0u);
-  uint4 h = make_uint4(0, 0, 0, 0);
+  const uint32_t g0 = first / G, ng = (first + n_inst - 1) / G - g0 + 1;
+  const uint32_t col = lane & 3u, qi = lane >> 2;
+  const bool active = qi < n_inst;
+  const uint32_t q = lane & ~3u;
+  const uint32_t src1 = q | ((col + 1) & 3u), src2 = q | ((col + 2) & 3u), src3 = q | ((col + 3) & 3u);
+  const uint32_t lb0 = lane << 2, lb2 = lb0 | 128u;
+  uint32_t rk[11];
+#pragma unroll
+  for (int r = 0; r < 11; r++) rk[r] = c_rk[4 * r + col];
+  // word `col` of instance (first + qi)'s ciphertext at stream position 0
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(p.ct + first + (active ? qi : 0u)) + col;
+  const size_t row = (size_t)p.B * 4u;  // words per stream position
+  uint32_t h = 0;
   for (uint32_t c = 0; c < p.n_calls; ++c) {
     const DevCallD call = p.calls[c];
     const uint32_t n = p.tasks[call.task].n_ct;
@@ -112,18 +143,28 @@ __device__ __forceinline__ void chain_warp(const EngineParams& p, const uint32_t
     unsigned long long k = call.ct_base;
     const unsigned long long end = k + n;
     constexpr int U = 8;
-    for (; k + U <= end; k += U) {
-      uint4 v[U];
+    uint32_t v[U];
+    if (k + U <= end) {
 #pragma unroll
-      for (int j = 0; j < U; j++) v[j] = __ldcg(base + (size_t)((k + j) & p.ct_mask) * p.B);
-#pragma unroll
-      for (int j = 0; j < U; j++) h = aes_fixed(te, xor4(h, v[j]));
+      for (int j = 0; j < U; j++) v[j] = __ldcg(base + (size_t)((k + j) & p.ct_mask) * row);
     }
-    for (; k < end; k++) h = aes_fixed(te, xor4(h, __ldcg(base + (size_t)(k & p.ct_mask) * p.B)));
+    for (; k + U <= end; k += U) {
+      uint32_t w[U];
+#pragma unroll
+      for (int j = 0; j < U; j++) w[j] = v[j];
+      if (k + 2 * U <= end) {  // prefetch the next batch under this batch's AES latency
+#pragma unroll
+        for (int j = 0; j < U; j++) v[j] = __ldcg(base + (size_t)((k + U + j) & p.ct_mask) * row);
+      }
+#pragma unroll
+      for (int j = 0; j < U; j++) h = quad_aes(te, h ^ w[j], rk, src1, src2, src3, lb0, lb2);
+    }
+    for (; k < end; k++)
+      h = quad_aes(te, h ^ __ldcg(base + (size_t)(k & p.ct_mask) * row), rk, src1, src2, src3, lb0, lb2);
     __syncwarp();
     if (lane == 0) st_release64(p.chain_progress + cw, end);
   }
-  if (active) p.commit[first + lane] = h;
+  if (active) reinterpret_cast<uint32_t*>(p.commit + first + qi)[col] = h;
 }
 
 // MODE 0 = garble (labels are label0, ciphertexts produced), MODE 1 = evaluate.
@@ -177,7 +218,7 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
     if (MODE == 0 && p.ct_ring && wt == NT - 1) {
       const unsigned long long need = call.ct_base + task.n_ct;
       if (need > p.ct_ring) {
-        const unsigned long long* pr = p.chain_progress + (grp * G) / 32u;
+        const unsigned long long* pr = p.chain_progress + (grp * G) / CHAIN_INST;  // G divides 8
         while (ld_acquire64(pr) + p.ct_ring < need) __nanosleep(256);
       }
     }
@@ -311,10 +352,12 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
       const uint32_t* f = p.flags + (size_t)p.deps[call.dep_off + d] * p.n_groups + grp;
       while (ld_acquire(f) != p.epoch) __nanosleep(100);
     }
-    if (MODE == 0 && p.ct_ring && lane == 31) {
+    if (MODE == 0 && p.ct_ring && lane >= 32 - 32 / CHAIN_INST) {
+      // the group's 32 instances are served by 4 chain warps: one polling lane each
       const unsigned long long need = call.ct_base + task.n_ct;
-      if (need > p.ct_ring) {
-        const unsigned long long* pr = p.chain_progress + grp;  // chain warp == instance group
+      const uint32_t cwi = grp * (32 / CHAIN_INST) + (lane - (32 - 32 / CHAIN_INST));
+      if (need > p.ct_ring && cwi * CHAIN_INST < p.B) {
+        const unsigned long long* pr = p.chain_progress + cwi;
         while (ld_acquire64(pr) + p.ct_ring < need) __nanosleep(256);
       }
     }

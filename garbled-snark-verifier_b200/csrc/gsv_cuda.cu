@@ -497,8 +497,8 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
     s->NT = opt->worker_threads ? opt->worker_threads : 256;
     if (s->NT != 64 && s->NT != 128 && s->NT != 256 && s->NT != 512 && s->NT != 1024)
       throw std::runtime_error("worker_threads must be 64/128/256/512/1024");
-    uint32_t n_chain = (s->ct_mode != GSV_CT_NONE) ? ((s->B + 31) / 32 + s->sm_count - 1) / s->sm_count : 0;
-    if (n_chain > 8) throw std::runtime_error("too many instances for one GPU (chain warps)");
+    uint32_t n_chain = (s->ct_mode != GSV_CT_NONE) ? ((s->B + CHAIN_INST - 1) / CHAIN_INST + s->sm_count - 1) / s->sm_count : 0;
+    if (n_chain > 16) throw std::runtime_error("too many instances for one GPU (chain warps)");
     uint32_t n_workers = (1024 - 32 * n_chain) / s->NT;
     if (n_workers == 0) throw std::runtime_error("worker_threads too large");
     // largest G (power of two dividing B, <= 8) whose label working set fits next to the tables
