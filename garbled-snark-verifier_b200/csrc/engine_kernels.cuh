@@ -56,7 +56,9 @@ struct EngineParams {
   unsigned long long ct_capacity;  // evaluate: ciphertexts available per instance
   uint32_t n_calls, n_groups, n_global_slots, B;
   uint32_t slots_per_worker;  // shared-memory label slots per instance reserved per worker
-  uint32_t worker_threads, n_workers, n_chain_warps;
+  uint32_t worker_threads, n_workers;
+  uint32_t n_chain_warps;     // chain warps per chain CTA
+  uint32_t n_chain_ctas;      // trailing CTAs of the grid that only run chain warps
   uint32_t epoch;
   uint32_t write_ct;          // garble: store ciphertexts
   uint32_t G;                 // instances per group (32 in lane mode)
@@ -178,15 +180,16 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
   load_tables(te, threadIdx.x, blockDim.x);
   __syncthreads();
 
-  if (threadIdx.x >= n_workers * NT) {
-    // ---- chain role
-    if (MODE == 0) {
-      const uint32_t k = (threadIdx.x - n_workers * NT) >> 5;
-      chain_warp(p, te, blockIdx.x * p.n_chain_warps + k);
-    }
+  if (MODE == 0 && blockIdx.x >= gridDim.x - p.n_chain_ctas) {
+    // ---- chain CTA: the last n_chain_ctas SMs only run commitment consumers, a few warps per
+    // SMSP, so the latency-bound chain never competes with garbling warps for issue slots
+    const uint32_t warp = threadIdx.x >> 5;
+    if (warp < p.n_chain_warps)
+      chain_warp(p, te, (blockIdx.x - (gridDim.x - p.n_chain_ctas)) * p.n_chain_warps + warp);
     return;
   }
 
+  if (threadIdx.x >= n_workers * NT) return;
   const uint32_t worker = threadIdx.x / NT;
   const uint32_t wt = threadIdx.x - worker * NT;
   const uint32_t bar_id = worker + 1;
@@ -326,10 +329,13 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
   load_tables(te, threadIdx.x, blockDim.x);
   __syncthreads();
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-  if (warp >= p.n_workers) {
-    if (MODE == 0) chain_warp(p, te, blockIdx.x * p.n_chain_warps + (warp - p.n_workers));
+  if (MODE == 0 && blockIdx.x >= gridDim.x - p.n_chain_ctas) {
+    // chain CTA (see k_engine): dedicated SMs for the serial commitment
+    if (warp < p.n_chain_warps)
+      chain_warp(p, te, (blockIdx.x - (gridDim.x - p.n_chain_ctas)) * p.n_chain_warps + warp);
     return;
   }
+  if (warp >= p.n_workers) return;
   const uint32_t wid = blockIdx.x * p.n_workers + warp;
   uint4* my = p.scratch + (size_t)wid * p.scratch_stride * 32u + lane;
   uint8_t* myv = p.scratch_vals + (size_t)wid * p.scratch_stride * 32u + lane;

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -271,7 +272,8 @@ struct gsv_session {
   uint32_t ct_mode = GSV_CT_COMMIT;
   int sm_count = 0;
   size_t smem_garble = 0, smem_eval = 0;
-  uint32_t n_chain_warps = 0;      // per CTA
+  uint32_t n_chain_warps = 0;      // chain warps per chain CTA
+  uint32_t n_chain_ctas = 0;       // trailing CTAs dedicated to the commitment chain
   uint64_t ct_ring = 0, ct_mask = ~0ull;  // ring capacity (0 = whole stream kept) / position mask
   uint32_t epoch = 0;
   cudaStream_t stream = nullptr;
@@ -432,7 +434,7 @@ EngineParams make_params(gsv_session* s) {
 template <int MODE>
 void launch_engine(gsv_session* s, int hasher, const EngineParams& p) {
   if (s->lane_mode) {
-    dim3 lgrid(s->sm_count), lblock(32 * (s->n_workers + p.n_chain_warps));
+    dim3 lgrid(s->sm_count), lblock(32 * s->n_workers);
     if (hasher == GSV_HASH_AES) {
       CUDA_TRY(cudaFuncSetAttribute(k_lane<HASH_AES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
       k_lane<HASH_AES, MODE><<<lgrid, lblock, AES_TABLE_BYTES, s->stream>>>(p);
@@ -446,7 +448,7 @@ void launch_engine(gsv_session* s, int hasher, const EngineParams& p) {
     return;
   }
   const size_t smem = MODE == 0 ? s->smem_garble : s->smem_eval;
-  dim3 grid(s->sm_count), block(s->n_workers * s->NT + 32 * p.n_chain_warps);
+  dim3 grid(s->sm_count), block(std::max<uint32_t>(s->n_workers * s->NT, 32 * p.n_chain_warps));
 #define GSV_LAUNCH(GG, HH)                                                                              \
   do {                                                                                                  \
     CUDA_TRY(cudaFuncSetAttribute(k_engine<GG, HH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
@@ -497,9 +499,20 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
     s->NT = opt->worker_threads ? opt->worker_threads : 256;
     if (s->NT != 64 && s->NT != 128 && s->NT != 256 && s->NT != 512 && s->NT != 1024)
       throw std::runtime_error("worker_threads must be 64/128/256/512/1024");
-    uint32_t n_chain = (s->ct_mode != GSV_CT_NONE) ? ((s->B + CHAIN_INST - 1) / CHAIN_INST + s->sm_count - 1) / s->sm_count : 0;
-    if (n_chain > 16) throw std::runtime_error("too many instances for one GPU (chain warps)");
-    uint32_t n_workers = (1024 - 32 * n_chain) / s->NT;
+    // commitment consumers: one chain warp per CHAIN_INST instances, packed a few warps per SMSP
+    // onto dedicated trailing CTAs (SMs) of the persistent grid
+    const uint32_t chain_warps_total = (s->ct_mode != GSV_CT_NONE) ? (s->B + CHAIN_INST - 1) / CHAIN_INST : 0;
+    uint32_t n_chain = 0;  // chain warps per chain CTA
+    s->n_chain_ctas = 0;
+    if (chain_warps_total) {
+      uint32_t per_cta = 16;
+      if (const char* e = getenv("GSV_CHAIN_WARPS_PER_SM")) per_cta = std::max(1, std::min(32, atoi(e)));
+      n_chain = std::min(per_cta, chain_warps_total);
+      s->n_chain_ctas = (chain_warps_total + n_chain - 1) / n_chain;
+      if (s->n_chain_ctas * 2 > (uint32_t)s->sm_count)
+        throw std::runtime_error("too many instances for one GPU (commitment warps would take over half the SMs)");
+    }
+    uint32_t n_workers = 1024 / s->NT;
     if (n_workers == 0) throw std::runtime_error("worker_threads too large");
     // largest G (power of two dividing B, <= 8) whose label working set fits next to the tables
     auto smem_for = [&](uint32_t G, uint32_t nw, bool eval) {
@@ -514,7 +527,7 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
     if (s->lane_mode) {
       G = 32;
       s->NT = 32;
-      n_workers = 32 - n_chain;
+      n_workers = 32;
       s->B_pad = (s->B + 31) / 32 * 32;
       s->n_groups = s->B_pad / 32;
       s->scratch_stride = std::max<uint32_t>(g.max_task_seq_slots, 4);
@@ -552,7 +565,7 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
     s->d_flags.alloc((size_t)g.calls.size() * s->n_groups + 1);
     CUDA_TRY(cudaMemset(s->d_flags.p, 0, s->d_flags.n * 4));
     s->d_ctrl.alloc(4);
-    s->d_progress.alloc((size_t)s->sm_count * std::max<uint32_t>(n_chain, 1));
+    s->d_progress.alloc((size_t)std::max<uint32_t>(s->n_chain_ctas * n_chain, 1));
     CUDA_TRY(cudaMemset(s->d_ctrl.p, 0, 16));
     if (s->ct_mode != GSV_CT_NONE) {
       // GSV_CT_KEEP: the whole interleaved stream stays resident.  GSV_CT_COMMIT: a power-of-two
@@ -613,6 +626,7 @@ int gsv_garble_batch(gsv_session* s, int hasher, const uint64_t* seeds, gsv_garb
     EngineParams p = make_params(s);
     p.write_ct = (s->ct_mode != GSV_CT_NONE) ? 1u : 0u;
     p.n_chain_warps = s->n_chain_warps;
+    p.n_chain_ctas = s->n_chain_ctas;
     if (s->n_chain_warps) CUDA_TRY(cudaMemsetAsync(s->d_progress.p, 0, s->d_progress.n * 8, s->stream));
     launch_engine<0>(s, hasher, p);
     launches++;
