@@ -74,17 +74,21 @@ struct EngineParams {
 __device__ __forceinline__ void named_bar(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// Flag polling uses RELAXED gpu-scope loads: an ld.acquire.gpu compiles to LDG + CCTL.IVALL, and
+// a spinning warp would invalidate its SM's L1 on every poll (52 M invalidates in the first
+// profile, profiles/r01_chain_poll.md).  The acquire is a single fence after the wait succeeds.
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_acquire64(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_release64(unsigned long long* p, unsigned long long v) {
@@ -141,6 +145,7 @@ __device__ __forceinline__ void chain_warp(const EngineParams& p, const uint32_t
       const uint32_t* f = p.flags + (size_t)c * p.n_groups + g0 + lane;
       while (ld_acquire(f) != p.epoch) __nanosleep(200);
     }
+    fence_acquire();
     __syncwarp();
     unsigned long long k = call.ct_base;
     const unsigned long long end = k + n;
@@ -225,6 +230,7 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
         while (ld_acquire64(pr) + p.ct_ring < need) __nanosleep(256);
       }
     }
+    fence_acquire();
     named_bar(bar_id, NT);
 
     // ---- gather inputs (and the two constant wires) into shared memory
@@ -367,6 +373,7 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
         while (ld_acquire64(pr) + p.ct_ring < need) __nanosleep(256);
       }
     }
+    fence_acquire();
     __syncwarp();
 
     // ---- gather: constants + inputs -> scratch (rows of 32 labels, 512 B each)

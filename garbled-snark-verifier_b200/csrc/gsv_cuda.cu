@@ -627,6 +627,7 @@ int gsv_garble_batch(gsv_session* s, int hasher, const uint64_t* seeds, gsv_garb
     p.write_ct = (s->ct_mode != GSV_CT_NONE) ? 1u : 0u;
     p.n_chain_warps = s->n_chain_warps;
     p.n_chain_ctas = s->n_chain_ctas;
+    if (getenv("GSV_DEBUG_NO_CHAIN")) p.n_chain_ctas = 0;  // profiling aid: ciphertexts written, not folded
     if (s->n_chain_warps) CUDA_TRY(cudaMemsetAsync(s->d_progress.p, 0, s->d_progress.n * 8, s->stream));
     launch_engine<0>(s, hasher, p);
     launches++;
