@@ -232,3 +232,31 @@ def test_commit_only_mode_matches_keep(gsv, circuit):
     c = gsv.Session(p, 4, ct_mode=gsv.CT_NONE).garble(seeds, 0)
     assert np.array_equal(a.ct_commit, b.ct_commit)
     assert np.array_equal(a.output_label0, b.output_label0) and np.array_equal(a.output_label0, c.output_label0)
+
+
+def test_cut_and_choose_commit_records(gsv, orc, circuit):
+    """Garbler::create + commit on the GPU == GarbledInstanceCommit::new over the oracle's labels
+    (garbler.rs:85-116: ct commit, (c(l0), c(l1)) per input, output label1/label0, constants)."""
+    from gsv_b200 import cut_and_choose as cc
+
+    p, st = circuit("fq_add")
+    total = 6
+    g = cc.Garbler(p, total, master_seed=1234)
+    g.create()
+    rec = g.commit()
+    seeds = cc.instance_seeds(1234, total)
+    xor = lambda a, b: bytes(x ^ y for x, y in zip(a, b))
+    for i in (0, 3, 5):
+        ref = st.garble(orc.HASH_AES, int(seeds[i]), want_ct=False)
+        d = ref["delta"]
+        assert bytes(rec.ct_commit()[i]) == ref["ct_commit"]
+        for j in (0, 1, p.n_inputs - 1):
+            l0 = bytes(ref["input_label0"][j])
+            assert bytes(rec.input_commits()[i, j, 0]) == orc.commit_label(l0)
+            assert bytes(rec.input_commits()[i, j, 1]) == orc.commit_label(xor(l0, d))
+        for j in (0, p.n_outputs - 1):
+            o0 = bytes(ref["output_label0"][j])
+            assert bytes(rec.output_commits()[i, j, 0]) == orc.commit_label(xor(o0, d))  # label1 first
+            assert bytes(rec.output_commits()[i, j, 1]) == orc.commit_label(o0)
+        assert bytes(rec.constant_commits()[i, 0]) == orc.commit_label(xor(ref["true_label0"], d))
+        assert bytes(rec.constant_commits()[i, 1]) == orc.commit_label(ref["false_label0"])
