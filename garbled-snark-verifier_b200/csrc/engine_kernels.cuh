@@ -419,10 +419,6 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
     const uint32_t n = task.n_seq_gates;
     uint4 rec_next = make_uint4(0, 0, 0, 0);
     if (lane < n) rec_next = __ldg(gates + lane);
-    // forwarding window: slot ids and labels (and plaintext bits) of the last three gate outputs
-    uint32_t f_s0 = 0xFFFFFFFFu, f_s1 = 0xFFFFFFFFu, f_s2 = 0xFFFFFFFFu;
-    uint32_t f_v0 = 0, f_v1 = 0, f_v2 = 0;
-    uint4 f_c0 = make_uint4(0, 0, 0, 0), f_c1 = f_c0, f_c2 = f_c0;
     for (uint32_t g0 = 0; g0 < n; g0 += 32) {
       const uint4 rec = rec_next;
       if (g0 + 32 + lane < n) rec_next = __ldg(gates + g0 + 32 + lane);
@@ -431,29 +427,8 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
         const uint32_t rx = __shfl_sync(FULL, rec.x, j), ry = __shfl_sync(FULL, rec.y, j);
         const uint32_t sa = rx & 0xFFFFu, sb = rx >> 16, sc = ry & 0xFFFFu;
         const uint32_t type = (ry >> 16) & 0xFFu;
-        // (1) prefetch the operand rows of the gate PF positions ahead into L1: the "old" operands
-        // of an emission-order walk (e.g. the a_i / b_i bits of a ripple adder) are independent of
-        // the carry chain, so their L2 round trip hides under the AES of the gates in between.
-        {
-          constexpr uint32_t PF = 8;
-          const uint32_t jp = j + PF;
-          const uint32_t px = __shfl_sync(FULL, jp < 32 ? rec.x : rec_next.x, jp & 31u);
-          if (g0 + jp < n) {
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(my + (px & 0xFFFFu) * 32u));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(my + (px >> 16) * 32u));
-          }
-        }
-        // (2) the last three results are forwarded from registers (warp-uniform slot compares): the
-        // dependent chain never waits for a store -> load round trip through L2.
-        uint4 la, lb;
-        if (sa == f_s0) la = f_c0;
-        else if (sa == f_s1) la = f_c1;
-        else if (sa == f_s2) la = f_c2;
-        else la = my[sa * 32u];
-        if (sb == f_s0) lb = f_c0;
-        else if (sb == f_s1) lb = f_c1;
-        else if (sb == f_s2) lb = f_c2;
-        else lb = my[sb * 32u];
+        const uint4 la = my[sa * 32u];
+        const uint4 lb = my[sb * 32u];
         uint4 lc;
         if (MODE == 0) {
           if (type >= 8) {
@@ -467,15 +442,7 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
             if (p.write_ct && act) __stcg(p.ct + (size_t)(cti & p.ct_mask) * p.B + instance, ct);
           }
         } else {
-          uint32_t va, vb;
-          if (sa == f_s0) va = f_v0;
-          else if (sa == f_s1) va = f_v1;
-          else if (sa == f_s2) va = f_v2;
-          else va = myv[sa * 32u];
-          if (sb == f_s0) vb = f_v0;
-          else if (sb == f_s1) vb = f_v1;
-          else if (sb == f_s2) vb = f_v2;
-          else vb = myv[sb * 32u];
+          const uint32_t va = myv[sa * 32u], vb = myv[sb * 32u];
           if (type >= 8) {
             lc = (type == 10) ? la : xor4(la, lb);
           } else {
@@ -489,14 +456,9 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
             }
             lc = degarble_nonfree<HASH>(te, type, ct, la, va, lb, gid);
           }
-          const uint32_t vc = gate_value(type, va, vb);
-          myv[sc * 32u] = (uint8_t)vc;
-          f_v2 = f_v1; f_v1 = f_v0; f_v0 = vc;
+          myv[sc * 32u] = (uint8_t)gate_value(type, va, vb);
         }
         my[sc * 32u] = lc;
-        f_s2 = f_s1; f_c2 = f_c1;
-        f_s1 = f_s0; f_c1 = f_c0;
-        f_s0 = sc; f_c0 = lc;
       }
     }
 

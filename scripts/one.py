@@ -1,16 +1,14 @@
-"""Run a few garble batches (for ncu captures): one.py CIRCUIT B SHAPE CT_MODE [ITERS] [RING_LOG2]"""
+"""Run one garble batch (for ncu captures): one.py CIRCUIT B SHAPE CT_MODE"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gsv_b200 as g
 circ, B, sh, ct = sys.argv[1], int(sys.argv[2]), sys.argv[3], int(sys.argv[4])
-iters = int(sys.argv[5]) if len(sys.argv) > 5 else 2
-ring = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 p = g.Program(circ)
 if sh == "lane":
-    s = g.Session(p, B, ct_mode=ct, exec_mode=2, ct_ring_log2=ring)
+    s = g.Session(p, B, ct_mode=ct, exec_mode=2)
 else:
     G, NT = (int(v) for v in sh.split("x"))
-    s = g.Session(p, B, group=G, worker_threads=NT, ct_mode=ct, exec_mode=1, ct_ring_log2=ring)
-for it in range(iters):
+    s = g.Session(p, B, group=G, worker_threads=NT, ct_mode=ct, exec_mode=1)
+for it in range(int(sys.argv[5]) if len(sys.argv) > 5 else 2):
     r = s.garble(list(range(B)), g.HASH_AES, want_inputs=False, want_outputs=False)
-    print(f"garble {r.ms_garble:.3f} ms  {p.n_gates * B / r.ms_garble / 1e6:.3f} Ggates/s", flush=True)
+    print(f"garble {r.ms_garble:.3f} ms", flush=True)
