@@ -51,8 +51,8 @@ struct EngineParams {
   uint32_t* error_flag;       // evaluate: set to 1 on ciphertext exhaustion
   unsigned long long* chain_progress;  // [chain warp] ciphertexts folded so far
   uint4* commit;        // [B] chain result
-  unsigned long long ct_mask;      // ring: position = index & ct_mask (all ones: no wrap)
-  unsigned long long ct_ring;      // ring capacity in ciphertexts (0: no back-pressure needed)
+  unsigned long long ct_ring;      // ring capacity in ciphertexts: position = index % ct_ring
+                                   // (0: whole stream resident, no wrap, no back-pressure)
   unsigned long long ct_capacity;  // evaluate: ciphertexts available per instance
   uint32_t n_calls, n_groups, n_global_slots, B;
   uint32_t slots_per_worker;  // shared-memory label slots per instance reserved per worker
@@ -149,11 +149,17 @@ __device__ __forceinline__ void chain_warp(const EngineParams& p, const uint32_t
     __syncwarp();
     unsigned long long k = call.ct_base;
     const unsigned long long end = k + n;
+    // ring position of the next ciphertext to LOAD (advanced incrementally, one wrap test per load)
+    unsigned long long pos = p.ct_ring ? k % p.ct_ring : k;
+    const unsigned long long wrap = p.ct_ring ? p.ct_ring : ~0ull;
     constexpr int U = 8;
     uint32_t v[U];
     if (k + U <= end) {
 #pragma unroll
-      for (int j = 0; j < U; j++) v[j] = __ldcg(base + (size_t)((k + j) & p.ct_mask) * row);
+      for (int j = 0; j < U; j++) {
+        v[j] = __ldcg(base + (size_t)pos * row);
+        if (++pos == wrap) pos = 0;
+      }
     }
     for (; k + U <= end; k += U) {
       uint32_t w[U];
@@ -161,13 +167,18 @@ __device__ __forceinline__ void chain_warp(const EngineParams& p, const uint32_t
       for (int j = 0; j < U; j++) w[j] = v[j];
       if (k + 2 * U <= end) {  // prefetch the next batch under this batch's AES latency
 #pragma unroll
-        for (int j = 0; j < U; j++) v[j] = __ldcg(base + (size_t)((k + U + j) & p.ct_mask) * row);
+        for (int j = 0; j < U; j++) {
+          v[j] = __ldcg(base + (size_t)pos * row);
+          if (++pos == wrap) pos = 0;
+        }
       }
 #pragma unroll
       for (int j = 0; j < U; j++) h = quad_aes(te, h ^ w[j], rk, src1, src2, src3, lb0, lb2);
     }
-    for (; k < end; k++)
-      h = quad_aes(te, h ^ __ldcg(base + (size_t)(k & p.ct_mask) * row), rk, src1, src2, src3, lb0, lb2);
+    for (; k < end; k++) {
+      h = quad_aes(te, h ^ __ldcg(base + (size_t)pos * row), rk, src1, src2, src3, lb0, lb2);
+      if (++pos == wrap) pos = 0;
+    }
     __syncwarp();
     if (lane == 0) st_release64(p.chain_progress + cw, end);
   }
@@ -233,6 +244,8 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
     fence_acquire();
     named_bar(bar_id, NT);
 
+    // ring position of the call's first ciphertext (a task never exceeds half the ring)
+    const unsigned long long ct_pos0 = p.ct_ring ? call.ct_base % p.ct_ring : call.ct_base;
     // ---- gather inputs (and the two constant wires) into shared memory
     const size_t gbase = (size_t)grp * p.n_global_slots;
     uint4 delta = make_uint4(0, 0, 0, 0);
@@ -285,7 +298,11 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
             uint4 ct;
             lc = garble_nonfree<HASH>(te, type, la, lb, delta, gid, ct);
             if (p.write_ct)
-              __stcg(p.ct + (size_t)((call.ct_base + graw.w) & p.ct_mask) * p.B + grp * G + inst, ct);
+            {
+              unsigned long long pos = ct_pos0 + graw.w;
+              if (p.ct_ring && pos >= p.ct_ring) pos -= p.ct_ring;
+              __stcg(p.ct + (size_t)pos * p.B + grp * G + inst, ct);
+            }
           }
         } else {
           const uint32_t va = sval[sa * G + inst], vb = sval[sb * G + inst];
@@ -376,6 +393,7 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
     fence_acquire();
     __syncwarp();
 
+    const unsigned long long ct_pos0 = p.ct_ring ? call.ct_base % p.ct_ring : call.ct_base;
     // ---- gather: constants + inputs -> scratch (rows of 32 labels, 512 B each)
     const size_t gbase = (size_t)grp * p.n_global_slots;
     const uint4* glab = p.labels + gbase * 32u + lane;
@@ -436,10 +454,11 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
             if (type == 9) lc = xor4(lc, delta);
           } else {
             const unsigned long long gid = call.gid_base + __shfl_sync(FULL, rec.z, j);
-            const unsigned long long cti = call.ct_base + __shfl_sync(FULL, rec.w, j);
+            unsigned long long pos = ct_pos0 + __shfl_sync(FULL, rec.w, j);
+            if (p.ct_ring && pos >= p.ct_ring) pos -= p.ct_ring;
             uint4 ct;
             lc = garble_nonfree<HASH>(te, type, la, lb, delta, gid, ct);
-            if (p.write_ct && act) __stcg(p.ct + (size_t)(cti & p.ct_mask) * p.B + instance, ct);
+            if (p.write_ct && act) __stcg(p.ct + (size_t)pos * p.B + instance, ct);
           }
         } else {
           const uint32_t va = myv[sa * 32u], vb = myv[sb * 32u];

@@ -274,7 +274,7 @@ struct gsv_session {
   size_t smem_garble = 0, smem_eval = 0;
   uint32_t n_chain_warps = 0;      // chain warps per chain CTA
   uint32_t n_chain_ctas = 0;       // trailing CTAs dedicated to the commitment chain
-  uint64_t ct_ring = 0, ct_mask = ~0ull;  // ring capacity (0 = whole stream kept) / position mask
+  uint64_t ct_ring = 0;  // ring capacity in ciphertexts (0 = whole stream kept)
   uint32_t epoch = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -410,7 +410,6 @@ EngineParams make_params(gsv_session* s) {
   p.error_flag = s->d_ctrl.p + 1;
   p.chain_progress = s->d_progress.p;
   p.commit = s->d_commit.p;
-  p.ct_mask = s->ct_mask;
   p.ct_ring = s->ct_ring;
   p.n_workers = s->n_workers;
   p.n_chain_warps = 0;
@@ -575,19 +574,18 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
       for (const auto& t : g.tasks) max_task_ct = std::max<uint64_t>(max_task_ct, t.n_ct);
       size_t free_b = 0, total_b = 0;
       CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-      const uint64_t budget = std::min<uint64_t>((uint64_t)(free_b * 0.6), 48ull << 30);
-      uint64_t ring = 1;
-      while (ring * 2 * s->B * 16 <= budget) ring *= 2;
+      // The ring bounds how far garbling may run ahead of the (serial, emission-ordered) chain, and
+      // with it the task parallelism available inside one instance: make it as large as HBM allows.
+      const uint64_t budget = (uint64_t)(free_b * 0.85);
+      uint64_t ring = std::max<uint64_t>(budget / ((uint64_t)s->B * 16), 1);
       if (opt->ct_ring_log2) ring = std::min<uint64_t>(ring, 1ull << opt->ct_ring_log2);
       if (s->ct_mode == GSV_CT_KEEP || ring >= total) {
         if (total * s->B * 16 > (uint64_t)(free_b * 0.9)) throw std::runtime_error("ciphertext stream does not fit in HBM; use GSV_CT_COMMIT");
         s->ct_ring = 0;
-        s->ct_mask = ~0ull;
         s->d_ct.alloc((size_t)total * s->B);
       } else {
         if (ring < 2 * max_task_ct) throw std::runtime_error("ciphertext ring smaller than two tasks; fewer instances needed");
         s->ct_ring = ring;
-        s->ct_mask = ring - 1;
         s->d_ct.alloc((size_t)ring * s->B);
       }
     }
