@@ -145,14 +145,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gsv", choices=["gsv", "reference"])
     ap.add_argument("--circuit", default="fq12_mul")
-    ap.add_argument("--instances", type=int, default=4096, help="cut-and-choose instances per GPU")
+    ap.add_argument("--instances", type=int, default=6144, help="cut-and-choose instances per GPU")
     ap.add_argument("--exec-mode", type=int, default=0, help="0 auto, 1 levelised, 2 lane")
     ap.add_argument("--group", type=int, default=0)
     ap.add_argument("--worker-threads", type=int, default=0)
     ap.add_argument("--hasher", default="aes", choices=["aes", "blake3"])
     ap.add_argument("--no-commit", action="store_true", help="drop ciphertexts (the `()` handler)")
-    ap.add_argument("--ref-instances-per-core", type=int, default=2)
-    ap.add_argument("--cpu-baseline-instances", type=int, default=2)
+    ap.add_argument("--ref-instances-per-core", type=int, default=8)
+    ap.add_argument("--cpu-baseline-instances", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
