@@ -25,6 +25,7 @@ HASH_BLAKE3 = 1
 CT_NONE = 0
 CT_COMMIT = 1
 CT_KEEP = 2
+CT_KEEP_RAW = 3
 WIRE_UNREACHABLE = 0xFFFFFFFF
 
 GATE_NAMES = ["And", "Nand", "Nimp", "Imp", "Ncimp", "Cimp", "Nor", "Or", "Xor", "Xnor", "Not"]
@@ -37,7 +38,7 @@ class GsvError(RuntimeError):
 
 
 class _PlanOptions(C.Structure):
-    _fields_ = [("max_task_gates", C.c_uint64), ("max_task_slots", C.c_uint32), ("reserved", C.c_uint32)]
+    _fields_ = [("max_task_gates", C.c_uint64), ("max_task_slots", C.c_uint32), ("lane_only", C.c_uint32)]
 
 
 class _ProgramInfo(C.Structure):
@@ -131,6 +132,8 @@ def load_library() -> C.CDLL:
     lib.gsv_program_get_info.argtypes = [C.c_void_p, C.POINTER(_ProgramInfo)]
     lib.gsv_program_flat_stream.restype = C.c_int64
     lib.gsv_program_flat_stream.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.gsv_program_execute.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.gsv_groth16_synthetic_inputs.argtypes = [C.c_uint64, C.c_int, C.c_void_p, C.c_uint32]
     lib.gsv_session_create.restype = C.c_void_p
     lib.gsv_session_create.argtypes = [C.c_void_p, C.POINTER(_SessionOptions)]
     lib.gsv_session_destroy.argtypes = [C.c_void_p]
@@ -160,9 +163,9 @@ def _ptr(a: Optional[np.ndarray]):
 class Program:
     """A recorded + planned circuit (the once-per-topology flatten step)."""
 
-    def __init__(self, circuit: str, max_task_slots: int = 0, max_task_gates: int = 0):
+    def __init__(self, circuit: str, max_task_slots: int = 0, max_task_gates: int = 0, lane_only: bool = False):
         lib = load_library()
-        opt = _PlanOptions(max_task_gates, max_task_slots, 0)
+        opt = _PlanOptions(max_task_gates, max_task_slots, 1 if lane_only else 0)
         self._h = lib.gsv_program_build(circuit.encode(), C.byref(opt))
         if not self._h:
             raise GsvError(-1, lib.gsv_last_error().decode())
@@ -187,6 +190,15 @@ class Program:
         if getattr(self, "_h", None) and _lib is not None:
             _lib.gsv_program_destroy(self._h)
             self._h = None
+
+    def execute(self, input_bits) -> np.ndarray:
+        """ExecuteMode: boolean evaluation of the recorded topology on the host (self-check)."""
+        lib = load_library()
+        ib = np.ascontiguousarray(input_bits, np.uint8).reshape(self.n_inputs)
+        ob = np.zeros(self.n_outputs, np.uint8)
+        n = C.c_uint64(0)
+        _check(lib.gsv_program_execute(self._h, _ptr(ib), _ptr(ob), C.byref(n)))
+        return ob
 
     def flat_stream(self):
         """Emission-order gate stream (type, a, b, c, outputs, n_wires) for checkers."""
@@ -316,6 +328,14 @@ class Session:
         io.output_active, io.output_bits, io.ct_commit = _ptr(oa), _ptr(ob), _ptr(cc)
         _check(lib.gsv_evaluate_batch(self._h, hasher, C.byref(io)))
         return EvalResult(oa, ob, cc, io.ms_evaluate, io.ms_commit, io.ms_total, io.n_launches)
+
+
+def groth16_synthetic_inputs(public_x: int = 424242, flip_public: bool = False) -> np.ndarray:
+    """1273 input bits of a synthetic proof for the "groth16_verify_compressed" circuit."""
+    lib = load_library()
+    bits = np.zeros(1273, np.uint8)
+    _check(lib.gsv_groth16_synthetic_inputs(public_x, 1 if flip_public else 0, _ptr(bits), 1273))
+    return bits
 
 
 def commit_labels(labels: np.ndarray, device: int = 0) -> np.ndarray:

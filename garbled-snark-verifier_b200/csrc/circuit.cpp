@@ -1,6 +1,7 @@
 // circuit.cpp -- two-pass (credits, execution) circuit recorder.  See circuit.h.
 #include "circuit.h"
 
+#include <algorithm>
 #include <cassert>
 #include <stdexcept>
 
@@ -260,6 +261,65 @@ struct Flattener {
   }
 };
 }  // namespace
+
+namespace {
+struct Executor {
+  const Builder& b;
+  std::vector<uint8_t> arena;  // per-instance wire values, stack allocated
+  uint64_t gates = 0;
+  static inline uint8_t eval(uint8_t t, uint8_t x, uint8_t y) {
+    if (t < 8) return (uint8_t)((((x ^ (t >> 2)) & (y ^ (t >> 1))) ^ t) & 1);
+    if (t == XOR) return x ^ y;
+    if (t == XNOR) return (uint8_t)(x ^ y ^ 1);
+    return (uint8_t)(x ^ 1);
+  }
+  // runs template `ti` whose frame starts at arena[base] (inputs already written at base+2..)
+  void run(uint32_t ti, size_t base) {
+    const Template& t = b.tmpl(ti);
+    if (arena.size() < base + t.n_wires) arena.resize(std::max(arena.size() * 2, base + t.n_wires));
+    arena[base] = 0;
+    arena[base + 1] = 1;
+    for (const Item& it : t.items) {
+      if (!it.is_call) {
+        const GateRec& g = t.gates[it.idx];
+        gates++;
+        if (g.c == WIRE_DEAD) continue;
+        arena[base + g.c] = eval(g.type, arena[base + g.a], arena[base + g.b]);
+      } else {
+        const CallRec& c = t.calls[it.idx];
+        const Template& ch = b.tmpl(c.tmpl);
+        const size_t cb = base + t.n_wires;
+        if (arena.size() < cb + ch.n_wires) arena.resize(std::max(arena.size() * 2, cb + ch.n_wires));
+        for (uint32_t i = 0; i < ch.n_in; i++) {
+          Wire w = t.call_wires[c.in_off + i];
+          arena[cb + WIRE_MIN + i] = (w == WIRE_DEAD) ? 0 : arena[base + w];
+        }
+        run(c.tmpl, cb);
+        for (size_t j = 0; j < ch.outs.size(); j++) {
+          Wire p = t.call_wires[c.out_off + j];
+          Wire o = ch.outs[j];
+          if (p == WIRE_DEAD || p < WIRE_MIN || o == WIRE_DEAD) continue;
+          if (o >= WIRE_MIN + ch.n_in) arena[base + p] = arena[cb + o];  // produced output (passthroughs alias)
+        }
+      }
+    }
+  }
+};
+}  // namespace
+
+std::vector<uint8_t> execute(const Builder& b, uint32_t root, const std::vector<uint8_t>& input_bits,
+                             uint64_t* gates_executed) {
+  const Template& t = b.tmpl(root);
+  if (input_bits.size() != t.n_in) throw std::invalid_argument("execute: wrong number of input bits");
+  Executor ex{b, std::vector<uint8_t>(1 << 20), 0};
+  if (ex.arena.size() < t.n_wires) ex.arena.resize(t.n_wires);
+  for (uint32_t i = 0; i < t.n_in; i++) ex.arena[WIRE_MIN + i] = input_bits[i] ? 1 : 0;
+  ex.run(root, 0);
+  std::vector<uint8_t> out(t.outs.size());
+  for (size_t j = 0; j < t.outs.size(); j++) out[j] = (t.outs[j] == WIRE_DEAD) ? 0 : ex.arena[t.outs[j]];
+  if (gates_executed) *gates_executed = ex.gates;
+  return out;
+}
 
 FlatStream flatten(const Builder& b, uint32_t root, uint64_t max_gates) {
   FlatStream fs;

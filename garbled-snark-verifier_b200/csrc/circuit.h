@@ -137,4 +137,10 @@ struct FlatStream {
 // stream would exceed `max_gates`.
 FlatStream flatten(const Builder& b, uint32_t root, uint64_t max_gates = (1ull << 31));
 
+// ExecuteMode (src/circuit/modes/execute_mode.rs): plain boolean evaluation of the recorded circuit,
+// walking the template DAG without materialising the flat stream.  Host-side topology self-check
+// (the reference uses the same mode for its gadget tests and pre-checks); NOT a garbling path.
+std::vector<uint8_t> execute(const Builder& b, uint32_t root, const std::vector<uint8_t>& input_bits,
+                             uint64_t* gates_executed = nullptr);
+
 }  // namespace gsv

@@ -8,6 +8,7 @@
 #include <string>
 
 #include "bigconst.h"
+#include "bn254_host.h"
 #include "circuit.h"
 
 namespace gsv {
@@ -89,6 +90,38 @@ Fq6 fq6_mul_montgomery(Builder& c, const Fq6& a, const Fq6& b);
 Fq6 fq6_mul_by_nonresidue(Builder& c, const Fq6& a);
 
 Fq12 fq12_mul_montgomery(Builder& c, const Fq12& a, const Fq12& b);
+
+// ---- gadgets_bn254.cpp: pairing / Groth16 verifier (src/gadgets/bn254/*, src/gadgets/groth16.rs) -----
+struct G1P { Fq x, y, z; };   // G1Projective wires (Montgomery Jacobian coordinates)
+struct G2P { Fq2 x, y, z; };  // G2Projective wires
+U256 mont254(const U256& x);  // x * 2^254 mod p
+Fq fq_constant(const U256& v);
+Wires to_wires(const G1P& p);
+Wires to_wires(const G2P& p);
+G1P g1_from_wires(const Wire* w);
+G2P g2_from_wires(const Wire* w);
+Fq fq_inverse(Builder& c, const Fq& a);
+Fq fq_inverse_montgomery(Builder& c, const Fq& a);
+Fq fq_mul_by_constant_montgomery(Builder& c, const Fq& a, const U256& b);
+Fq fq_exp_by_constant_montgomery(Builder& c, const Fq& a, const U256& exp);
+Fq fq_sqrt_montgomery(Builder& c, const Fq& a);
+Wire fq_is_qnr_montgomery(Builder& c, const Fq& x);
+G1P g1_add_montgomery(Builder& c, const G1P& p, const G1P& q);
+Wire groth16_verify(Builder& c, const std::vector<Wires>& publics, const G1P& a, const G2P& b, const G1P& cc,
+                    const host::VerifyingKey& vk);
+Wire groth16_verify_compressed(Builder& c, const Wires& in, size_t n_public, const host::VerifyingKey& vk);
+uint32_t build_groth16_verify_compressed(Builder& b, const host::VerifyingKey& vk, size_t n_public);
+uint32_t build_fq_inverse(Builder& b);
+uint32_t build_fq_sqrt(Builder& b);
+uint32_t build_fq2_sqrt(Builder& b);
+uint32_t build_g1_add(Builder& b);
+uint32_t build_g1_msm1(Builder& b, const host::G1Affine& base);
+uint32_t build_fq12_square(Builder& b);
+uint32_t build_fq12_cyclotomic_square(Builder& b);
+uint32_t build_fq12_inverse(Builder& b);
+uint32_t build_fq12_frobenius(Builder& b, size_t i);
+uint32_t build_final_exponentiation(Builder& b);
+uint32_t build_miller_loop_groth16(Builder& b, const host::G2Affine& q1, const host::G2Affine& q2);
 
 // ---- named workload circuits (root closures) ---------------------------------------------------
 // Returns the root template index.  Input order = the reference's EncodeInput order.

@@ -138,6 +138,7 @@ gsv_program* finish_program(std::unique_ptr<gsv::Builder> b, uint32_t root, cons
   if (opt) {
     if (opt->max_task_gates) po.max_task_gates = opt->max_task_gates;
     if (opt->max_task_slots) po.max_task_slots = opt->max_task_slots;
+    if (opt->lane_only) po.build_levelised = false;
   }
   auto p = std::make_unique<gsv_program>();
   p->prog = gsv::plan_program(*b, root, po);
@@ -205,6 +206,23 @@ gsv_program* gsv_program_build(const char* circuit, const gsv_plan_options* opt)
     else if (c == "fq_expr") r = gsv::build_fq_expr(*b);
     else if (c == "gate_zoo") r = gsv::build_gate_zoo(*b);
     else if (c.rfind("bn_mul", 0) == 0) r = gsv::build_bn_mul(*b, (size_t)std::stoul(c.substr(6)));
+    else if (c == "fq_inverse") r = gsv::build_fq_inverse(*b);
+    else if (c == "fq_sqrt") r = gsv::build_fq_sqrt(*b);
+    else if (c == "fq2_sqrt") r = gsv::build_fq2_sqrt(*b);
+    else if (c == "g1_add") r = gsv::build_g1_add(*b);
+    else if (c == "g1_msm1") r = gsv::build_g1_msm1(*b, gsv::host::g1_to_affine(gsv::host::g1_mul(gsv::host::g1_from_affine(gsv::host::g1_generator()), gsv::U256(0xC0FFEE))));
+    else if (c == "fq12_square") r = gsv::build_fq12_square(*b);
+    else if (c == "fq12_cyclotomic_square") r = gsv::build_fq12_cyclotomic_square(*b);
+    else if (c == "fq12_inverse") r = gsv::build_fq12_inverse(*b);
+    else if (c.rfind("fq12_frobenius", 0) == 0) r = gsv::build_fq12_frobenius(*b, (size_t)std::stoul(c.substr(14)));
+    else if (c == "final_exponentiation") r = gsv::build_final_exponentiation(*b);
+    else if (c == "miller_loop_groth16" || c == "groth16_verify_compressed") {
+      gsv::host::VerifyingKey vk;
+      gsv::host::Proof pr;
+      gsv::host::synthetic_groth16(7, gsv::U256(424242), vk, pr);
+      if (c == "miller_loop_groth16") r = gsv::build_miller_loop_groth16(*b, gsv::host::g2_neg(vk.gamma_g2), gsv::host::g2_neg(vk.delta_g2));
+      else r = gsv::build_groth16_verify_compressed(*b, vk, 1);
+    }
     else {
       fail(GSV_ERR_INVALID, "unknown circuit: " + c);
       return nullptr;
@@ -217,6 +235,51 @@ gsv_program* gsv_program_build(const char* circuit, const gsv_plan_options* opt)
 }
 
 void gsv_program_destroy(gsv_program* p) { delete p; }
+
+int gsv_program_execute(const gsv_program* p, const uint8_t* input_bits, uint8_t* output_bits, uint64_t* gates_executed) {
+  if (!p || !input_bits || !output_bits) return fail(GSV_ERR_INVALID, "null argument");
+  try {
+    const gsv::Template& rt = p->builder->tmpl(p->root);
+    std::vector<uint8_t> in(input_bits, input_bits + rt.n_in);
+    std::vector<uint8_t> out = gsv::execute(*p->builder, p->root, in, gates_executed);
+    memcpy(output_bits, out.data(), out.size());
+    return GSV_OK;
+  } catch (const std::exception& e) {
+    return fail(GSV_ERR_INVALID, e.what());
+  }
+}
+
+int gsv_groth16_synthetic_inputs(uint64_t public_x, int flip_public, uint8_t* bits, uint32_t n_bits) {
+  if (!bits || n_bits != 1273) return fail(GSV_ERR_INVALID, "need a 1273-bit buffer");
+  try {
+    using namespace gsv::host;
+    VerifyingKey vk;
+    Proof pr;
+    synthetic_groth16(7, gsv::U256(public_x), vk, pr);
+    const gsv::U256 e_sqrt = gsv::U256::from_dec("5472060717959818805561601436314318772174077789324455915672259473661306552146");
+    const gsv::U256& pm = FpCtx::get().p;
+    auto g1flag = [&](const G1Affine& a) { return fp_pow(a.x * a.x * a.x + Fp::from_u64(3), e_sqrt) == a.y; };
+    // mirror of Fq2::sqrt_general_montgomery (fq2.rs:425-447) to learn which root the circuit picks
+    Fp2 y2 = pr.b.x * pr.b.x * pr.b.x + Params::get().g2_b;
+    Fp alpha_sqrt = fp_pow(y2.c0 * y2.c0 + y2.c1 * y2.c1, e_sqrt);
+    Fp half = fp_inv(Fp::from_u64(2));
+    Fp delta = (alpha_sqrt + y2.c0) * half;
+    bool is_qnr = fp_pow(delta, gsv::shr1(gsv::sub(pm, gsv::U256(1)))) == -Fp::from_u64(1);
+    Fp delta_final = is_qnr ? delta - alpha_sqrt : delta;
+    Fp c0 = fp_pow(delta_final, e_sqrt);
+    Fp c1 = fp_inv(c0) * (y2.c1 * half);
+    bool bflag = (c0 == pr.b.y.c0) && (c1 == pr.b.y.c1);
+    size_t o = 0;
+    auto put = [&](const gsv::U256& v) { for (unsigned i = 0; i < 254; i++) bits[o++] = v.bit(i); };
+    put(gsv::U256(flip_public ? public_x + 1 : public_x));
+    put(gsv::mont254(pr.a.x.to_u256())); bits[o++] = g1flag(pr.a);
+    put(gsv::mont254(pr.b.x.c0.to_u256())); put(gsv::mont254(pr.b.x.c1.to_u256())); bits[o++] = bflag;
+    put(gsv::mont254(pr.c.x.to_u256())); bits[o++] = g1flag(pr.c);
+    return GSV_OK;
+  } catch (const std::exception& e) {
+    return fail(GSV_ERR_INVALID, e.what());
+  }
+}
 
 int gsv_program_get_info(const gsv_program* p, gsv_program_info* out) {
   if (!p || !out) return fail(GSV_ERR_INVALID, "null argument");
@@ -500,7 +563,7 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
       throw std::runtime_error("worker_threads must be 64/128/256/512/1024");
     // commitment consumers: one chain warp per CHAIN_INST instances, packed a few warps per SMSP
     // onto dedicated trailing CTAs (SMs) of the persistent grid
-    const uint32_t chain_warps_total = (s->ct_mode != GSV_CT_NONE) ? (s->B + CHAIN_INST - 1) / CHAIN_INST : 0;
+    const uint32_t chain_warps_total = (s->ct_mode == GSV_CT_COMMIT || s->ct_mode == GSV_CT_KEEP) ? (s->B + CHAIN_INST - 1) / CHAIN_INST : 0;
     uint32_t n_chain = 0;  // chain warps per chain CTA
     s->n_chain_ctas = 0;
     if (chain_warps_total) {
@@ -579,7 +642,7 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
       const uint64_t budget = (uint64_t)(free_b * 0.85);
       uint64_t ring = std::max<uint64_t>(budget / ((uint64_t)s->B * 16), 1);
       if (opt->ct_ring_log2) ring = std::min<uint64_t>(ring, 1ull << opt->ct_ring_log2);
-      if (s->ct_mode == GSV_CT_KEEP || ring >= total) {
+      if (s->ct_mode == GSV_CT_KEEP || s->ct_mode == GSV_CT_KEEP_RAW || ring >= total) {
         if (total * s->B * 16 > (uint64_t)(free_b * 0.9)) throw std::runtime_error("ciphertext stream does not fit in HBM; use GSV_CT_COMMIT");
         s->ct_ring = 0;
         s->d_ct.alloc((size_t)total * s->B);
@@ -634,7 +697,7 @@ int gsv_garble_batch(gsv_session* s, int hasher, const uint64_t* seeds, gsv_garb
     CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
     // ---- results
     if (res->delta) CUDA_TRY(cudaMemcpyAsync(res->delta, s->d_delta.p, (size_t)B * 16, cudaMemcpyDeviceToHost, s->stream));
-    if (res->ct_commit && s->ct_mode != GSV_CT_NONE)
+    if (res->ct_commit && (s->ct_mode == GSV_CT_COMMIT || s->ct_mode == GSV_CT_KEEP))
       CUDA_TRY(cudaMemcpyAsync(res->ct_commit, s->d_commit.p, (size_t)B * 16, cudaMemcpyDeviceToHost, s->stream));
     auto gather = [&](const std::vector<uint32_t>& slots, uint8_t* host_out) {
       if (!host_out || slots.empty()) return;
@@ -664,7 +727,7 @@ int gsv_garble_batch(gsv_session* s, int hasher, const uint64_t* seeds, gsv_garb
     cudaEventElapsedTime(&res->ms_total, s->ev[0], s->ev[3]);
     res->n_ciphertexts = g.total_ct;
     res->n_launches = launches;
-    s->ct_valid = (s->ct_mode == GSV_CT_KEEP || s->ct_mode == GSV_CT_COMMIT);
+    s->ct_valid = (s->ct_mode != GSV_CT_NONE);
     return GSV_OK;
   } catch (const std::exception& e) {
     return fail(GSV_ERR_CUDA, e.what());
@@ -749,10 +812,12 @@ int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io) {
     CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
     // the evaluator's own chain hash over what it consumed (FileSource hashes while reading)
     const uint64_t used = std::min<uint64_t>(ct_avail, g.total_ct);
+    if (io->ct_commit) {
     CUDA_TRY(cudaFuncSetAttribute(k_chain<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
     k_chain<0><<<(B + 31) / 32, 32, AES_TABLE_BYTES, s->stream>>>(s->d_ct.p, used, B, s->d_commit.p);
     CUDA_TRY(cudaGetLastError());
     launches++;
+    }
     CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
     uint32_t ctrl[4] = {0, 0, 0, 0};
     CUDA_TRY(cudaMemcpyAsync(ctrl, s->d_ctrl.p, 16, cudaMemcpyDeviceToHost, s->stream));

@@ -43,6 +43,8 @@ Task compile_flat(const FlatStream& fs, const std::string& key, const PlanOption
   t.n_live = n_live;
   t.n_levels = depth;
 
+  if (!opt.build_levelised) goto lane_form;
+  {
   // ---- ALAP levels: as late as the consumers allow; sinks (outputs, unread wires) at `depth`
   if (opt.alap) {
     std::vector<uint32_t> req(nw, depth);  // latest level at which the wire must be available
@@ -136,15 +138,27 @@ Task compile_flat(const FlatStream& fs, const std::string& key, const PlanOption
   }
   t.level_off[depth] = (uint32_t)t.gates.size();
   t.n_slots = next_slot;
-
+  for (size_t j = 0; j < fs.outputs.size(); j++) {
+    uint32_t o = fs.outputs[j];
+    if (o == WIRE_DEAD || o < first_def) continue;
+    t.out_slot.push_back((uint16_t)slot[o]);
+  }
+  }
+lane_form:
+  if (!opt.build_levelised) {
+    t.n_levels = 0;
+    t.n_slots = 2;
+    t.level_off.assign(1, 0);
+    t.in_slot.assign(fs.n_inputs, 0xFFFF);
+  }
   // ---- produced outputs
   for (size_t j = 0; j < fs.outputs.size(); j++) {
     uint32_t o = fs.outputs[j];
     if (o == WIRE_DEAD || o < first_def) continue;  // dead / constant / passthrough input
     t.out_pos.push_back((uint32_t)j);
-    t.out_slot.push_back((uint16_t)slot[o]);
   }
   t.n_out = (uint32_t)t.out_pos.size();
+  if (!opt.build_levelised) t.out_slot.assign(t.n_out, 0);
 
   // ---- lane-mode form: emission order, slots freed right after the last read (LIFO reuse)
   {
@@ -216,16 +230,31 @@ struct Planner {
   // loose-gate runs of structural templates: (template, first item) -> task index
   std::map<std::pair<uint32_t, uint32_t>, uint32_t> loose_task;
   std::vector<int64_t> producer;  // global wire -> producing call (-1: circuit input / constant)
+  std::vector<uint64_t> mult;     // occurrences of each template in the flattened circuit
   uint32_t next_global = 0;
   uint64_t gid = 0, ct = 0;
 
-  Planner(const Builder& b_, const PlanOptions& o) : b(b_), opt(o), kind(b_.n_templates(), -2) {}
+  Planner(const Builder& b_, const PlanOptions& o, uint32_t root) : b(b_), opt(o), kind(b_.n_templates(), -2) {
+    // children are created before their parents, so a descending sweep propagates multiplicities
+    mult.assign(b.n_templates(), 0);
+    mult[root] = 1;
+    for (uint32_t ti = (uint32_t)b.n_templates(); ti-- > 0;) {
+      if (!mult[ti]) continue;
+      for (const CallRec& c : b.tmpl(ti).calls) mult[c.tmpl] += mult[ti];
+    }
+    // a circuit that fits one task needs no sharing analysis
+    if (b.tmpl(root).total_gates <= opt.max_task_gates) opt.min_shared_calls = 0;
+  }
 
   int64_t classify(uint32_t ti) {
     if (kind[ti] != -2) return kind[ti];
     const Template& t = b.tmpl(ti);
     bool can_split = !t.calls.empty();
     if (t.total_gates > opt.max_task_gates && can_split) return kind[ti] = -1;
+    // Sharing-aware cut: a component that occurs only a few times (e.g. a multiplier by one
+    // vk-specific constant) but is built from widely shared children (bigint::add) is expanded into
+    // those children, so the device program holds each distinct gate list once.
+    if (can_split && t.total_gates > opt.small_task_gates && mult[ti] < opt.min_shared_calls) return kind[ti] = -1;
     if (t.total_gates == 0) {
       // pure re-wiring component (e.g. add_constant(0)): an empty task
       Task e;
@@ -241,10 +270,9 @@ struct Planner {
     }
     FlatStream fs = flatten(b, ti, std::max<uint64_t>(opt.max_task_gates, t.total_gates) + 1);
     Task task = compile_flat(fs, t.key, opt);
-    if (task.n_slots > opt.max_task_slots && can_split) return kind[ti] = -1;
-    if (task.n_slots > opt.max_task_slots)
-      throw std::length_error("unsplittable component exceeds the slot budget: " + t.key + " (" +
-                              std::to_string(task.n_slots) + " slots)");
+    if (opt.build_levelised && task.n_slots > opt.max_task_slots && can_split) return kind[ti] = -1;
+    // an unsplittable body above the slot budget stays a task: it runs in lane mode only (the
+    // session refuses the levelised mode when max_task_slots does not fit shared memory)
     prog.tasks.push_back(std::move(task));
     return kind[ti] = (int64_t)prog.tasks.size() - 1;
   }
@@ -382,8 +410,6 @@ struct Planner {
         if (lt != loose_task.end()) task_idx = lt->second;
         else {
           Task task = compile_flat(fs, t.key + "@run" + std::to_string(k), opt);
-          if (task.n_slots > opt.max_task_slots)
-            throw std::length_error("loose gate run exceeds the slot budget in " + t.key);
           prog.tasks.push_back(std::move(task));
           task_idx = (uint32_t)prog.tasks.size() - 1;
           loose_task.emplace(key, task_idx);
@@ -446,7 +472,7 @@ Task compile_task(const Builder& b, uint32_t tmpl, const PlanOptions& opt) {
 }
 
 Program plan_program(const Builder& b, uint32_t root, const PlanOptions& opt) {
-  Planner p(b, opt);
+  Planner p(b, opt, root);
   const Template& rt = b.tmpl(root);
   p.prog.n_inputs = rt.n_in;
   p.next_global = WIRE_MIN + rt.n_in;
@@ -473,7 +499,101 @@ Program plan_program(const Builder& b, uint32_t root, const PlanOptions& opt) {
   }
   Program& prog = p.prog;
   prog.output_slots = outs;
-  prog.n_global_slots = p.next_global;  // v1: one slot per inter-task wire (no recycling)
+  prog.n_global_slots = p.next_global;
+  if (opt.reuse_distance > 0 && !prog.calls.empty()) {
+    // ---- global slot recycling.  Inter-task wires are SSA so far; pack them into recycled slots,
+    // one contiguous BLOCK per call (its produced wires), freed after the block's last reader.
+    // A call that takes over a block lists the readers of the previous occupant as WAR
+    // dependencies.  Blocks are only recycled `reuse_distance` calls after their last reader, so
+    // those dependencies are almost always satisfied long before the new owner starts.
+    const uint32_t n_calls = (uint32_t)prog.calls.size();
+    const uint32_t first_wire = WIRE_MIN + prog.n_inputs;
+    const uint32_t n_w = p.next_global;
+    std::vector<uint8_t> pinned(n_w, 0);
+    for (uint32_t o : outs)
+      if (o != WIRE_DEAD && o < n_w) pinned[o] = 1;
+    std::vector<std::vector<uint32_t>> readers(n_calls);  // producer call -> reader calls (ascending)
+    std::vector<uint32_t> block_last(n_calls, 0);
+    std::vector<uint8_t> block_pinned(n_calls, 0);
+    for (uint32_t c = 0; c < n_calls; c++) {
+      const Call& call = prog.calls[c];
+      const Task& task = prog.tasks[call.task];
+      block_last[c] = std::max(block_last[c], c);
+      for (uint32_t i = 0; i < task.n_in; i++) {
+        if (task.seq_in_slot[i] == 0xFFFF) continue;
+        uint32_t w = prog.call_slots[call.in_off + i];
+        if (w < first_wire) continue;
+        uint32_t pc = (uint32_t)p.producer[w];
+        if (readers[pc].empty() || readers[pc].back() != c) readers[pc].push_back(c);
+        block_last[pc] = std::max(block_last[pc], c);
+      }
+      for (uint32_t k = 0; k < task.n_out; k++)
+        if (pinned[prog.call_slots[call.out_off + k]]) block_pinned[c] = 1;
+    }
+    struct FreeBlock { uint32_t base, producer, free_at; };
+    std::map<uint32_t, std::vector<FreeBlock>> pool;       // size class -> FIFO (push back, pop front index)
+    std::map<uint32_t, size_t> pool_head;
+    std::vector<std::vector<uint32_t>> release_at(n_calls + 1);
+    std::vector<uint32_t> slot_of(n_w, UNSET), block_base(n_calls, 0), block_size(n_calls, 0);
+    for (uint32_t w = 0; w < first_wire; w++) slot_of[w] = w;
+    uint32_t next_slot = first_wire;
+    std::vector<std::vector<uint32_t>> war(n_calls);
+    for (uint32_t c = 0; c < n_calls; c++) {
+      for (uint32_t pc : release_at[c]) pool[block_size[pc]].push_back(FreeBlock{block_base[pc], pc, c});
+      const Call& call = prog.calls[c];
+      const Task& task = prog.tasks[call.task];
+      // unique produced wires of this call, in output order
+      std::vector<uint32_t> uniq;
+      for (uint32_t k = 0; k < task.n_out; k++) {
+        uint32_t w = prog.call_slots[call.out_off + k];
+        if (slot_of[w] == UNSET) {
+          slot_of[w] = 0;  // mark
+          uniq.push_back(w);
+        }
+      }
+      const uint32_t size = (uint32_t)uniq.size();
+      if (size == 0) continue;
+      uint32_t base;
+      auto& q = pool[size];
+      size_t& head = pool_head[size];
+      if (head < q.size() && q[head].free_at + opt.reuse_distance <= c) {
+        base = q[head].base;
+        const uint32_t prev = q[head].producer;
+        war[c] = readers[prev];
+        if (war[c].empty()) war[c].push_back(prev);  // never read: at least wait for the old writer
+        head++;
+      } else {
+        base = next_slot;
+        next_slot += size;
+      }
+      for (uint32_t k = 0; k < size; k++) slot_of[uniq[k]] = base + k;
+      block_base[c] = base;
+      block_size[c] = size;
+      // high-fan-out blocks (e.g. the affine G1 points every line evaluation reads) are never recycled:
+      // their reader list would become the next owner's dependency list
+      if (!block_pinned[c] && readers[c].size() <= 32) release_at[std::min(n_calls, block_last[c] + 1)].push_back(c);
+    }
+    // rewrite wires -> slots, merge WAR dependencies
+    for (uint32_t& w : prog.call_slots) w = slot_of[w] == UNSET ? 0u : slot_of[w];
+    for (uint32_t& o : prog.output_slots)
+      if (o != WIRE_DEAD) o = slot_of[o];
+    std::vector<uint32_t> deps;
+    deps.reserve(prog.deps.size() + n_calls);
+    prog.max_call_deps = 0;
+    for (uint32_t c = 0; c < n_calls; c++) {
+      Call& call = prog.calls[c];
+      std::vector<uint32_t> d(prog.deps.begin() + call.dep_off, prog.deps.begin() + call.dep_off + call.n_deps);
+      d.insert(d.end(), war[c].begin(), war[c].end());
+      std::sort(d.begin(), d.end());
+      d.erase(std::unique(d.begin(), d.end()), d.end());
+      call.dep_off = (uint32_t)deps.size();
+      call.n_deps = (uint32_t)d.size();
+      deps.insert(deps.end(), d.begin(), d.end());
+      prog.max_call_deps = std::max(prog.max_call_deps, call.n_deps);
+    }
+    prog.deps.swap(deps);
+    prog.n_global_slots = next_slot;
+  }
   prog.total_gates = p.gid;
   prog.total_ct = p.ct;
   prog.total_live = rt.total_live;

@@ -90,7 +90,11 @@ struct PlanOptions {
   uint64_t max_task_gates = 600000;  // templates above this are structural (split into children)
   uint32_t max_task_slots = 1536;    // shared-memory label slots per instance
   bool alap = true;                  // schedule gates as late as possible (smaller live sets)
-  uint32_t reuse_distance = 0;       // 0: never recycle global slots; else min #calls before reuse
+  uint32_t reuse_distance = 512;     // global slot blocks are recycled no sooner than this many calls
+                                     // after their last reader (0: never recycle)
+  uint64_t small_task_gates = 8192;  // bodies up to this size are tasks even when they occur once
+  uint64_t min_shared_calls = 4;     // larger bodies become tasks only if they occur this often
+  bool build_levelised = true;       // false: lane-mode form only (large circuits)
 };
 
 // Cuts, flattens, levelises and packs.  Throws on circuits it cannot plan.

@@ -67,7 +67,8 @@ enum gsv_gate_type {
 enum gsv_ct_mode {
   GSV_CT_NONE = 0,   /* `()` handler: ciphertexts are dropped (src/circuit/mod.rs:172-178)       */
   GSV_CT_COMMIT = 1, /* AESAccumulatingHash: bit-exact chain commitment, stream not kept         */
-  GSV_CT_KEEP = 2    /* commitment + the stream stays in HBM for evaluation / read-back / P2P     */
+  GSV_CT_KEEP = 2,   /* commitment + the stream stays in HBM for evaluation / read-back / P2P     */
+  GSV_CT_KEEP_RAW = 3 /* stream kept, commitment not computed (channel::Sender<S> handler)          */
 };
 
 const char* gsv_last_error(void);
@@ -95,7 +96,7 @@ void gsv_ctx_component(gsv_ctx* ctx, const char* key, const uint32_t* inputs, ui
 typedef struct {
   uint64_t max_task_gates; /* 0 = default (600000) */
   uint32_t max_task_slots; /* 0 = default (1536 shared-memory label slots per instance) */
-  uint32_t reserved;
+  uint32_t lane_only;      /* 1 = build only the lane-mode (emission order) task form: large circuits */
 } gsv_plan_options;
 
 /* Records `root(ctx, user, inputs[n_inputs], outputs[n_outputs])` (CircuitBuilder::run_streaming,
@@ -104,8 +105,22 @@ gsv_program* gsv_program_record(const char* name, uint32_t n_inputs, uint32_t n_
                                 gsv_body_fn root, void* user, const gsv_plan_options* opt);
 /* The named workload circuits built by the library's own C++ gadget restatement
  * (src/gadgets/**): "fq12_mul", "fq6_mul", "fq2_mul", "fq_mul", "fq_add", "fq_expr",
- * "gate_zoo", "bn_mul<N>". */
+ * "gate_zoo", "bn_mul<N>", "fq_inverse", "fq_sqrt", "fq2_sqrt", "g1_add", "g1_msm1", "fq12_square",
+ * "fq12_cyclotomic_square", "fq12_inverse", "fq12_frobenius<i>", "final_exponentiation",
+ * "miller_loop_groth16", and "groth16_verify_compressed" (src/gadgets/groth16.rs:250-268 with one
+ * public input over the deterministic synthetic verifying key of gsv_groth16_synthetic_inputs). */
 gsv_program* gsv_program_build(const char* circuit, const gsv_plan_options* opt);
+
+/* ExecuteMode (src/circuit/modes/execute_mode.rs): plain boolean evaluation of the recorded
+ * topology on the host.  A topology self-check (what the reference's gadget tests do), not a
+ * garbling path.  input_bits: n_inputs bytes (0/1), output_bits: n_outputs bytes. */
+int gsv_program_execute(const gsv_program* p, const uint8_t* input_bits, uint8_t* output_bits,
+                        uint64_t* gates_executed);
+
+/* Input bits (EncodeInput order, 1273 wires: public | a.x a.flag | b.x.c0 b.x.c1 b.flag | c.x c.flag,
+ * src/gadgets/groth16.rs:425-490) of a synthetic proof for "groth16_verify_compressed":
+ * the proof verifies for `public_x`; pass flip_public = 1 to get the rejecting variant. */
+int gsv_groth16_synthetic_inputs(uint64_t public_x, int flip_public, uint8_t* bits, uint32_t n_bits);
 void gsv_program_destroy(gsv_program* p);
 
 typedef struct {

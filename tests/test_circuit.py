@@ -163,3 +163,67 @@ def test_planner_invariants(gsv):
     assert small.n_calls == 507 and small.n_gates == p.n_gates and small.n_ciphertexts == p.n_ciphertexts
     one = gsv.Program("fq_mul", max_task_slots=8192, max_task_gates=10**7)
     assert one.n_calls == 1  # whole circuit as a single task
+
+
+# ---- pairing / Groth16 gadgets (src/gadgets/bn254/*, src/gadgets/groth16.rs): functional checks through
+# the host ExecuteMode walker, the role arkworks plays in the reference's gadget tests
+def _mont_bits(x):
+    return bn.bits_le(bn.to_mont(x))
+
+
+def _from_mont(bits):
+    return bn.from_bits(bits) * pow(bn.R, -1, bn.P) % bn.P
+
+
+def test_fq_inverse_and_sqrt_functional(gsv):
+    inv = gsv.Program("fq_inverse", lane_only=True)
+    assert inv.n_gates == 23200543
+    for x in (1, 123456789, bn.P - 2):
+        assert _from_mont(inv.execute(_mont_bits(x))) == pow(x, -1, bn.P)
+    sq = gsv.Program("fq_sqrt", lane_only=True)
+    y = 987654321
+    r = _from_mont(sq.execute(_mont_bits(y * y % bn.P)))
+    assert r * r % bn.P == y * y % bn.P
+
+
+def test_fq12_square_functional(gsv):
+    p = gsv.Program("fq12_square", lane_only=True)
+    rng = random.Random(31)
+    a = bn.rand_fq12(rng)
+    assert list(p.execute(bn.fq12_bits_mont(a))) == bn.fq12_bits_mont(bn.fq12_mul(a, a))
+
+
+def test_g1_add_functional(gsv):
+    """G1Projective::add_montgomery (g1.rs:159-235) against affine chord addition."""
+    p = gsv.Program("g1_add", lane_only=True)
+
+    def aff_add(p1, p2):
+        lam = (p2[1] - p1[1]) * pow(p2[0] - p1[0], -1, bn.P) % bn.P
+        x = (lam * lam - p1[0] - p2[0]) % bn.P
+        return x, (lam * (p1[0] - x) - p1[1]) % bn.P
+
+    g1, g2 = (1, 2), None
+    lam = 3 * pow(4, -1, bn.P) % bn.P  # 2G
+    x2 = (lam * lam - 2) % bn.P
+    g2 = (x2, (lam * (1 - x2) - 2) % bn.P)
+    g3 = aff_add(g1, g2)
+    bits = []
+    for pt in (g2, g3):
+        bits += _mont_bits(pt[0]) + _mont_bits(pt[1]) + _mont_bits(1)
+    out = p.execute(bits)
+    x, y, z = (_from_mont(out[i * 254:(i + 1) * 254]) for i in range(3))
+    zi = pow(z, -1, bn.P)
+    assert (x * zi * zi % bn.P, y * zi * zi * zi % bn.P) == aff_add(g2, g3)
+
+
+def test_groth16_verifier_accepts_and_rejects(gsv):
+    """groth16_verify_compressed (groth16.rs:250-268) over a synthetic key: 11.46 G gates walked in
+    ExecuteMode; the valid proof yields 1, a different public input yields 0 (the reference's
+    true / bit-flip cases, groth16.rs:510-604).  The published 11 174 708 821 is for the reference's
+    own vk; constant multipliers make the count vk dependent."""
+    p = gsv.Program("groth16_verify_compressed", lane_only=True)
+    assert p.n_inputs == 1273 and p.n_outputs == 1
+    assert 11.0e9 < p.n_gates < 11.8e9 and 0.25 < p.n_ciphertexts / p.n_gates < 0.28
+    assert p.n_global_slots < 150_000  # the reference's live-wire capacity (cut_and_choose/groth16.rs:17)
+    assert list(p.execute(gsv.groth16_synthetic_inputs(424242, False))) == [1]
+    assert list(p.execute(gsv.groth16_synthetic_inputs(424242, True))) == [0]

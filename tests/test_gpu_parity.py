@@ -260,3 +260,16 @@ def test_cut_and_choose_commit_records(gsv, orc, circuit):
             assert bytes(rec.output_commits()[i, j, 1]) == orc.commit_label(o0)
         assert bytes(rec.constant_commits()[i, 0]) == orc.commit_label(xor(ref["true_label0"], d))
         assert bytes(rec.constant_commits()[i, 1]) == orc.commit_label(ref["false_label0"])
+
+
+@pytest.mark.parametrize("name,B,mode", [("fq_inverse", 32, 2), ("fq_inverse", 4, 1), ("g1_add", 64, 2), ("fq12_square", 4, 1)])
+def test_pairing_gadget_circuits_match_oracle(gsv, orc, circuit, name, B, mode):
+    """Sub-circuits of the Groth16 verifier (inverse: 32 k calls, recycled global slots with WAR
+    dependencies): commitment and output labels vs the oracle in both execution modes."""
+    p, st = circuit(name)
+    seeds = [0, 42, 99, 777] + list(range(50, 50 + B - 4))
+    res = gsv.Session(p, B, ct_mode=gsv.CT_COMMIT, exec_mode=mode, group=2 if mode == 1 else 0).garble(seeds, gsv.HASH_AES)
+    for i in (0, 3, B - 1):
+        ref = st.garble(orc.HASH_AES, seeds[i], want_ct=False)
+        assert bytes(res.ct_commit[i]) == ref["ct_commit"], (name, i)
+        assert np.array_equal(res.output_label0[i], ref["output_label0"])
