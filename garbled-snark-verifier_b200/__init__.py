@@ -304,7 +304,7 @@ class Session:
 
     def evaluate(self, hasher: int, true_label: np.ndarray, false_label: np.ndarray,
                  input_active: np.ndarray, input_bits: np.ndarray,
-                 ct_streams: Optional[Sequence[np.ndarray]] = None) -> EvalResult:
+                 ct_streams: Optional[Sequence[np.ndarray]] = None, want_commit: bool = True) -> EvalResult:
         lib = load_library()
         B, p = self.n_instances, self.program
         tl = np.ascontiguousarray(true_label, np.uint8).reshape(B, 16)
@@ -325,7 +325,7 @@ class Session:
             arr = (C.c_void_p * B)(*[k.ctypes.data for k in keep])
             io.ct_streams = C.cast(arr, C.POINTER(C.c_void_p))
             io.ct_stream_len = lens.pop()
-        io.output_active, io.output_bits, io.ct_commit = _ptr(oa), _ptr(ob), _ptr(cc)
+        io.output_active, io.output_bits, io.ct_commit = _ptr(oa), _ptr(ob), _ptr(cc if want_commit else None)
         _check(lib.gsv_evaluate_batch(self._h, hasher, C.byref(io)))
         return EvalResult(oa, ob, cc, io.ms_evaluate, io.ms_commit, io.ms_total, io.n_launches)
 

@@ -34,7 +34,7 @@ else:
         act = r.input_label0.copy()
         m = bits.astype(bool)
         act[m] ^= np.broadcast_to(r.delta[:, None, :], act.shape)[m]
-        ev = s.evaluate(g.HASH_AES, r.true_label1, r.false_label0, act, bits)
+        ev = s.evaluate(g.HASH_AES, r.true_label1, r.false_label0, act, bits, want_commit=False)
         want_bit = 0 if flip else 1
         sel = r.output_label0[:, 0, :] ^ (r.delta * want_bit)
         ok = bool(np.all(ev.output_bits[:, 0] == want_bit) and np.array_equal(ev.output_active[:, 0, :], sel))

@@ -273,3 +273,23 @@ def test_pairing_gadget_circuits_match_oracle(gsv, orc, circuit, name, B, mode):
         ref = st.garble(orc.HASH_AES, seeds[i], want_ct=False)
         assert bytes(res.ct_commit[i]) == ref["ct_commit"], (name, i)
         assert np.array_equal(res.output_label0[i], ref["output_label0"])
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_keep_raw_stream_evaluates_without_commit(gsv, orc, circuit, mode):
+    """GSV_CT_KEEP_RAW: the stream stays in HBM for the evaluator, no chain is folded on either side
+    (the `()` ciphertext handler / evaluator without a commitment check)."""
+    p, st = circuit("fq_mul")
+    B = 4
+    seeds = [5, 6, 7, 8]
+    sess = gsv.Session(p, B, ct_mode=gsv.CT_KEEP_RAW, exec_mode=mode, group=2 if mode == 1 else 0)
+    res = sess.garble(seeds, gsv.HASH_AES)
+    bits = np.random.default_rng(11).integers(0, 2, (B, p.n_inputs), dtype=np.uint8)
+    act = _eval_inputs(res, bits)
+    ev = sess.evaluate(gsv.HASH_AES, res.true_label1, res.false_label0, act, bits, want_commit=False)
+    for i in range(B):
+        ref = st.garble(orc.HASH_AES, seeds[i])
+        assert np.array_equal(sess.read_ciphertexts(i), ref["cts"])
+        o = st.evaluate(orc.HASH_AES, bytes(res.true_label1[i]), bytes(res.false_label0[i]), act[i], bits[i], ref["cts"])
+        assert np.array_equal(ev.output_active[i], o["output_active"])
+        assert np.array_equal(ev.output_bits[i], o["output_bits"])
