@@ -26,6 +26,7 @@ CT_NONE = 0
 CT_COMMIT = 1
 CT_KEEP = 2
 CT_KEEP_RAW = 3
+CT_COMMIT_HOST = 4
 WIRE_UNREACHABLE = 0xFFFFFFFF
 
 GATE_NAMES = ["And", "Nand", "Nimp", "Imp", "Ncimp", "Cimp", "Nor", "Or", "Xor", "Xnor", "Not"]
@@ -56,6 +57,8 @@ class _ProgramInfo(C.Structure):
         ("max_task_levels", C.c_uint32),
         ("max_call_deps", C.c_uint32),
         ("sum_call_levels", C.c_uint64),
+        ("critical_path_gates", C.c_uint64),
+        ("critical_path_levels", C.c_uint64),
     ]
 
 
@@ -133,6 +136,7 @@ def load_library() -> C.CDLL:
     lib.gsv_program_flat_stream.restype = C.c_int64
     lib.gsv_program_flat_stream.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_uint64, C.c_void_p, C.c_void_p]
     lib.gsv_program_execute.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.gsv_program_execute_plan.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.gsv_groth16_synthetic_inputs.argtypes = [C.c_uint64, C.c_int, C.c_void_p, C.c_uint32]
     lib.gsv_session_create.restype = C.c_void_p
     lib.gsv_session_create.argtypes = [C.c_void_p, C.POINTER(_SessionOptions)]
@@ -183,6 +187,8 @@ class Program:
         self.n_global_slots = info.n_global_slots
         self.max_task_slots = info.max_task_slots
         self.max_task_levels = info.max_task_levels
+        self.critical_path_gates = info.critical_path_gates
+        self.critical_path_levels = info.critical_path_levels
         self.max_call_deps = info.max_call_deps
         self.sum_call_levels = info.sum_call_levels
 
@@ -198,6 +204,14 @@ class Program:
         ob = np.zeros(self.n_outputs, np.uint8)
         n = C.c_uint64(0)
         _check(lib.gsv_program_execute(self._h, _ptr(ib), _ptr(ob), C.byref(n)))
+        return ob
+
+    def execute_plan(self, input_bits, lane_form: bool = False) -> np.ndarray:
+        """Boolean evaluation of the PLANNED program (tasks / calls / recycled slots): planner self-check."""
+        lib = load_library()
+        ib = np.ascontiguousarray(input_bits, np.uint8).reshape(self.n_inputs)
+        ob = np.zeros(self.n_outputs, np.uint8)
+        _check(lib.gsv_program_execute_plan(self._h, 1 if lane_form else 0, _ptr(ib), _ptr(ob)))
         return ob
 
     def flat_stream(self):
@@ -328,6 +342,19 @@ class Session:
         io.output_active, io.output_bits, io.ct_commit = _ptr(oa), _ptr(ob), _ptr(cc if want_commit else None)
         _check(lib.gsv_evaluate_batch(self._h, hasher, C.byref(io)))
         return EvalResult(oa, ob, cc, io.ms_evaluate, io.ms_commit, io.ms_total, io.n_launches)
+
+
+def host_chain_fold(h: np.ndarray, blocks: np.ndarray, instance_major: bool = False) -> np.ndarray:
+    """Host half of CT_COMMIT_HOST: blocks[n_pos, n_inst, 16] (or [n_inst, n_pos, 16] when
+    instance_major) folded into h[n_inst, 16] (returns a copy)."""
+    lib = load_library()
+    blocks = np.ascontiguousarray(blocks, np.uint8)
+    n_inst, n_pos = (blocks.shape[0], blocks.shape[1]) if instance_major else (blocks.shape[1], blocks.shape[0])
+    out = np.ascontiguousarray(h, np.uint8).reshape(n_inst, 16).copy()
+    lib.gsv_host_chain_fold.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
+    ps, is_ = (1, n_pos) if instance_major else (n_inst, 1)
+    _check(lib.gsv_host_chain_fold(_ptr(out), _ptr(blocks), ps, is_, n_pos, n_inst))
+    return out
 
 
 def groth16_synthetic_inputs(public_x: int = 424242, flip_public: bool = False) -> np.ndarray:

@@ -24,7 +24,7 @@
 namespace gsvdev {
 
 struct DevTaskD {
-  uint32_t gate_off, level_off, n_levels, n_in, n_out, n_slots, in_slot_off, out_slot_off;
+  uint32_t gate_off, n_gates, n_levels, n_in, n_out, n_slots, in_slot_off, out_slot_off;
   uint32_t n_ct;
   uint32_t seq_gate_off, n_seq_gates, n_seq_slots;  // lane-mode (emission order) form
 };
@@ -35,7 +35,6 @@ struct DevCallD {
 
 struct EngineParams {
   const uint4* gates;  // gsv::DevGate records as uint4
-  const uint32_t* level_off;
   const uint16_t* in_slot;
   const uint16_t* out_slot;
   const DevTaskD* tasks;
@@ -46,8 +45,16 @@ struct EngineParams {
   uint8_t* vals;        // evaluate: plaintext bit per label, same indexing
   const uint4* delta;   // [B]
   uint4* ct;            // [ct position][B]  (garble: written, evaluate: read)
+  unsigned long long ct_pos_stride, ct_inst_stride;  // garble stores: (B, 1); GSV_CT_COMMIT_HOST keeps
+                                                     // the ring instance-major, (1, ring capacity)
   uint32_t* flags;      // [call][group] == epoch when done
-  uint32_t* next_item;
+  // dataflow scheduler: ready queue of work items (call * n_groups + group)
+  unsigned long long* queue;  // [1 << queue_log2]: (round + 1) << 32 | item
+  uint32_t* pending;          // [item]: producers / slot owners still running
+  const uint32_t* succ_off;   // [n_calls + 1] CSR of the reverse dependency edges
+  const uint32_t* succ;
+  uint32_t* sched;            // [0] queue head, [1] queue tail, [2] items completed
+  uint32_t queue_log2;
   uint32_t* error_flag;       // evaluate: set to 1 on ciphertext exhaustion
   unsigned long long* chain_progress;  // [chain warp] ciphertexts folded so far
   uint4* commit;        // [B] chain result
@@ -62,6 +69,9 @@ struct EngineParams {
   uint32_t epoch;
   uint32_t write_ct;          // garble: store ciphertexts
   uint32_t G;                 // instances per group (32 in lane mode)
+  // GSV_CT_COMMIT_HOST: the (single) chain CTA only publishes how much of the stream is complete
+  uint32_t host_chain;
+  unsigned long long* host_ready;  // mapped host memory: ciphertexts complete in emission order
   // lane mode
   const uint4* seq_gates;
   const uint16_t* seq_in_slot;
@@ -70,6 +80,22 @@ struct EngineParams {
   uint8_t* scratch_vals;
   uint32_t scratch_stride;    // scratch slots per worker warp
 };
+
+// Gate-record staging of the levelised mode: a task's records are contiguous in level order, so
+// they are streamed global -> shared with cp.async in chunks of GATE_CHUNK records, GATE_CHUNKS
+// chunks in flight per worker, independent of the level structure (levels are <= GATE_CHUNK wide
+// and carry their width in their first record).  The level loop then never waits on L2.
+constexpr uint32_t GATE_CHUNK = 128;
+constexpr uint32_t GATE_CHUNKS = 4;
+constexpr uint32_t GATE_RING = GATE_CHUNK * GATE_CHUNKS;  // records (8 KB) per worker
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 __device__ __forceinline__ void named_bar(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -185,6 +211,89 @@ __device__ __forceinline__ void chain_warp(const EngineParams& p, const uint32_t
   if (active) reinterpret_cast<uint32_t*>(p.commit + first + qi)[col] = h;
 }
 
+// ---- dataflow scheduler.  A work item (call, instance group) enters the ready queue when its last
+// producer (RAW) or last reader of the global slots it will overwrite (WAR) completes; workers pop
+// tickets in FIFO order.  Unlike claiming items in emission order, a worker never sits on an item
+// whose inputs are not there, so all of the circuit's call-level parallelism is exposed however many
+// instance groups share the workers.  Each slot of the circular queue is tagged with its round.
+constexpr uint32_t SCHED_DONE = 0xFFFFFFFFu;
+__device__ __forceinline__ void sched_push(const EngineParams& p, uint32_t item) {
+  const uint32_t pos = atomicAdd(p.sched + 1, 1u);
+  const unsigned long long e = ((unsigned long long)((pos >> p.queue_log2) + 1u) << 32) | item;
+  st_release64(p.queue + (pos & ((1u << p.queue_log2) - 1u)), e);
+}
+// one thread: next ready item, or SCHED_DONE once every item has completed
+__device__ __forceinline__ uint32_t sched_pop(const EngineParams& p, uint32_t n_items) {
+  const uint32_t t = atomicAdd(p.sched, 1u);
+  const unsigned long long* slot = p.queue + (t & ((1u << p.queue_log2) - 1u));
+  const uint32_t want = (t >> p.queue_log2) + 1u;
+  for (;;) {
+    const unsigned long long e = ld_acquire64(slot);
+    if ((uint32_t)(e >> 32) == want) {
+      fence_acquire();
+      return (uint32_t)e;
+    }
+    if (ld_acquire(p.sched + 2) >= n_items) return SCHED_DONE;
+    __nanosleep(100);
+  }
+}
+// the calling threads (tid of nthreads) release the successors of a completed item; every thread
+// must have fenced its global stores and synchronised with the others before
+__device__ __forceinline__ void sched_complete(const EngineParams& p, uint32_t call_i, uint32_t grp, uint32_t tid,
+                                               uint32_t nthreads) {
+  const uint32_t lo = p.succ_off[call_i], hi = p.succ_off[call_i + 1];
+  for (uint32_t k = lo + tid; k < hi; k += nthreads) {
+    const uint32_t it = p.succ[k] * p.n_groups + grp;
+    if (atomicSub(p.pending + it, 1u) == 1u) {
+      __threadfence();  // order after the other producers' releases observed through the counter
+      sched_push(p, it);
+    }
+  }
+  if (tid == 0) {
+    st_release(p.flags + (size_t)call_i * p.n_groups + grp, p.epoch);
+    atomicAdd(p.sched + 2, 1u);
+  }
+}
+
+// pending[item] = number of dependencies; items without any are pushed right away
+__global__ void k_sched_init(const EngineParams p) {
+  const uint32_t n_items = p.n_calls * p.n_groups;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
+    const uint32_t nd = p.calls[i / p.n_groups].n_deps;
+    p.pending[i] = nd;
+    if (nd == 0) sched_push(p, i);
+  }
+}
+
+// GSV_CT_COMMIT_HOST: instead of folding, one warp tracks the emission-order frontier of finished
+// calls (all instance groups) and publishes the number of complete stream positions to mapped host
+// memory; the host drains the ring by DMA and folds the chains with AES-NI (host_chain.h).  Ring
+// back-pressure comes back through chain_progress[0], which the host advances after each drain.
+__device__ __forceinline__ void publish_warp(const EngineParams& p) {
+  const uint32_t lane = threadIdx.x & 31u;
+  unsigned long long end = 0;
+  for (uint32_t c = 0; c < p.n_calls; ++c) {
+    const DevCallD call = p.calls[c];
+    const uint32_t n = p.tasks[call.task].n_ct;
+    if (n == 0) continue;
+    for (uint32_t g = lane; g < p.n_groups; g += 32) {
+      const uint32_t* f = p.flags + (size_t)c * p.n_groups + g;
+      while (ld_acquire(f) != p.epoch) __nanosleep(200);
+    }
+    fence_acquire();
+    __syncwarp();
+    end = call.ct_base + n;
+    if (lane == 0) {
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned long long*>(p.host_ready) = end;
+    }
+  }
+  if (lane == 0) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(p.host_ready) = end;
+  }
+}
+
 // MODE 0 = garble (labels are label0, ciphertexts produced), MODE 1 = evaluate.
 template <int G, int HASH, int MODE>
 __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
@@ -200,8 +309,11 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
     // ---- chain CTA: the last n_chain_ctas SMs only run commitment consumers, a few warps per
     // SMSP, so the latency-bound chain never competes with garbling warps for issue slots
     const uint32_t warp = threadIdx.x >> 5;
-    if (warp < p.n_chain_warps)
+    if (p.host_chain) {
+      if (warp == 0) publish_warp(p);
+    } else if (warp < p.n_chain_warps) {
       chain_warp(p, te, (blockIdx.x - (gridDim.x - p.n_chain_ctas)) * p.n_chain_warps + warp);
+    }
     return;
   }
 
@@ -214,35 +326,53 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
   uint4* lab = smem + TE_Q + worker * lab_words;
   uint8_t* tail = reinterpret_cast<uint8_t*>(smem + TE_Q + n_workers * lab_words);
   uint8_t* sval = tail + worker * lab_words;
-  volatile uint32_t* ctrl = reinterpret_cast<volatile uint32_t*>(tail + (MODE == 1 ? n_workers * lab_words : 0)) + worker;
+  uint8_t* tail2 = tail + (MODE == 1 ? n_workers * lab_words : 0);
+  volatile uint32_t* ctrl = reinterpret_cast<volatile uint32_t*>(tail2) + worker;
+  // gate-record ring, 16-byte aligned behind the value bytes and the ticket words
+  const uint32_t tail_bytes = ((MODE == 1 ? n_workers * lab_words : 0u) + n_workers * 4u + 15u) & ~15u;
+  const uint4* ring = reinterpret_cast<const uint4*>(tail + tail_bytes) + worker * GATE_RING;
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
 
   const uint32_t inst = wt % G;  // NT % G == 0, so a thread always serves the same instance lane
   const uint32_t n_items = p.n_calls * p.n_groups;
 
   for (;;) {
-    if (wt == 0) *ctrl = atomicAdd(p.next_item, 1u);
+    if (wt == 0) {
+      uint32_t it;
+      for (;;) {
+        it = sched_pop(p, n_items);
+        if (it == SCHED_DONE || MODE != 0 || !p.ct_ring) break;
+        // ring space: an item whose ciphertexts would overrun the unconsumed part of the ring goes
+        // back to the end of the queue (the items the consumer is waiting for are ahead of it)
+        const uint32_t ci = it / p.n_groups, gi = it - ci * p.n_groups;
+        const unsigned long long need = p.calls[ci].ct_base + p.tasks[p.calls[ci].task].n_ct;
+        const unsigned long long* pr = p.chain_progress + (p.host_chain ? 0u : (gi * G) / CHAIN_INST);  // G divides 8
+        if (need <= p.ct_ring || ld_acquire64(pr) + p.ct_ring >= need) break;
+        sched_push(p, it);
+        __nanosleep(256);
+      }
+      *ctrl = it;
+    }
     named_bar(bar_id, NT);
     const uint32_t item = *ctrl;
-    if (item >= n_items) break;
+    if (item == SCHED_DONE) break;
     const uint32_t call_i = item / p.n_groups;
     const uint32_t grp = item - call_i * p.n_groups;
     const DevCallD call = p.calls[call_i];
     const DevTaskD task = p.tasks[call.task];
 
-    // ---- wait for producer calls of this instance group, and for ring space
-    for (uint32_t d = wt; d < call.n_deps; d += NT) {
-      const uint32_t* f = p.flags + (size_t)p.deps[call.dep_off + d] * p.n_groups + grp;
-      while (ld_acquire(f) != p.epoch) __nanosleep(64);
-    }
-    if (MODE == 0 && p.ct_ring && wt == NT - 1) {
-      const unsigned long long need = call.ct_base + task.n_ct;
-      if (need > p.ct_ring) {
-        const unsigned long long* pr = p.chain_progress + (grp * G) / CHAIN_INST;  // G divides 8
-        while (ld_acquire64(pr) + p.ct_ring < need) __nanosleep(256);
-      }
-    }
-    fence_acquire();
-    named_bar(bar_id, NT);
+    // ---- start streaming the task's gate records (independent of the producers)
+    const uint4* gsrc = p.gates + task.gate_off;
+    uint32_t issued = 0;  // chunks requested so far (one cp.async group each, uniform over the worker)
+    auto issue_chunk = [&]() {
+      const uint32_t base = issued * GATE_CHUNK;
+      for (uint32_t r = base + wt; r < base + GATE_CHUNK && r < task.n_gates; r += NT)
+        cp_async16(ring_s + ((r & (GATE_RING - 1)) << 4), gsrc + r);
+      cp_async_commit();
+      issued++;
+    };
+#pragma unroll
+    for (uint32_t k = 0; k < GATE_CHUNKS; k++) issue_chunk();
 
     // ring position of the call's first ciphertext (a task never exceeds half the ring)
     const unsigned long long ct_pos0 = p.ct_ring ? call.ct_base % p.ct_ring : call.ct_base;
@@ -264,25 +394,16 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
         if (MODE == 1) sval[s * G + inst] = __ldcg(p.vals + gi);
       }
     }
+    cp_async_wait<1>();  // chunks 0..2 have landed
     named_bar(bar_id, NT);
 
-    // ---- level loop
-    const uint4* gates = p.gates + task.gate_off;
-    const uint32_t* loff = p.level_off + task.level_off;
-    uint32_t lo = __ldg(loff), hi = (task.n_levels ? __ldg(loff + 1) : lo);
-    uint4 nxt = make_uint4(0, 0, 0, 0);
-    if (wt < (hi - lo) * G) nxt = __ldg(gates + lo + wt / G);
+    // ---- level loop.  Invariant at a level start: `pos` lies in chunk j = released, chunks up to
+    // j + 3 are requested, chunks j and j + 1 (all a level can touch) have landed.
+    uint32_t pos = 0, released = 0;
     for (uint32_t lvl = 0; lvl < task.n_levels; ++lvl) {
-      const uint32_t cur_lo = lo, n = (hi - lo) * G;
-      uint4 graw = nxt;
-      // prefetch the first gate of the next level while this level computes
-      lo = hi;
-      if (lvl + 1 < task.n_levels) {
-        hi = __ldg(loff + lvl + 2);
-        if (wt < (hi - lo) * G) nxt = __ldg(gates + lo + wt / G);
-      }
+      const uint32_t n = (((ring[pos & (GATE_RING - 1)].y >> 25) & 0x7Fu) + 1u) * G;
       for (uint32_t idx = wt; idx < n; idx += NT) {
-        if (idx != wt) graw = __ldg(gates + cur_lo + idx / G);
+        const uint4 graw = ring[(pos + idx / G) & (GATE_RING - 1)];
         const uint32_t sa = graw.x & 0xFFFFu, sb = graw.x >> 16, sc = graw.y & 0xFFFFu;
         const uint32_t type = (graw.y >> 16) & 0xFFu;
         const uint4 la = lab[sa * G + inst];
@@ -299,9 +420,9 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
             lc = garble_nonfree<HASH>(te, type, la, lb, delta, gid, ct);
             if (p.write_ct)
             {
-              unsigned long long pos = ct_pos0 + graw.w;
-              if (p.ct_ring && pos >= p.ct_ring) pos -= p.ct_ring;
-              __stcg(p.ct + (size_t)pos * p.B + grp * G + inst, ct);
+              unsigned long long cpos = ct_pos0 + graw.w;
+              if (p.ct_ring && cpos >= p.ct_ring) cpos -= p.ct_ring;
+              __stcg(p.ct + (size_t)cpos * p.ct_pos_stride + (size_t)(grp * G + inst) * p.ct_inst_stride, ct);
             }
           }
         } else {
@@ -320,8 +441,15 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
         }
         lab[sc * G + inst] = lc;
       }
+      pos += n / G;
+      cp_async_wait<1>();  // everything but the newest chunk: covers chunk(pos) + 1
       named_bar(bar_id, NT);
+      while (released < pos / GATE_CHUNK) {  // chunks behind `pos` are free: request the next ones
+        issue_chunk();
+        released++;
+      }
     }
+    cp_async_wait<0>();
 
     // ---- scatter produced labels to the instance's global slots
     for (uint32_t k = wt; k < task.n_out * G; k += NT) {
@@ -333,7 +461,7 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
     }
     __threadfence();
     named_bar(bar_id, NT);
-    if (wt == 0) st_release(p.flags + (size_t)call_i * p.n_groups + grp, p.epoch);
+    sched_complete(p, call_i, grp, wt, NT);
   }
 }
 
@@ -354,8 +482,11 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   if (MODE == 0 && blockIdx.x >= gridDim.x - p.n_chain_ctas) {
     // chain CTA (see k_engine): dedicated SMs for the serial commitment
-    if (warp < p.n_chain_warps)
+    if (p.host_chain) {
+      if (warp == 0) publish_warp(p);
+    } else if (warp < p.n_chain_warps) {
       chain_warp(p, te, (blockIdx.x - (gridDim.x - p.n_chain_ctas)) * p.n_chain_warps + warp);
+    }
     return;
   }
   if (warp >= p.n_workers) return;
@@ -367,29 +498,29 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
 
   for (;;) {
     uint32_t item = 0;
-    if (lane == 0) item = atomicAdd(p.next_item, 1u);
-    item = __shfl_sync(FULL, item, 0);
-    if (item >= n_items) break;
+    for (;;) {
+      if (lane == 0) item = sched_pop(p, n_items);
+      item = __shfl_sync(FULL, item, 0);
+      if (item == SCHED_DONE || MODE != 0 || !p.ct_ring) break;
+      // ring space (see k_engine): the group's 32 instances are served by 4 chain warps, one lane each
+      const uint32_t ci = item / p.n_groups, gi = item - ci * p.n_groups;
+      const unsigned long long need = p.calls[ci].ct_base + p.tasks[p.calls[ci].task].n_ct;
+      bool ok = true;
+      if (need > p.ct_ring && lane < 32 / CHAIN_INST) {
+        const uint32_t cwi = gi * (32 / CHAIN_INST) + lane;
+        if (cwi * CHAIN_INST < p.B) ok = ld_acquire64(p.chain_progress + (p.host_chain ? 0u : cwi)) + p.ct_ring >= need;
+      }
+      if (__all_sync(FULL, ok)) break;
+      if (lane == 0) sched_push(p, item);
+      __nanosleep(256);
+    }
+    if (item == SCHED_DONE) break;
     const uint32_t call_i = item / p.n_groups;
     const uint32_t grp = item - call_i * p.n_groups;
     const DevCallD call = p.calls[call_i];
     const DevTaskD task = p.tasks[call.task];
     const uint32_t instance = grp * 32u + lane;
     const bool act = instance < p.B;
-
-    for (uint32_t d = lane; d < call.n_deps; d += 32) {
-      const uint32_t* f = p.flags + (size_t)p.deps[call.dep_off + d] * p.n_groups + grp;
-      while (ld_acquire(f) != p.epoch) __nanosleep(100);
-    }
-    if (MODE == 0 && p.ct_ring && lane >= 32 - 32 / CHAIN_INST) {
-      // the group's 32 instances are served by 4 chain warps: one polling lane each
-      const unsigned long long need = call.ct_base + task.n_ct;
-      const uint32_t cwi = grp * (32 / CHAIN_INST) + (lane - (32 - 32 / CHAIN_INST));
-      if (need > p.ct_ring && cwi * CHAIN_INST < p.B) {
-        const unsigned long long* pr = p.chain_progress + cwi;
-        while (ld_acquire64(pr) + p.ct_ring < need) __nanosleep(256);
-      }
-    }
     fence_acquire();
     __syncwarp();
 
@@ -458,7 +589,7 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
             if (p.ct_ring && pos >= p.ct_ring) pos -= p.ct_ring;
             uint4 ct;
             lc = garble_nonfree<HASH>(te, type, la, lb, delta, gid, ct);
-            if (p.write_ct && act) __stcg(p.ct + (size_t)pos * p.B + instance, ct);
+            if (p.write_ct && act) __stcg(p.ct + (size_t)pos * p.ct_pos_stride + (size_t)instance * p.ct_inst_stride, ct);
           }
         } else {
           const uint32_t va = myv[sa * 32u], vb = myv[sb * 32u];
@@ -499,7 +630,7 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
     }
     __threadfence();
     __syncwarp();
-    if (lane == 0) st_release(p.flags + (size_t)call_i * p.n_groups + grp, p.epoch);
+    sched_complete(p, call_i, grp, lane, 32);
   }
 }
 

@@ -8,6 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <thread>
+#include <atomic>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -16,6 +19,7 @@
 #include "engine_kernels.cuh"
 #include "gadgets.h"
 #include "program.h"
+#include "host_chain.h"
 
 using namespace gsvdev;
 
@@ -126,6 +130,8 @@ struct gsv_program {
   gsv::Program prog;
   uint32_t max_task_levels = 0;
   uint64_t sum_call_levels = 0;
+  uint64_t critical_path_gates = 0;   // longest dependency chain through the calls, weighted by gates
+  uint64_t critical_path_levels = 0;  // ... weighted by the tasks' level counts
 };
 
 struct gsv_ctx {
@@ -146,6 +152,23 @@ gsv_program* finish_program(std::unique_ptr<gsv::Builder> b, uint32_t root, cons
   p->root = root;
   for (const auto& t : p->prog.tasks) p->max_task_levels = std::max(p->max_task_levels, t.n_levels);
   for (const auto& c : p->prog.calls) p->sum_call_levels += p->prog.tasks[c.task].n_levels;
+  {
+    // dependency-chain lengths: what bounds one instance's latency however many SMs there are
+    const auto& g = p->prog;
+    std::vector<uint64_t> fg(g.calls.size()), fl(g.calls.size());
+    for (size_t i = 0; i < g.calls.size(); i++) {
+      const auto& c = g.calls[i];
+      uint64_t sg = 0, sl = 0;
+      for (uint32_t d = 0; d < c.n_deps; d++) {
+        sg = std::max(sg, fg[g.deps[c.dep_off + d]]);
+        sl = std::max(sl, fl[g.deps[c.dep_off + d]]);
+      }
+      fg[i] = sg + g.tasks[c.task].n_gates_total;
+      fl[i] = sl + g.tasks[c.task].n_levels;
+      p->critical_path_gates = std::max(p->critical_path_gates, fg[i]);
+      p->critical_path_levels = std::max(p->critical_path_levels, fl[i]);
+    }
+  }
   return p.release();
 }
 }  // namespace
@@ -249,6 +272,58 @@ int gsv_program_execute(const gsv_program* p, const uint8_t* input_bits, uint8_t
   }
 }
 
+int gsv_host_chain_fold(uint8_t* h, const uint8_t* base, uint64_t pos_stride, uint64_t inst_stride, uint64_t n_pos, uint32_t n_inst) {
+  if (!h || (!base && n_pos)) return fail(GSV_ERR_INVALID, "null argument");
+  if (!gsv::host_chain_available()) return fail(GSV_ERR_INVALID, "host CPU has no AES-NI");
+  gsv::host_chain_fold(h, base, pos_stride, inst_stride, n_pos, n_inst);
+  return GSV_OK;
+}
+
+int gsv_program_execute_plan(const gsv_program* p, int lane_form, const uint8_t* input_bits, uint8_t* output_bits) {
+  if (!p || !input_bits || !output_bits) return fail(GSV_ERR_INVALID, "null argument");
+  try {
+    const gsv::Program& g = p->prog;
+    if (!lane_form && !g.has_levelised) throw std::runtime_error("program was planned lane-only");
+    auto eval = [](uint8_t type, uint8_t a, uint8_t b) -> uint8_t {
+      if (type == gsv::NOT) return a ^ 1;
+      if (type == gsv::XOR) return a ^ b;
+      if (type == gsv::XNOR) return a ^ b ^ 1;
+      const uint8_t aa = (type >> 2) & 1, ab = (type >> 1) & 1, ac = type & 1;  // gate_type.rs alphas
+      return ((a ^ aa) & (b ^ ab)) ^ ac;
+    };
+    // 0xFF marks a slot nobody has written in this pass: reading one is a planner bug
+    std::vector<uint8_t> glob(g.n_global_slots, 0xFF), loc;
+    glob[0] = 0;
+    glob[1] = 1;
+    for (uint32_t i = 0; i < g.n_inputs; i++) glob[2 + i] = input_bits[i] & 1;
+    for (size_t ci = 0; ci < g.calls.size(); ci++) {
+      const gsv::Call& c = g.calls[ci];
+      const gsv::Task& t = g.tasks[c.task];
+      const auto& gates = lane_form ? t.seq_gates : t.gates;
+      const auto& in_slot = lane_form ? t.seq_in_slot : t.in_slot;
+      const auto& out_slot = lane_form ? t.seq_out_slot : t.out_slot;
+      loc.assign(std::max<uint32_t>(lane_form ? t.n_seq_slots : t.n_slots, 2), 0xFF);
+      loc[0] = 0;
+      loc[1] = 1;
+      for (uint32_t i = 0; i < t.n_in; i++)
+        if (in_slot[i] != 0xFFFF) loc[in_slot[i]] = glob[g.call_slots[c.in_off + i]];
+      for (const gsv::DevGate& dg : gates) {
+        const uint8_t a = loc[dg.a], b = loc[dg.type == gsv::NOT ? dg.a : dg.b];
+        if ((a | b) > 1) throw std::runtime_error("plan reads an unwritten slot in call " + std::to_string(ci) + " (" + t.key + ")");
+        loc[dg.c] = eval(dg.type, a, b);
+      }
+      for (uint32_t k = 0; k < t.n_out; k++) glob[g.call_slots[c.out_off + k]] = loc[out_slot[k]];
+    }
+    for (size_t j = 0; j < g.output_slots.size(); j++) {
+      if (glob[g.output_slots[j]] > 1) throw std::runtime_error("circuit output slot never written");
+      output_bits[j] = glob[g.output_slots[j]];
+    }
+    return GSV_OK;
+  } catch (const std::exception& e) {
+    return fail(GSV_ERR_INVALID, e.what());
+  }
+}
+
 int gsv_groth16_synthetic_inputs(uint64_t public_x, int flip_public, uint8_t* bits, uint32_t n_bits) {
   if (!bits || n_bits != 1273) return fail(GSV_ERR_INVALID, "need a 1273-bit buffer");
   try {
@@ -298,6 +373,8 @@ int gsv_program_get_info(const gsv_program* p, gsv_program_info* out) {
   out->max_task_levels = p->max_task_levels;
   out->max_call_deps = g.max_call_deps;
   out->sum_call_levels = p->sum_call_levels;
+  out->critical_path_gates = p->critical_path_gates;
+  out->critical_path_levels = p->critical_path_levels;
   return GSV_OK;
 }
 
@@ -343,7 +420,6 @@ struct gsv_session {
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   // program on device
   DevBuf<uint4> d_gates;
-  DevBuf<uint32_t> d_level_off;
   DevBuf<uint16_t> d_in_slot, d_out_slot;
   DevBuf<DevTaskD> d_tasks;
   DevBuf<DevCallD> d_calls;
@@ -351,7 +427,10 @@ struct gsv_session {
   // instance state
   DevBuf<uint4> d_labels, d_delta, d_ct, d_commit, d_io, d_stage;
   DevBuf<uint8_t> d_vals, d_io_bits;
-  DevBuf<uint32_t> d_flags, d_ctrl;  // d_ctrl[0] = next_item, [1] = error flag
+  DevBuf<uint32_t> d_flags, d_ctrl;  // d_ctrl[1] = error flag, [4..6] = scheduler head / tail / completed
+  DevBuf<uint32_t> d_succ_off, d_succ, d_pending;
+  DevBuf<unsigned long long> d_queue;
+  uint32_t queue_log2 = 0;
   DevBuf<unsigned long long> d_progress;
   DevBuf<unsigned long long> d_seeds;
   // lane mode (one warp = 32 instances, emission-order tasks)
@@ -362,7 +441,23 @@ struct gsv_session {
   DevBuf<uint16_t> d_seq_in_slot, d_seq_out_slot;
   DevBuf<uint8_t> d_scratch_vals;
   bool ct_valid = false;
+  // GSV_CT_COMMIT_HOST: ring drained to pinned host buffers, chains folded by AES-NI threads
+  static constexpr int HC_BUFS = 4;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t hc_ev[HC_BUFS] = {nullptr, nullptr, nullptr, nullptr};
+  uint8_t* hc_buf[HC_BUFS] = {nullptr, nullptr, nullptr, nullptr};
+  size_t hc_buf_bytes = 0;
+  unsigned long long* hc_ready = nullptr;      // mapped: stream positions complete (device writes)
+  unsigned long long* hc_ready_dev = nullptr;  // its device address
+  unsigned long long* hc_consumed = nullptr;   // pinned [HC_BUFS]: sources of the back-pressure copies
   ~gsv_session() {
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    for (auto& e : hc_ev)
+      if (e) cudaEventDestroy(e);
+    for (auto& b : hc_buf)
+      if (b) cudaFreeHost(b);
+    if (hc_ready) cudaFreeHost(hc_ready);
+    if (hc_consumed) cudaFreeHost(hc_consumed);
     if (stream) cudaStreamDestroy(stream);
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
@@ -374,7 +469,6 @@ namespace {
 void upload_program(gsv_session* s) {
   const gsv::Program& g = s->prog->prog;
   std::vector<uint4> gates;
-  std::vector<uint32_t> level_off;
   std::vector<uint16_t> in_slot, out_slot;
   std::vector<uint4> seq_gates;
   std::vector<uint16_t> seq_in_slot, seq_out_slot;
@@ -382,7 +476,7 @@ void upload_program(gsv_session* s) {
   for (const gsv::Task& t : g.tasks) {
     DevTaskD d;
     d.gate_off = (uint32_t)gates.size();
-    d.level_off = (uint32_t)level_off.size();
+    d.n_gates = (uint32_t)t.gates.size();
     d.n_levels = t.n_levels;
     d.n_in = t.n_in;
     d.n_out = t.n_out;
@@ -405,8 +499,6 @@ void upload_program(gsv_session* s) {
     }
     seq_in_slot.insert(seq_in_slot.end(), t.seq_in_slot.begin(), t.seq_in_slot.end());
     seq_out_slot.insert(seq_out_slot.end(), t.seq_out_slot.begin(), t.seq_out_slot.end());
-    level_off.insert(level_off.end(), t.level_off.begin(), t.level_off.end());
-    if (t.level_off.empty()) level_off.push_back(0);
     in_slot.insert(in_slot.end(), t.in_slot.begin(), t.in_slot.end());
     out_slot.insert(out_slot.end(), t.out_slot.begin(), t.out_slot.end());
     tasks.push_back(d);
@@ -439,7 +531,6 @@ void upload_program(gsv_session* s) {
     gates.assign(1, make_uint4(0, 0, 0, 0));
   }
   s->d_gates.upload(gates);
-  s->d_level_off.upload(level_off);
   s->d_in_slot.upload(in_slot);
   s->d_out_slot.upload(out_slot);
   s->d_tasks.upload(tasks);
@@ -457,7 +548,6 @@ EngineParams make_params(gsv_session* s) {
   EngineParams p;
   memset(&p, 0, sizeof(p));
   p.gates = s->d_gates.p;
-  p.level_off = s->d_level_off.p;
   p.in_slot = s->d_in_slot.p;
   p.out_slot = s->d_out_slot.p;
   p.tasks = s->d_tasks.p;
@@ -469,7 +559,12 @@ EngineParams make_params(gsv_session* s) {
   p.delta = s->d_delta.p;
   p.ct = s->d_ct.p;
   p.flags = s->d_flags.p;
-  p.next_item = s->d_ctrl.p;
+  p.sched = s->d_ctrl.p + 4;
+  p.queue = s->d_queue.p;
+  p.pending = s->d_pending.p;
+  p.succ_off = s->d_succ_off.p;
+  p.succ = s->d_succ.p;
+  p.queue_log2 = s->queue_log2;
   p.error_flag = s->d_ctrl.p + 1;
   p.chain_progress = s->d_progress.p;
   p.commit = s->d_commit.p;
@@ -490,11 +585,27 @@ EngineParams make_params(gsv_session* s) {
   p.scratch = s->d_scratch.p;
   p.scratch_vals = s->d_scratch_vals.p;
   p.scratch_stride = s->scratch_stride;
+  p.host_chain = s->ct_mode == GSV_CT_COMMIT_HOST ? 1u : 0u;
+  p.ct_pos_stride = s->B;
+  p.ct_inst_stride = 1;
+  if (p.host_chain) {  // instance-major ring: each chain drains as one sequential host stream
+    p.ct_pos_stride = 1;
+    p.ct_inst_stride = s->d_ct.n / s->B;
+  }
+  p.host_ready = s->hc_ready_dev;
   return p;
 }
 
 template <int MODE>
 void launch_engine(gsv_session* s, int hasher, const EngineParams& p) {
+  // scheduler reset: empty queue, counters at zero, dependency counts loaded, root items queued
+  CUDA_TRY(cudaMemsetAsync(s->d_ctrl.p + 4, 0, 16, s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->d_queue.p, 0, s->d_queue.n * 8, s->stream));
+  {
+    const size_t n_items = (size_t)p.n_calls * p.n_groups;
+    k_sched_init<<<(unsigned)std::min<size_t>((n_items + 255) / 256 + 1, 4096), 256, 0, s->stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+  }
   if (s->lane_mode) {
     dim3 lgrid(s->sm_count), lblock(32 * s->n_workers);
     if (hasher == GSV_HASH_AES) {
@@ -531,6 +642,105 @@ void launch_engine(gsv_session* s, int hasher, const EngineParams& p) {
 #undef GSV_LAUNCH_G
 #undef GSV_LAUNCH
   CUDA_TRY(cudaGetLastError());
+}
+
+// Drains the ciphertext ring of a running GSV_CT_COMMIT_HOST garbling kernel and folds the B chains
+// on host threads.  Called right after the kernel launch; returns when every chain is complete.
+void run_host_chain(gsv_session* s, uint8_t* commits) {
+  const gsv::Program& g = s->prog->prog;
+  const uint32_t B = s->B;
+  const uint64_t total = g.total_ct;
+  const size_t pos_bytes = (size_t)B * 16;
+  const uint64_t chunk_pos = std::max<uint64_t>(1, s->hc_buf_bytes / pos_bytes);
+  const uint64_t cap = s->d_ct.n / B;  // device ring (or whole stream) positions per instance
+  constexpr int NB = gsv_session::HC_BUFS;
+  unsigned hw = std::thread::hardware_concurrency();
+  if (hw == 0) hw = 4;
+  uint32_t T = std::min<uint32_t>((B + 1) / 2, hw > 2 ? hw - 2 : 1);
+  if (const char* e = getenv("GSV_HOST_CHAIN_THREADS")) T = std::max(1, atoi(e));
+  T = std::max<uint32_t>(1, std::min(T, B));
+  std::vector<uint8_t> h((size_t)B * 16, 0);
+  std::atomic<uint64_t> slot_job[NB];   // 1 + index of the job whose copy was enqueued into the slot
+  std::atomic<uint64_t> slot_done[NB];  // hasher completions on the slot, over all jobs
+  uint64_t slot_npos[NB] = {0, 0, 0, 0};
+  for (int b = 0; b < NB; b++) {
+    slot_job[b].store(0);
+    slot_done[b].store(0);
+  }
+  std::atomic<int64_t> n_jobs{-1};
+  std::atomic<bool> abort{false};
+  auto hasher = [&](uint32_t t) {
+    const uint32_t i0 = (uint32_t)((uint64_t)B * t / T), i1 = (uint32_t)((uint64_t)B * (t + 1) / T);
+    cudaSetDevice(s->device);
+    for (uint64_t j = 0;; j++) {
+      const int b = (int)(j % NB);
+      while (slot_job[b].load(std::memory_order_acquire) != j + 1) {
+        const int64_t nj = n_jobs.load(std::memory_order_acquire);
+        if (abort.load() || (nj >= 0 && (int64_t)j >= nj)) return;
+        std::this_thread::yield();
+      }
+      if (cudaEventSynchronize(s->hc_ev[b]) != cudaSuccess) {
+        abort.store(true);
+        return;
+      }
+      if (i1 > i0) gsv::host_chain_fold(h.data() + (size_t)i0 * 16, s->hc_buf[b] + (size_t)i0 * chunk_pos * 16, 1, chunk_pos, slot_npos[b], i1 - i0);
+      slot_done[b].fetch_add(1, std::memory_order_release);
+    }
+  };
+  std::vector<std::thread> threads;
+  for (uint32_t t = 0; t < T; t++) threads.emplace_back(hasher, t);
+  std::string err;
+  try {
+    uint64_t copied = 0, jobs = 0;
+    auto last_query = std::chrono::steady_clock::now();
+    while (copied < total) {
+      const uint64_t ready = *reinterpret_cast<volatile unsigned long long*>(s->hc_ready);
+      if (ready <= copied) {
+        auto now = std::chrono::steady_clock::now();
+        if (now - last_query > std::chrono::milliseconds(5)) {
+          last_query = now;
+          cudaError_t q = cudaStreamQuery(s->stream);
+          if (q != cudaSuccess && q != cudaErrorNotReady) throw std::runtime_error(std::string("garbling kernel failed: ") + cudaGetErrorString(q));
+          if (q == cudaSuccess && *reinterpret_cast<volatile unsigned long long*>(s->hc_ready) <= copied)
+            throw std::runtime_error("garbling kernel ended before the stream was complete");
+        }
+        std::this_thread::yield();
+        continue;
+      }
+      uint64_t n = std::min<uint64_t>(ready - copied, chunk_pos);
+      uint64_t pos = copied;
+      if (s->ct_ring) {
+        pos = copied % s->ct_ring;
+        n = std::min<uint64_t>(n, s->ct_ring - pos);
+      }
+      // small drains waste DMA launches: unless the stream is ending, wait for half a buffer
+      if (n < chunk_pos / 2 && copied + n < total && ready - copied < chunk_pos / 2 && !(s->ct_ring && pos + n == s->ct_ring)) {
+        std::this_thread::yield();
+        continue;
+      }
+      const int b = (int)(jobs % NB);
+      while (slot_done[b].load(std::memory_order_acquire) != (uint64_t)T * (jobs / NB)) {
+        if (abort.load()) throw std::runtime_error("host chain thread failed");
+        std::this_thread::yield();
+      }
+      CUDA_TRY(cudaMemcpy2DAsync(s->hc_buf[b], (size_t)chunk_pos * 16, s->d_ct.p + pos, (size_t)cap * 16, (size_t)n * 16, B, cudaMemcpyDeviceToHost, s->copy_stream));
+      s->hc_consumed[b] = copied + n;
+      CUDA_TRY(cudaMemcpyAsync(s->d_progress.p, s->hc_consumed + b, 8, cudaMemcpyHostToDevice, s->copy_stream));
+      CUDA_TRY(cudaEventRecord(s->hc_ev[b], s->copy_stream));
+      slot_npos[b] = n;
+      slot_job[b].store(jobs + 1, std::memory_order_release);
+      jobs++;
+      copied += n;
+    }
+    n_jobs.store((int64_t)jobs, std::memory_order_release);
+  } catch (const std::exception& e) {
+    err = e.what();
+    abort.store(true);
+  }
+  for (auto& t : threads) t.join();
+  if (err.empty() && abort.load()) err = "host chain thread failed";
+  if (!err.empty()) throw std::runtime_error(err);
+  memcpy(commits, h.data(), h.size());
 }
 
 }  // namespace
@@ -574,17 +784,26 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
       if (s->n_chain_ctas * 2 > (uint32_t)s->sm_count)
         throw std::runtime_error("too many instances for one GPU (commitment warps would take over half the SMs)");
     }
+    if (s->ct_mode == GSV_CT_COMMIT_HOST) {
+      if (!gsv::host_chain_available()) throw std::runtime_error("GSV_CT_COMMIT_HOST needs a host CPU with AES-NI");
+      n_chain = 1;  // one publisher warp on one trailing CTA
+      s->n_chain_ctas = 1;
+    }
     uint32_t n_workers = 1024 / s->NT;
     if (n_workers == 0) throw std::runtime_error("worker_threads too large");
     // largest G (power of two dividing B, <= 8) whose label working set fits next to the tables
     auto smem_for = [&](uint32_t G, uint32_t nw, bool eval) {
       size_t lab = (size_t)slots * G;
-      return (size_t)AES_TABLE_BYTES + nw * lab * 16 + (eval ? nw * lab : 0) + nw * 4 + 16;
+      return (size_t)AES_TABLE_BYTES + nw * lab * 16 + (((eval ? nw * lab : 0) + nw * 4 + 15) & ~(size_t)15) + (size_t)nw * GATE_RING * 16;
     };
     // execution mode: lane mode (warp = 32 instances) for batches that fill warps, the levelised
     // shared-memory mode otherwise
     if (opt->exec_mode > 2) throw std::runtime_error("exec_mode must be 0 (auto), 1 (levelised) or 2 (lane)");
     s->lane_mode = opt->exec_mode == 2 || (opt->exec_mode == 0 && opt->group == 0 && s->B >= 128);
+    if (!g.has_levelised) {
+      if (opt->exec_mode == 1) throw std::runtime_error("program was planned lane-only; it has no levelised form");
+      s->lane_mode = true;
+    }
     uint32_t G = opt->group;
     if (s->lane_mode) {
       G = 32;
@@ -613,6 +832,18 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
     s->n_chain_warps = n_chain;
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto& e : s->ev) CUDA_TRY(cudaEventCreate(&e));
+    if (s->ct_mode == GSV_CT_COMMIT_HOST) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+      s->hc_buf_bytes = 64u << 20;
+      if (const char* e = getenv("GSV_HOST_CHAIN_BUF_MB")) s->hc_buf_bytes = (size_t)std::max(1, atoi(e)) << 20;
+      for (int b = 0; b < gsv_session::HC_BUFS; b++) {
+        CUDA_TRY(cudaEventCreateWithFlags(&s->hc_ev[b], cudaEventDisableTiming));
+        CUDA_TRY(cudaHostAlloc((void**)&s->hc_buf[b], s->hc_buf_bytes, cudaHostAllocDefault));
+      }
+      CUDA_TRY(cudaHostAlloc((void**)&s->hc_ready, 64, cudaHostAllocMapped));
+      CUDA_TRY(cudaHostGetDevicePointer((void**)&s->hc_ready_dev, s->hc_ready, 0));
+      CUDA_TRY(cudaHostAlloc((void**)&s->hc_consumed, 8 * gsv_session::HC_BUFS, cudaHostAllocDefault));
+    }
     upload_program(s.get());
     s->d_labels.alloc((size_t)s->B_pad * g.n_global_slots);
     s->d_delta.alloc(s->B_pad);
@@ -626,9 +857,26 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
     s->d_seeds.alloc(s->B);
     s->d_flags.alloc((size_t)g.calls.size() * s->n_groups + 1);
     CUDA_TRY(cudaMemset(s->d_flags.p, 0, s->d_flags.n * 4));
-    s->d_ctrl.alloc(4);
+    s->d_ctrl.alloc(8);
     s->d_progress.alloc((size_t)std::max<uint32_t>(s->n_chain_ctas * n_chain, 1));
-    CUDA_TRY(cudaMemset(s->d_ctrl.p, 0, 16));
+    CUDA_TRY(cudaMemset(s->d_ctrl.p, 0, 32));
+    {
+      // scheduler state: reverse dependency edges, per-item counters, the ready queue
+      const size_t n_items = g.calls.size() * (size_t)s->n_groups;
+      if (n_items >= (1ull << 30)) throw std::runtime_error("too many work items (calls x instance groups)");
+      std::vector<uint32_t> succ_off(g.calls.size() + 1, 0), succ(g.deps.size());
+      for (uint32_t d : g.deps) succ_off[d + 1]++;
+      for (size_t i = 0; i < g.calls.size(); i++) succ_off[i + 1] += succ_off[i];
+      std::vector<uint32_t> fill(succ_off.begin(), succ_off.end() - 1);
+      for (size_t c = 0; c < g.calls.size(); c++)
+        for (uint32_t k = 0; k < g.calls[c].n_deps; k++) succ[fill[g.deps[g.calls[c].dep_off + k]]++] = (uint32_t)c;
+      s->d_succ_off.upload(succ_off);
+      s->d_succ.upload(succ);
+      s->d_pending.alloc(std::max<size_t>(n_items, 1));
+      s->queue_log2 = 4;
+      while ((1ull << s->queue_log2) < 2 * n_items) s->queue_log2++;
+      s->d_queue.alloc((size_t)1 << s->queue_log2);
+    }
     if (s->ct_mode != GSV_CT_NONE) {
       // GSV_CT_KEEP: the whole interleaved stream stays resident.  GSV_CT_COMMIT: a power-of-two
       // ring the chain warps drain (back-pressure through chain_progress).
@@ -690,15 +938,25 @@ int gsv_garble_batch(gsv_session* s, int hasher, const uint64_t* seeds, gsv_garb
     p.n_chain_ctas = s->n_chain_ctas;
     if (getenv("GSV_DEBUG_NO_CHAIN")) p.n_chain_ctas = 0;  // profiling aid: ciphertexts written, not folded
     if (s->n_chain_warps) CUDA_TRY(cudaMemsetAsync(s->d_progress.p, 0, s->d_progress.n * 8, s->stream));
+    if (s->ct_mode == GSV_CT_COMMIT_HOST) {
+      *reinterpret_cast<volatile unsigned long long*>(s->hc_ready) = 0;
+      CUDA_TRY(cudaMemsetAsync(s->d_progress.p, 0, 8, s->stream));
+    }
     launch_engine<0>(s, hasher, p);
-    launches++;
+    launches += 2;  // k_sched_init + the persistent engine kernel
     CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
+    std::vector<uint8_t> host_commits;
+    if (s->ct_mode == GSV_CT_COMMIT_HOST) {
+      host_commits.resize((size_t)B * 16);
+      run_host_chain(s, host_commits.data());
+    }
     // the chain commitment is folded inside k_engine by the chain warps (no separate launch)
     CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
     // ---- results
     if (res->delta) CUDA_TRY(cudaMemcpyAsync(res->delta, s->d_delta.p, (size_t)B * 16, cudaMemcpyDeviceToHost, s->stream));
     if (res->ct_commit && (s->ct_mode == GSV_CT_COMMIT || s->ct_mode == GSV_CT_KEEP))
       CUDA_TRY(cudaMemcpyAsync(res->ct_commit, s->d_commit.p, (size_t)B * 16, cudaMemcpyDeviceToHost, s->stream));
+    if (res->ct_commit && s->ct_mode == GSV_CT_COMMIT_HOST) memcpy(res->ct_commit, host_commits.data(), host_commits.size());
     auto gather = [&](const std::vector<uint32_t>& slots, uint8_t* host_out) {
       if (!host_out || slots.empty()) return;
       DevBuf<uint32_t> d_slots;
@@ -808,7 +1066,7 @@ int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io) {
     EngineParams p = make_params(s);
     p.ct_capacity = ct_avail;
     launch_engine<1>(s, hasher, p);
-    launches++;
+    launches += 2;
     CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
     // the evaluator's own chain hash over what it consumed (FileSource hashes while reading)
     const uint64_t used = std::min<uint64_t>(ct_avail, g.total_ct);

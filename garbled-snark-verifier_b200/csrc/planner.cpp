@@ -102,16 +102,19 @@ Task compile_flat(const FlatStream& fs, const std::string& key, const PlanOption
     t.in_slot[i] = (uint16_t)slot[w];
     release[last_use[w]].push_back(w);
   }
-  t.level_off.assign(depth + 1, 0);
+  // Device levels are capped at LEVEL_WIDTH_MAX gates (a wider level becomes consecutive
+  // sub-levels: extra barriers only) and the first record of each carries its width, so the
+  // kernel streams the gate list through a small shared-memory ring without a level table.
+  t.level_off.clear();
   t.gates.reserve(order.size());
   size_t oi = 0;
   for (uint32_t l = 1; l <= depth; l++) {
     for (uint32_t w : release[l - 1]) free_slots.push_back(slot[w]);
-    t.level_off[l - 1] = (uint32_t)t.gates.size();
     size_t begin = oi;
     while (oi < order.size() && sched[order[oi]] == l) oi++;
     t.max_width = std::max<uint32_t>(t.max_width, (uint32_t)(oi - begin));
     for (size_t k = begin; k < oi; k++) {
+      if ((k - begin) % LEVEL_WIDTH_MAX == 0) t.level_off.push_back((uint32_t)t.gates.size());
       uint32_t g = order[k];
       uint32_t c = fs.c[g];
       uint32_t s;
@@ -136,7 +139,10 @@ Task compile_flat(const FlatStream& fs, const std::string& key, const PlanOption
       t.gates.push_back(dg);
     }
   }
-  t.level_off[depth] = (uint32_t)t.gates.size();
+  t.level_off.push_back((uint32_t)t.gates.size());
+  t.n_levels = (uint32_t)t.level_off.size() - 1;
+  for (uint32_t l = 0; l < t.n_levels; l++)
+    t.gates[t.level_off[l]].flags |= (uint8_t)((t.level_off[l + 1] - t.level_off[l] - 1) << 1);
   t.n_slots = next_slot;
   for (size_t j = 0; j < fs.outputs.size(); j++) {
     uint32_t o = fs.outputs[j];
@@ -217,6 +223,8 @@ lane_form:
       if (o == WIRE_DEAD || o < first_def) continue;
       t.seq_out_slot.push_back((uint16_t)sl[o]);
     }
+    // lane-only plans: out_slot only serves as the "same produced wire" key of emit_call
+    if (!opt.build_levelised) t.out_slot = t.seq_out_slot;
   }
   return t;
 }
@@ -289,7 +297,7 @@ struct Planner {
       uint32_t w = in_global[i];
       // inputs the task never reads are not gathered; keep the slot list dense anyway
       prog.call_slots.push_back(w == WIRE_DEAD ? 0u : w);
-      if (task.in_slot[i] != 0xFFFF && w != WIRE_DEAD && producer[w] >= 0) deps.push_back((uint32_t)producer[w]);
+      if ((task.in_slot[i] != 0xFFFF || task.seq_in_slot[i] != 0xFFFF) && w != WIRE_DEAD && producer[w] >= 0) deps.push_back((uint32_t)producer[w]);
     }
     c.out_off = (uint32_t)prog.call_slots.size();
     uint32_t call_idx = (uint32_t)prog.calls.size();
@@ -602,6 +610,7 @@ Program plan_program(const Builder& b, uint32_t root, const PlanOptions& opt) {
     prog.max_task_slots = std::max(prog.max_task_slots, t.n_slots);
     prog.max_task_in = std::max(prog.max_task_in, t.n_in);
     prog.max_task_seq_slots = std::max(prog.max_task_seq_slots, t.n_seq_slots);
+    prog.has_levelised = opt.build_levelised;
   }
   if (prog.total_gates != rt.total_gates || prog.total_ct != rt.total_ct)
     throw std::logic_error("planner lost gates: " + std::to_string(prog.total_gates) + " vs " +

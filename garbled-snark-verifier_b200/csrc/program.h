@@ -26,10 +26,12 @@
 namespace gsv {
 
 // 16-byte device gate record.  Slots are task-local shared-memory label slots.
+constexpr uint32_t LEVEL_WIDTH_MAX = 128;  // gates per device level (7-bit width field, ring staging)
+
 struct alignas(16) DevGate {
   uint16_t a, b, c;
   uint8_t type;
-  uint8_t flags;    // bit0: has ciphertext
+  uint8_t flags;    // bit0: has ciphertext; bits 1-7 (levelised form, first gate of a level): level width - 1
   uint32_t gid_off; // gate index relative to the call's gid_base (dead gates counted)
   uint32_t ct_off;  // ciphertext index relative to the call's ct_base
 };
@@ -81,6 +83,7 @@ struct Program {
   uint64_t total_live = 0;
   uint32_t max_task_slots = 0;
   uint32_t max_task_seq_slots = 0;
+  bool has_levelised = true;         // false: planned lane-only (PlanOptions::build_levelised off)
   uint32_t max_task_in = 0;
   uint32_t max_call_deps = 0;
   uint64_t type_count[11] = {0};

@@ -68,7 +68,12 @@ enum gsv_ct_mode {
   GSV_CT_NONE = 0,   /* `()` handler: ciphertexts are dropped (src/circuit/mod.rs:172-178)       */
   GSV_CT_COMMIT = 1, /* AESAccumulatingHash: bit-exact chain commitment, stream not kept         */
   GSV_CT_KEEP = 2,   /* commitment + the stream stays in HBM for evaluation / read-back / P2P     */
-  GSV_CT_KEEP_RAW = 3 /* stream kept, commitment not computed (channel::Sender<S> handler)          */
+  GSV_CT_KEEP_RAW = 3, /* stream kept, commitment not computed (channel::Sender<S> handler)         */
+  GSV_CT_COMMIT_HOST = 4 /* same commitment as GSV_CT_COMMIT; every gate hash runs on the GPU, but the
+                            strictly serial chain is folded by host AES-NI threads that drain the
+                            ciphertext ring over PCIe while the kernel runs.  For few-instance runs of
+                            billion-ciphertext circuits, where one dependent AES per 0.46 us on the GPU
+                            (23 min for the Groth16 verifier) would dwarf the garbling itself.         */
 };
 
 const char* gsv_last_error(void);
@@ -116,6 +121,12 @@ gsv_program* gsv_program_build(const char* circuit, const gsv_plan_options* opt)
  * garbling path.  input_bits: n_inputs bytes (0/1), output_bits: n_outputs bytes. */
 int gsv_program_execute(const gsv_program* p, const uint8_t* input_bits, uint8_t* output_bits,
                         uint64_t* gates_executed);
+/* The same boolean evaluation, but over the PLANNED program (tasks, calls, task-local slots, recycled
+ * global slots) in call order, in the levelised (lane_form = 0) or emission-order (lane_form = 1)
+ * task form: a host-side planner self-check that needs no GPU.  Fails if the plan ever reads a
+ * slot that was not written. */
+int gsv_program_execute_plan(const gsv_program* p, int lane_form, const uint8_t* input_bits,
+                             uint8_t* output_bits);
 
 /* Input bits (EncodeInput order, 1273 wires: public | a.x a.flag | b.x.c0 b.x.c1 b.flag | c.x c.flag,
  * src/gadgets/groth16.rs:425-490) of a synthetic proof for "groth16_verify_compressed":
@@ -137,6 +148,9 @@ typedef struct {
   uint32_t max_task_levels;
   uint32_t max_call_deps;
   uint64_t sum_call_levels; /* sum over calls of their task's level count */
+  uint64_t critical_path_gates;  /* longest dependency chain through the calls, in gates: the
+                                    per-instance latency floor of the lane mode */
+  uint64_t critical_path_levels; /* the same chain in levels (levelised mode) */
 } gsv_program_info;
 int gsv_program_get_info(const gsv_program* p, gsv_program_info* out);
 
@@ -183,6 +197,12 @@ typedef struct {
   uint32_t n_launches;    /* kernels launched by this call                               */
   uint32_t reserved;
 } gsv_garble_result;
+
+/* Host half of GSV_CT_COMMIT_HOST, exposed for checkers: folds n_pos stream positions of n_inst
+ * instances, h[i] <- AES_K(h[i] ^ block(p, i)), block(p, i) = base + (p * pos_stride + i * inst_stride)
+ * * 16 (src/ciphertext_hasher.rs:22-29).  Needs AES-NI (GSV_ERR_INVALID otherwise). */
+int gsv_host_chain_fold(uint8_t* h, const uint8_t* base, uint64_t pos_stride, uint64_t inst_stride,
+                        uint64_t n_pos, uint32_t n_inst);
 
 /* streaming_garbling for B instances: instance i uses seeds[i] (garble_mode.rs:80-97). */
 int gsv_garble_batch(gsv_session* s, int hasher, const uint64_t* seeds, gsv_garble_result* res);

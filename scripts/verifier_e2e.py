@@ -12,20 +12,40 @@ import numpy as np
 import gsv_b200 as g
 
 mode, B = sys.argv[1], int(sys.argv[2])
+NT = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+GRP = int(sys.argv[4]) if len(sys.argv) > 4 else (2 if B % 2 == 0 else 1)
 t0 = time.time()
-prog = g.Program("groth16_verify_compressed", lane_only=(mode != "levelised"))
-rec = {"circuit": "groth16_verify_compressed", "mode": mode, "instances": B, "gates": prog.n_gates,
+prog = g.Program("groth16_verify_compressed", lane_only=mode.startswith("lane"))
+rec = {"circuit": "groth16_verify_compressed", "mode": mode, "instances": B, "worker_threads": NT, "group": GRP, "gates": prog.n_gates,
        "ciphertexts": prog.n_ciphertexts, "calls": prog.n_calls, "tasks": prog.n_tasks,
        "global_slots": prog.n_global_slots, "plan_s": round(time.time() - t0, 1)}
 print(rec, flush=True)
 seeds = [1234 + i for i in range(B)]
-if mode == "lane_throughput":
+if mode == "levelised_none":
+    s = g.Session(prog, B, ct_mode=g.CT_NONE, exec_mode=1, group=GRP, worker_threads=NT)
+    r = s.garble(seeds, g.HASH_AES, want_inputs=False)
+    rec.update(garble_ms=r.ms_garble, gates_per_s=prog.n_gates * B / (r.ms_garble * 1e-3))
+elif mode == "host_commit":
+    # config 2/4 of BASELINE.json: garbling with the ciphertext commitment only, every gate hash on the
+    # GPU, the serial chain folded by host AES-NI threads draining the ring (GSV_CT_COMMIT_HOST)
+    s = g.Session(prog, B, ct_mode=g.CT_COMMIT_HOST, exec_mode=1, group=GRP, worker_threads=NT)
+    for it in range(int(os.environ.get("REPS", "1"))):
+        t1 = time.time()
+        r = s.garble(seeds, g.HASH_AES, want_inputs=False)
+        wall = time.time() - t1
+        rec.setdefault("runs", []).append({"kernel_ms": r.ms_garble, "wall_s": round(wall, 2),
+                                           "gates_per_s": prog.n_gates * B / wall})
+        print(rec["runs"][-1], flush=True)
+    rec["commit_seed1234"] = bytes(r.ct_commit[0]).hex()
+    rec["commit_seed1235"] = bytes(r.ct_commit[1]).hex() if B > 1 else None
+    rec["output_label0_seed1234"] = bytes(r.output_label0[0, 0]).hex()
+elif mode == "lane_throughput":
     s = g.Session(prog, B, ct_mode=g.CT_NONE, exec_mode=2)
     r = s.garble(seeds, g.HASH_AES, want_inputs=False)
     rec.update(garble_ms=r.ms_garble, gates_per_s=prog.n_gates * B / (r.ms_garble * 1e-3))
 else:
     s = g.Session(prog, B, ct_mode=g.CT_KEEP_RAW, exec_mode=1 if mode == "levelised" else 2,
-                  group=(2 if B % 2 == 0 else 1) if mode == "levelised" else 0)
+                  group=GRP if mode == "levelised" else 0, worker_threads=NT)
     r = s.garble(seeds, g.HASH_AES)
     rec.update(garble_ms=r.ms_garble, gates_per_s=prog.n_gates * B / (r.ms_garble * 1e-3))
     print(rec, flush=True)
@@ -43,4 +63,4 @@ else:
         assert ok, rec
 print(json.dumps(rec), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
-open("gpurun_out/verifier_%s_B%d.json" % (mode, B), "w").write(json.dumps(rec))
+open("gpurun_out/verifier_%s_B%d_nt%d_g%d.json" % (mode, B, NT, GRP), "w").write(json.dumps(rec))

@@ -83,3 +83,23 @@ def test_no_cpu_fallback(gsv):
 def test_unknown_circuit(gsv):
     with pytest.raises(gsv.GsvError):
         gsv.Program("no_such_circuit")
+
+
+def test_host_chain_fold_matches_cbc_mac(gsv):
+    """Host half of GSV_CT_COMMIT_HOST vs an independent statement of the chain: h <- AES_K(h ^ ct)
+    is CBC-MAC with a zero IV under the fixed key (OpenSSL), for 1..13 interleaved instances, folded
+    in two pieces (the drain-buffer boundary)."""
+    import numpy as np
+    from cryptography.hazmat.primitives.ciphers import Cipher, algorithms, modes
+
+    rng = np.random.default_rng(3)
+    for n_inst in (1, 2, 3, 4, 7, 8, 13):
+        blocks = rng.integers(0, 256, (57, n_inst, 16), dtype=np.uint8)
+        h = gsv.host_chain_fold(np.zeros((n_inst, 16), np.uint8), blocks[:20])
+        h = gsv.host_chain_fold(h, blocks[20:])
+        h2 = gsv.host_chain_fold(np.zeros((n_inst, 16), np.uint8), blocks.transpose(1, 0, 2), instance_major=True)
+        assert np.array_equal(h, h2)
+        for i in range(n_inst):
+            enc = Cipher(algorithms.AES(bytes([0x42]) * 16), modes.CBC(bytes(16))).encryptor()
+            want = enc.update(blocks[:, i, :].tobytes())[-16:]
+            assert bytes(h[i]) == want

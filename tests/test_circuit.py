@@ -224,6 +224,36 @@ def test_groth16_verifier_accepts_and_rejects(gsv):
     p = gsv.Program("groth16_verify_compressed", lane_only=True)
     assert p.n_inputs == 1273 and p.n_outputs == 1
     assert 11.0e9 < p.n_gates < 11.8e9 and 0.25 < p.n_ciphertexts / p.n_gates < 0.28
-    assert p.n_global_slots < 150_000  # the reference's live-wire capacity (cut_and_choose/groth16.rs:17)
-    assert list(p.execute(gsv.groth16_synthetic_inputs(424242, False))) == [1]
-    assert list(p.execute(gsv.groth16_synthetic_inputs(424242, True))) == [0]
+    good, bad = gsv.groth16_synthetic_inputs(424242, False), gsv.groth16_synthetic_inputs(424242, True)
+    assert list(p.execute(good)) == [1]
+    # the planned program (298 976 calls over recycled global slots) computes the same function
+    assert list(p.execute_plan(good, lane_form=True)) == [1]
+    assert list(p.execute_plan(bad, lane_form=True)) == [0]
+
+
+@pytest.mark.parametrize("name", ["gate_zoo", "fq_add", "fq_mul", "fq12_mul", "fq_inverse", "g1_add"])
+def test_planned_program_computes_the_recorded_function(gsv, name):
+    """Planner self-check without a GPU: tasks, calls, task-local slots and recycled global slots, in
+    the levelised and the emission-order form and in a lane-only plan, against ExecuteMode."""
+    rng = np.random.default_rng(5)
+    both, lane = gsv.Program(name), gsv.Program(name, lane_only=True)
+    for _ in range(2):
+        bits = rng.integers(0, 2, both.n_inputs, dtype=np.uint8)
+        want = both.execute(bits)
+        assert np.array_equal(both.execute_plan(bits, lane_form=False), want)
+        assert np.array_equal(both.execute_plan(bits, lane_form=True), want)
+        assert np.array_equal(lane.execute_plan(bits, lane_form=True), want)
+    with pytest.raises(gsv.GsvError):
+        lane.execute_plan(bits, lane_form=False)
+
+
+def test_lane_only_plan_keeps_dependencies(gsv):
+    """A lane-only plan (no levelised task form) must carry the same RAW edges between calls: the
+    dependency-chain length of a serial circuit (Fq inverse: 2 x 254 dependent rounds) is a large
+    fraction of its gates in both plans."""
+    both = gsv.Program("fq_inverse")
+    lane = gsv.Program("fq_inverse", lane_only=True)
+    assert lane.n_gates == both.n_gates and lane.n_ciphertexts == both.n_ciphertexts
+    assert both.critical_path_gates > both.n_gates // 8
+    assert lane.critical_path_gates > lane.n_gates // 8
+    assert lane.critical_path_levels == 0 and both.critical_path_levels > 0

@@ -293,3 +293,38 @@ def test_keep_raw_stream_evaluates_without_commit(gsv, orc, circuit, mode):
         o = st.evaluate(orc.HASH_AES, bytes(res.true_label1[i]), bytes(res.false_label0[i]), act[i], bits[i], ref["cts"])
         assert np.array_equal(ev.output_active[i], o["output_active"])
         assert np.array_equal(ev.output_bits[i], o["output_bits"])
+
+
+def test_lane_only_program_matches_oracle(gsv, orc, circuit):
+    """Programs planned with lane_only (how the 11 G-gate verifier is planned for large batches) carry
+    only the emission-order task form; same commitment and labels."""
+    _, st = circuit("fq_inverse")
+    p = gsv.Program("fq_inverse", lane_only=True)
+    B = 64
+    seeds = list(range(900, 900 + B))
+    res = gsv.Session(p, B, ct_mode=gsv.CT_COMMIT, exec_mode=2).garble(seeds, gsv.HASH_AES)
+    for i in (0, 33, 63):
+        ref = st.garble(orc.HASH_AES, seeds[i], want_ct=False)
+        assert bytes(res.ct_commit[i]) == ref["ct_commit"]
+        assert np.array_equal(res.output_label0[i], ref["output_label0"])
+    with pytest.raises(gsv.GsvError):
+        gsv.Session(p, 2, exec_mode=1)  # no levelised form in this plan
+
+
+@pytest.mark.parametrize("mode,B", [(1, 4), (1, 3), (2, 40)])
+def test_host_folded_commitment_matches_gpu_chain(gsv, orc, circuit, mode, B, monkeypatch):
+    """GSV_CT_COMMIT_HOST: gate hashes on the GPU, the serial chain folded by host AES-NI threads
+    draining the ring (small ring and 1 MB drain buffers so both wrap many times)."""
+    monkeypatch.setenv("GSV_HOST_CHAIN_BUF_MB", "1")
+    p, st = circuit("fq12_mul")
+    seeds = [0, 42] + list(range(10, 10 + B - 2))
+    host = gsv.Session(p, B, ct_mode=gsv.CT_COMMIT_HOST, exec_mode=mode, ct_ring_log2=19).garble(seeds, gsv.HASH_AES)
+    dev = gsv.Session(p, B, ct_mode=gsv.CT_COMMIT, exec_mode=mode, ct_ring_log2=19).garble(seeds, gsv.HASH_AES)
+    assert np.array_equal(host.ct_commit, dev.ct_commit)
+    assert np.array_equal(host.output_label0, dev.output_label0)
+    for i in (0, 1):
+        ref = st.garble(orc.HASH_AES, seeds[i], want_ct=False)
+        assert bytes(host.ct_commit[i]) == ref["ct_commit"]
+    monkeypatch.delenv("GSV_HOST_CHAIN_BUF_MB")
+    again = gsv.Session(p, B, ct_mode=gsv.CT_COMMIT_HOST, exec_mode=mode).garble(seeds, gsv.HASH_AES)  # whole stream resident
+    assert np.array_equal(again.ct_commit, dev.ct_commit)
