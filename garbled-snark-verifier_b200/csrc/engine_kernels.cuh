@@ -53,8 +53,15 @@ struct EngineParams {
   uint32_t* pending;          // [item]: producers / slot owners still running
   const uint32_t* succ_off;   // [n_calls + 1] CSR of the reverse dependency edges
   const uint32_t* succ;
-  uint32_t* sched;            // [0] queue head, [1] queue tail, [2] items completed
+  uint32_t* sched;            // [0] queue head, [1] queue tail, [2] items completed, [3] park buckets released
   uint32_t queue_log2;
+  // ring governor (commit modes with a ciphertext ring): items that would overrun the ring are parked
+  unsigned long long* sched_limit;  // ciphertext index up to which ring space is free (min consumer + ring)
+  uint32_t* park_head;              // [n_buckets] lock-free lists of parked items, by ring-space need
+  uint32_t* park_next;              // [item]
+  unsigned long long park_q;        // bucket width in ciphertexts
+  uint32_t n_buckets;
+  uint32_t n_progress;              // consumer progress counters to take the minimum of
   uint32_t* error_flag;       // evaluate: set to 1 on ciphertext exhaustion
   unsigned long long* chain_progress;  // [chain warp] ciphertexts folded so far
   uint4* commit;        // [B] chain result
@@ -237,16 +244,84 @@ __device__ __forceinline__ uint32_t sched_pop(const EngineParams& p, uint32_t n_
     __nanosleep(100);
   }
 }
-// the calling threads (tid of nthreads) release the successors of a completed item; every thread
-// must have fenced its global stores and synchronised with the others before
-__device__ __forceinline__ void sched_complete(const EngineParams& p, uint32_t call_i, uint32_t grp, uint32_t tid,
-                                               uint32_t nthreads) {
+// ---- ring governor.  With a ciphertext ring, an item may only start once the ring has room for all
+// of its ciphertexts (need = ct_base + n_ct <= limit = slowest consumer + ring).  Out-of-order
+// scheduling can run far ahead of the consumer, so such items are PARKED in per-bucket lists
+// (bucket = need / park_q) instead of occupying a worker or cycling through the queue; one governor
+// warp tracks the consumers, publishes the limit and re-queues whole buckets once they are covered.
+// The item the consumer is waiting for always fits (ring >= 2 tasks), so progress is guaranteed.
+constexpr uint32_t PARK_EMPTY = 0xFFFFFFFFu;
+__device__ __forceinline__ void park_release_bucket(const EngineParams& p, uint32_t b) {
+  uint32_t h = atomicExch(p.park_head + b, PARK_EMPTY);
+  __threadfence();
+  while (h != PARK_EMPTY) {
+    const uint32_t nx = *reinterpret_cast<volatile uint32_t*>(p.park_next + h);
+    sched_push(p, h);
+    h = nx;
+  }
+}
+__device__ __forceinline__ void sched_park(const EngineParams& p, uint32_t item, unsigned long long need) {
+  const uint32_t b = (uint32_t)min((unsigned long long)(p.n_buckets - 1), need / p.park_q);
+  uint32_t h = *reinterpret_cast<volatile uint32_t*>(p.park_head + b);
+  for (;;) {
+    *reinterpret_cast<volatile uint32_t*>(p.park_next + item) = h;
+    __threadfence();
+    const uint32_t seen = atomicCAS(p.park_head + b, h, item);
+    if (seen == h) break;
+    h = seen;
+  }
+  __threadfence();
+  // the governor may have swept this bucket just before the insertion
+  if (ld_acquire(p.sched + 3) > b) park_release_bucket(p, b);
+}
+// true when the item may start now; otherwise it has been parked
+__device__ __forceinline__ bool sched_ring_admit(const EngineParams& p, uint32_t item) {
+  const uint32_t ci = item / p.n_groups;
+  const unsigned long long need = p.calls[ci].ct_base + p.tasks[p.calls[ci].task].n_ct;
+  if (need <= p.ct_ring || need <= ld_acquire64(p.sched_limit)) return true;
+  sched_park(p, item, need);
+  return false;
+}
+__device__ __forceinline__ void governor_warp(const EngineParams& p) {
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t n_items = p.n_calls * p.n_groups;
+  uint32_t released = 0;
+  for (;;) {
+    const bool done = ld_acquire(p.sched + 2) >= n_items;
+    unsigned long long m = ~0ull;
+    for (uint32_t i = lane; i < p.n_progress; i += 32) m = min(m, ld_acquire64(p.chain_progress + i));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(FULL, m, o));
+    const unsigned long long limit = m + p.ct_ring;
+    if (lane == 0) st_release64(p.sched_limit, limit);
+    const uint32_t nb = (uint32_t)min((unsigned long long)p.n_buckets, limit / p.park_q);  // fully covered
+    if (nb > released) {
+      if (lane == 0) st_release(p.sched + 3, nb);
+      __threadfence();
+      __syncwarp();
+      for (uint32_t b = released + lane; b < nb; b += 32) park_release_bucket(p, b);
+      released = nb;
+    }
+    if (done) break;
+    __nanosleep(2000);
+  }
+}
+
+// Completion of an item: its successors' counters drop; those that reach zero become ready.  One
+// ready successor is KEPT by the completing worker (no queue round trip on the dependent chains
+// that make up a circuit's critical path), the others are queued.  Every thread must have fenced
+// its global stores and synchronised with the others before.
+constexpr uint32_t SCHED_NONE = 0xFFFFFFFEu;
+// worker of nthreads threads; `keep` is the worker's shared-memory word (SCHED_NONE on entry)
+__device__ __forceinline__ void sched_complete_cta(const EngineParams& p, uint32_t call_i, uint32_t grp, uint32_t tid,
+                                                   uint32_t nthreads, uint32_t* keep) {
   const uint32_t lo = p.succ_off[call_i], hi = p.succ_off[call_i + 1];
   for (uint32_t k = lo + tid; k < hi; k += nthreads) {
     const uint32_t it = p.succ[k] * p.n_groups + grp;
     if (atomicSub(p.pending + it, 1u) == 1u) {
       __threadfence();  // order after the other producers' releases observed through the counter
-      sched_push(p, it);
+      if (atomicCAS(keep, SCHED_NONE, it) != SCHED_NONE) sched_push(p, it);
     }
   }
   if (tid == 0) {
@@ -254,10 +329,41 @@ __device__ __forceinline__ void sched_complete(const EngineParams& p, uint32_t c
     atomicAdd(p.sched + 2, 1u);
   }
 }
+// one warp; returns the kept item (uniform) or SCHED_NONE
+__device__ __forceinline__ uint32_t sched_complete_warp(const EngineParams& p, uint32_t call_i, uint32_t grp,
+                                                        uint32_t lane) {
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t lo = p.succ_off[call_i], hi = p.succ_off[call_i + 1];
+  uint32_t keep = SCHED_NONE;
+  for (uint32_t k = lo; k < hi; k += 32) {
+    uint32_t it = 0;
+    bool rdy = false;
+    if (k + lane < hi) {
+      it = p.succ[k + lane] * p.n_groups + grp;
+      rdy = atomicSub(p.pending + it, 1u) == 1u;
+      if (rdy) __threadfence();
+    }
+    const uint32_t m = __ballot_sync(FULL, rdy);
+    if (m) {
+      uint32_t first = 32;
+      if (keep == SCHED_NONE) {
+        first = __ffs(m) - 1;
+        keep = __shfl_sync(FULL, it, first);
+      }
+      if (rdy && lane != first) sched_push(p, it);
+    }
+  }
+  if (lane == 0) {
+    st_release(p.flags + (size_t)call_i * p.n_groups + grp, p.epoch);
+    atomicAdd(p.sched + 2, 1u);
+  }
+  return keep;
+}
 
 // pending[item] = number of dependencies; items without any are pushed right away
 __global__ void k_sched_init(const EngineParams p) {
   const uint32_t n_items = p.n_calls * p.n_groups;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.sched_limit = p.ct_ring;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
     const uint32_t nd = p.calls[i / p.n_groups].n_deps;
     p.pending[i] = nd;
@@ -309,7 +415,9 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
     // ---- chain CTA: the last n_chain_ctas SMs only run commitment consumers, a few warps per
     // SMSP, so the latency-bound chain never competes with garbling warps for issue slots
     const uint32_t warp = threadIdx.x >> 5;
-    if (p.host_chain) {
+    if (p.ct_ring && blockIdx.x == gridDim.x - p.n_chain_ctas && warp == (blockDim.x >> 5) - 1) {
+      governor_warp(p);
+    } else if (p.host_chain) {
       if (warp == 0) publish_warp(p);
     } else if (warp < p.n_chain_warps) {
       chain_warp(p, te, (blockIdx.x - (gridDim.x - p.n_chain_ctas)) * p.n_chain_warps + warp);
@@ -327,9 +435,11 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
   uint8_t* tail = reinterpret_cast<uint8_t*>(smem + TE_Q + n_workers * lab_words);
   uint8_t* sval = tail + worker * lab_words;
   uint8_t* tail2 = tail + (MODE == 1 ? n_workers * lab_words : 0);
-  volatile uint32_t* ctrl = reinterpret_cast<volatile uint32_t*>(tail2) + worker;
+  volatile uint32_t* ctrl = reinterpret_cast<volatile uint32_t*>(tail2) + 2 * worker;
+  uint32_t* keep = reinterpret_cast<uint32_t*>(tail2) + 2 * worker + 1;  // successor kept at completion
+  if (wt == 0) *keep = SCHED_NONE;
   // gate-record ring, 16-byte aligned behind the value bytes and the ticket words
-  const uint32_t tail_bytes = ((MODE == 1 ? n_workers * lab_words : 0u) + n_workers * 4u + 15u) & ~15u;
+  const uint32_t tail_bytes = ((MODE == 1 ? n_workers * lab_words : 0u) + n_workers * 8u + 15u) & ~15u;
   const uint4* ring = reinterpret_cast<const uint4*>(tail + tail_bytes) + worker * GATE_RING;
   const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
 
@@ -338,18 +448,12 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
 
   for (;;) {
     if (wt == 0) {
-      uint32_t it;
+      uint32_t it = *keep;
+      *keep = SCHED_NONE;
       for (;;) {
-        it = sched_pop(p, n_items);
-        if (it == SCHED_DONE || MODE != 0 || !p.ct_ring) break;
-        // ring space: an item whose ciphertexts would overrun the unconsumed part of the ring goes
-        // back to the end of the queue (the items the consumer is waiting for are ahead of it)
-        const uint32_t ci = it / p.n_groups, gi = it - ci * p.n_groups;
-        const unsigned long long need = p.calls[ci].ct_base + p.tasks[p.calls[ci].task].n_ct;
-        const unsigned long long* pr = p.chain_progress + (p.host_chain ? 0u : (gi * G) / CHAIN_INST);  // G divides 8
-        if (need <= p.ct_ring || ld_acquire64(pr) + p.ct_ring >= need) break;
-        sched_push(p, it);
-        __nanosleep(256);
+        if (it == SCHED_NONE) it = sched_pop(p, n_items);
+        if (it == SCHED_DONE || MODE != 0 || !p.ct_ring || sched_ring_admit(p, it)) break;
+        it = SCHED_NONE;  // parked until the ring has room
       }
       *ctrl = it;
     }
@@ -461,7 +565,8 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
     }
     __threadfence();
     named_bar(bar_id, NT);
-    sched_complete(p, call_i, grp, wt, NT);
+    sched_complete_cta(p, call_i, grp, wt, NT, keep);
+    named_bar(bar_id, NT);
   }
 }
 
@@ -482,7 +587,9 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   if (MODE == 0 && blockIdx.x >= gridDim.x - p.n_chain_ctas) {
     // chain CTA (see k_engine): dedicated SMs for the serial commitment
-    if (p.host_chain) {
+    if (p.ct_ring && blockIdx.x == gridDim.x - p.n_chain_ctas && warp == (blockDim.x >> 5) - 1) {
+      governor_warp(p);
+    } else if (p.host_chain) {
       if (warp == 0) publish_warp(p);
     } else if (warp < p.n_chain_warps) {
       chain_warp(p, te, (blockIdx.x - (gridDim.x - p.n_chain_ctas)) * p.n_chain_warps + warp);
@@ -496,23 +603,20 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
   const uint32_t n_items = p.n_calls * p.n_groups;
   constexpr uint32_t FULL = 0xFFFFFFFFu;
 
+  uint32_t kept = SCHED_NONE;
   for (;;) {
-    uint32_t item = 0;
+    uint32_t item = kept;
+    kept = SCHED_NONE;
     for (;;) {
-      if (lane == 0) item = sched_pop(p, n_items);
-      item = __shfl_sync(FULL, item, 0);
-      if (item == SCHED_DONE || MODE != 0 || !p.ct_ring) break;
-      // ring space (see k_engine): the group's 32 instances are served by 4 chain warps, one lane each
-      const uint32_t ci = item / p.n_groups, gi = item - ci * p.n_groups;
-      const unsigned long long need = p.calls[ci].ct_base + p.tasks[p.calls[ci].task].n_ct;
-      bool ok = true;
-      if (need > p.ct_ring && lane < 32 / CHAIN_INST) {
-        const uint32_t cwi = gi * (32 / CHAIN_INST) + lane;
-        if (cwi * CHAIN_INST < p.B) ok = ld_acquire64(p.chain_progress + (p.host_chain ? 0u : cwi)) + p.ct_ring >= need;
+      if (item == SCHED_NONE) {
+        if (lane == 0) item = sched_pop(p, n_items);
+        item = __shfl_sync(FULL, item, 0);
       }
-      if (__all_sync(FULL, ok)) break;
-      if (lane == 0) sched_push(p, item);
-      __nanosleep(256);
+      if (item == SCHED_DONE || MODE != 0 || !p.ct_ring) break;
+      uint32_t ok = 0;
+      if (lane == 0) ok = sched_ring_admit(p, item) ? 1u : 0u;
+      if (__shfl_sync(FULL, ok, 0)) break;
+      item = SCHED_NONE;  // parked until the ring has room
     }
     if (item == SCHED_DONE) break;
     const uint32_t call_i = item / p.n_groups;
@@ -630,7 +734,7 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
     }
     __threadfence();
     __syncwarp();
-    sched_complete(p, call_i, grp, lane, 32);
+    kept = sched_complete_warp(p, call_i, grp, lane);
   }
 }
 

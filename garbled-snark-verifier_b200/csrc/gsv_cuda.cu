@@ -429,7 +429,9 @@ struct gsv_session {
   DevBuf<uint8_t> d_vals, d_io_bits;
   DevBuf<uint32_t> d_flags, d_ctrl;  // d_ctrl[1] = error flag, [4..6] = scheduler head / tail / completed
   DevBuf<uint32_t> d_succ_off, d_succ, d_pending;
-  DevBuf<unsigned long long> d_queue;
+  DevBuf<unsigned long long> d_queue, d_limit;
+  DevBuf<uint32_t> d_park_head, d_park_next;
+  uint64_t park_q = 1;
   uint32_t queue_log2 = 0;
   DevBuf<unsigned long long> d_progress;
   DevBuf<unsigned long long> d_seeds;
@@ -565,6 +567,12 @@ EngineParams make_params(gsv_session* s) {
   p.succ_off = s->d_succ_off.p;
   p.succ = s->d_succ.p;
   p.queue_log2 = s->queue_log2;
+  p.sched_limit = s->d_limit.p;
+  p.park_head = s->d_park_head.p;
+  p.park_next = s->d_park_next.p;
+  p.park_q = s->park_q;
+  p.n_buckets = (uint32_t)s->d_park_head.n;
+  p.n_progress = s->ct_mode == GSV_CT_COMMIT_HOST ? 1u : (s->B + CHAIN_INST - 1) / CHAIN_INST;
   p.error_flag = s->d_ctrl.p + 1;
   p.chain_progress = s->d_progress.p;
   p.commit = s->d_commit.p;
@@ -601,6 +609,7 @@ void launch_engine(gsv_session* s, int hasher, const EngineParams& p) {
   // scheduler reset: empty queue, counters at zero, dependency counts loaded, root items queued
   CUDA_TRY(cudaMemsetAsync(s->d_ctrl.p + 4, 0, 16, s->stream));
   CUDA_TRY(cudaMemsetAsync(s->d_queue.p, 0, s->d_queue.n * 8, s->stream));
+  if (s->d_park_head.n) CUDA_TRY(cudaMemsetAsync(s->d_park_head.p, 0xFF, s->d_park_head.n * 4, s->stream));
   {
     const size_t n_items = (size_t)p.n_calls * p.n_groups;
     k_sched_init<<<(unsigned)std::min<size_t>((n_items + 255) / 256 + 1, 4096), 256, 0, s->stream>>>(p);
@@ -621,7 +630,7 @@ void launch_engine(gsv_session* s, int hasher, const EngineParams& p) {
     return;
   }
   const size_t smem = MODE == 0 ? s->smem_garble : s->smem_eval;
-  dim3 grid(s->sm_count), block(std::max<uint32_t>(s->n_workers * s->NT, 32 * p.n_chain_warps));
+  dim3 grid(s->sm_count), block(std::max<uint32_t>(s->n_workers * s->NT, 32 * (p.n_chain_warps + (p.n_chain_ctas ? 1 : 0))));  // + governor warp
 #define GSV_LAUNCH(GG, HH)                                                                              \
   do {                                                                                                  \
     CUDA_TRY(cudaFuncSetAttribute(k_engine<GG, HH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
@@ -778,7 +787,7 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
     s->n_chain_ctas = 0;
     if (chain_warps_total) {
       uint32_t per_cta = 16;
-      if (const char* e = getenv("GSV_CHAIN_WARPS_PER_SM")) per_cta = std::max(1, std::min(32, atoi(e)));
+      if (const char* e = getenv("GSV_CHAIN_WARPS_PER_SM")) per_cta = std::max(1, std::min(31, atoi(e)));  // warp 31: governor
       n_chain = std::min(per_cta, chain_warps_total);
       s->n_chain_ctas = (chain_warps_total + n_chain - 1) / n_chain;
       if (s->n_chain_ctas * 2 > (uint32_t)s->sm_count)
@@ -794,7 +803,7 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
     // largest G (power of two dividing B, <= 8) whose label working set fits next to the tables
     auto smem_for = [&](uint32_t G, uint32_t nw, bool eval) {
       size_t lab = (size_t)slots * G;
-      return (size_t)AES_TABLE_BYTES + nw * lab * 16 + (((eval ? nw * lab : 0) + nw * 4 + 15) & ~(size_t)15) + (size_t)nw * GATE_RING * 16;
+      return (size_t)AES_TABLE_BYTES + nw * lab * 16 + (((eval ? nw * lab : 0) + nw * 8 + 15) & ~(size_t)15) + (size_t)nw * GATE_RING * 16;
     };
     // execution mode: lane mode (warp = 32 instances) for batches that fill warps, the levelised
     // shared-memory mode otherwise
@@ -898,8 +907,13 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
         if (ring < 2 * max_task_ct) throw std::runtime_error("ciphertext ring smaller than two tasks; fewer instances needed");
         s->ct_ring = ring;
         s->d_ct.alloc((size_t)ring * s->B);
+        // ring governor: parking buckets of ring/16 ciphertexts
+        s->park_q = std::max<uint64_t>(ring / 16, 1);
+        s->d_park_head.alloc((size_t)(total / s->park_q + 2));
+        s->d_park_next.alloc(std::max<size_t>(g.calls.size() * (size_t)s->n_groups, 1));
       }
     }
+    s->d_limit.alloc(1);
     return s.release();
   } catch (const std::exception& e) {
     fail(std::string(e.what()).find("no CUDA device") != std::string::npos ? GSV_ERR_NO_DEVICE : GSV_ERR_CUDA, e.what());
