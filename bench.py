@@ -1,15 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- garbled gates/s of the B200 engine on the largest circuit the generator builds.
+"""bench.py -- garbled gates/s of the B200 engine on the Groth16 verifier circuit.
 
 A "step" garbles one batch of B cut-and-choose instances of the workload circuit per GPU from
 seeds (seed expansion -> garbling -> bit-exact ciphertext chain commitment), i.e. the first
 garbling stage of the reference's cut-and-choose (src/cut_and_choose/garbler.rs:191-242) with
 `AesNiHasher` + `AESAccumulatingHash`.
 
-  value : whole-job gates/s, device time (CUDA events inside the library, on its stream), seeds
-          already resident in HBM being the only input.
-  e2e   : same metric through the public API with HOST buffers (seeds H2D, commitments + input /
-          output labels D2H inside the timed region).
+Workloads (--workload):
+  verifier (default) : groth16_verify_compressed (11.46 G gates, 2.98 G ciphertexts; BASELINE.json
+          configs 2/4) x 32 instances per GPU, levelised kernel, commitment in GSV_CT_COMMIT_HOST mode:
+          every gate hash on the GPU, the strictly serial AES chain folded by host AES-NI threads that
+          drain the ciphertext ring while the kernel runs (a GPU folds one dependent AES per 0.46 us:
+          23 min for 2.98 G ciphertexts, whatever the batch).
+  batch   : fq12_mul (20.3 M gates) x 6144 instances per GPU, lane kernel, commitment fused on the GPU
+          (GSV_CT_COMMIT): the large-batch regime where thousands of chains run side by side.
+
+  value : whole-job gates/s over the device time of the step (CUDA events inside the library, on its
+          stream), seeds already resident in HBM being the only input.
+  e2e   : same metric over the wall time of the public API call with HOST buffers (seeds H2D; commitments,
+          input / output labels D2H; in the verifier workload also the ciphertext drain and the host
+          fold, which end a few seconds after the kernel) -- the headline.
   --impl reference : the CPU oracle (AES-NI restatement of the reference's per-gate loop; the
           reference itself is Rust and cannot be built in this image) on all host cores.
 
@@ -118,19 +128,20 @@ def run_reference(args):
     rates = []
     per_core = max(1, args.ref_instances_per_core)
     for i in range(args.warmup + args.steps):
-        rate, dt, prog, aesni = cpu_garble_rate(args.circuit, per_core, cores)
+        rate, dt, prog, aesni = cpu_garble_rate(args.cpu_circuit, per_core, cores)
         if i >= args.warmup:
             rates.append((rate, dt))
     value = sum(r for r, _ in rates) / len(rates)
     ms = 1e3 * sum(d for _, d in rates) / len(rates)
-    sample = (f"{per_core} instance(s) of {args.circuit} per core on {cores} threads per step, garble + chain "
+    sample = (f"{per_core} instance(s) of {args.cpu_circuit} per core on {cores} threads per step, garble + chain "
               f"commitment, {'AES-NI' if aesni else 'portable AES'}; oracle omits the reference's slab/credit "
               f"bookkeeping (upper bound on the reference's CPU speed)")
     line = {
         "impl": "reference", "metric": "garbled_gates_per_s", "value": value, "unit": "gates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{args.circuit} garble+commit, AES hasher (CPU oracle, bounded sample)",
+        "config": {"workload": f"{args.circuit} garble+commit, AES hasher (CPU oracle; bounded sample: "
+                               f"{args.cpu_circuit} instances, independent per core)",
                    "gates_per_instance": prog.n_gates},
         "cpu_baseline": {"value": value, "unit": "gates/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -141,13 +152,15 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gsv", choices=["gsv", "reference"])
-    ap.add_argument("--circuit", default="fq12_mul")
-    ap.add_argument("--instances", type=int, default=6144, help="cut-and-choose instances per GPU")
-    ap.add_argument("--exec-mode", type=int, default=0, help="0 auto, 1 levelised, 2 lane")
-    ap.add_argument("--group", type=int, default=0)
+    ap.add_argument("--workload", default="verifier", choices=["verifier", "batch"])
+    ap.add_argument("--circuit", default=None, help="override the workload's circuit")
+    ap.add_argument("--instances", type=int, default=None, help="cut-and-choose instances per GPU")
+    ap.add_argument("--exec-mode", type=int, default=None, help="0 auto, 1 levelised, 2 lane")
+    ap.add_argument("--group", type=int, default=None)
+    ap.add_argument("--ct-mode", default=None, choices=["commit", "commit_host", "none"])
     ap.add_argument("--worker-threads", type=int, default=0)
     ap.add_argument("--hasher", default="aes", choices=["aes", "blake3"])
     ap.add_argument("--no-commit", action="store_true", help="drop ciphertexts (the `()` handler)")
@@ -155,6 +168,18 @@ def main():
     ap.add_argument("--cpu-baseline-instances", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # workload presets (explicit flags win)
+    preset = {"verifier": dict(circuit="groth16_verify_compressed", instances=32, exec_mode=1, group=2,
+                               ct_mode="commit_host", steps=1),
+              "batch": dict(circuit="fq12_mul", instances=6144, exec_mode=2, group=0, ct_mode="commit", steps=3)}[args.workload]
+    for k, v in preset.items():
+        if getattr(args, k) is None:
+            setattr(args, k, v)
+    if args.no_commit:
+        args.ct_mode = "none"
+    # the CPU oracle needs the flat gate stream in memory (13 B/gate): the verifier's CPU sample is its
+    # dominant sub-circuit, the Fq12 multiplication (same gate mix: 26.8 % vs 26.0 % non-free gates)
+    args.cpu_circuit = args.circuit if args.circuit != "groth16_verify_compressed" else "fq12_mul"
 
     if args.impl == "reference":
         run_reference(args)
@@ -176,13 +201,19 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     hasher = g.HASH_AES if args.hasher == "aes" else g.HASH_BLAKE3
-    ct_mode = g.CT_NONE if args.no_commit else g.CT_COMMIT
+    ct_mode = {"none": g.CT_NONE, "commit": g.CT_COMMIT, "commit_host": g.CT_COMMIT_HOST}[args.ct_mode]
+    t_plan = time.perf_counter()
     prog = g.Program(args.circuit)
+    t_plan = time.perf_counter() - t_plan
     B = args.instances
     sess = g.Session(prog, B, device=local, group=args.group, worker_threads=args.worker_threads, ct_mode=ct_mode,
                      exec_mode=args.exec_mode)
     lane = args.exec_mode == 2 or (args.exec_mode == 0 and args.group == 0 and B >= 128)
     kernel_name = "k_lane" if lane else "k_engine"
+    commit_txt = {"none": "no commitment (ciphertexts dropped)",
+                  "commit": "bit-exact AES chain commitment fused into the kernel (chain CTAs)",
+                  "commit_host": "bit-exact AES chain commitment, gate hashes on the GPU, serial chain folded by "
+                                 "host AES-NI threads draining the ciphertext ring during the kernel"}[args.ct_mode]
     # cut-and-choose seeds: instance i of rank r (garbler.rs:201-203 draws them from one RNG;
     # here a fixed arithmetic pattern so every rank/step is reproducible)
     def seeds_for(step):
@@ -200,7 +231,9 @@ def main():
     gathered = torch.empty((world * B, 16), dtype=torch.uint8, device="cuda") if world > 1 else None
 
     def step(i, want_labels):
+        t1 = time.perf_counter()
         res = sess.garble(seeds_for(i), hasher, want_inputs=want_labels, want_outputs=want_labels)
+        res.wall_ms = 1e3 * (time.perf_counter() - t1)
         if world > 1:
             # the only collective of the path: gather the per-instance commitments
             commits_dev.copy_(torch.from_numpy(res.ct_commit))
@@ -238,6 +271,8 @@ def main():
     e2e = gates_per_step * args.steps / (wall_ms_max * 1e-3)
     h2d = 8 * B
     d2h = B * 16 * (4 + prog.n_inputs + prog.n_outputs)
+    if args.ct_mode == "commit_host":
+        d2h += B * 16 * prog.n_ciphertexts  # the ciphertext stream itself is drained to the host
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -249,10 +284,19 @@ def main():
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "kernel": kernel_name, "kernel_ms": k_ms, "peak_source": peak_src,
                     "algorithmic_bytes_per_gate": ALGO_BYTES_PER_GATE}
+        if prog.critical_path_levels and not lane:
+            # what actually bounds the levelised kernel at this batch size: the circuit's dependency chain
+            roofline["latency_floor"] = {
+                "critical_path_levels": prog.critical_path_levels,
+                "us_per_level_at_measured_time": 1e3 * k_ms / prog.critical_path_levels,
+                "note": "one barrier-separated level = a dependent fixed-key AES through shared-memory tables; "
+                        "kernel time / critical-path levels is the per-level latency if nothing else limited the run"}
+        if args.ct_mode == "commit_host":
+            roofline["gpu_chain_floor_s"] = prog.n_ciphertexts * 0.46e-6  # measured dependent-AES step, profiles/r01_chain_poll.md
         try:
             blocks = g.bench_hash(hasher, 1 << 28, 2, device=local)
             nonfree = sum(prog.type_count[:8]) / prog.n_gates
-            need = nonfree * (AES_BLOCKS_PER_GATE_GARBLE + (0.0 if args.no_commit else 1.0)) * k_gates / (k_ms * 1e-3)
+            need = nonfree * (AES_BLOCKS_PER_GATE_GARBLE + (1.0 if args.ct_mode == "commit" else 0.0)) * k_gates / (k_ms * 1e-3)
             roofline["alu"] = {"hash_blocks_per_s_peak": blocks, "hash_blocks_per_s_achieved": need,
                                "frac": need / blocks, "note": "register-resident 2-block gate-hash micro-kernel"}
         except Exception as e:  # pragma: no cover
@@ -262,16 +306,18 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {
-                "workload": f"{args.circuit} x {B} cut-and-choose instances per GPU, garble + "
-                            f"{'no commitment' if args.no_commit else 'bit-exact AES chain commitment'}, "
-                            f"{args.hasher} gate hasher (largest circuit the generator builds; the k=6 "
-                            f"verifier generator is not built yet)",
+                "workload": f"{args.circuit} x {B} cut-and-choose instances per GPU, garble + {commit_txt}, "
+                            f"{args.hasher} gate hasher"
+                            + (" (BASELINE.json configs 2/4: Groth16 verifier, 1 public input, synthetic vk; "
+                               "11.46 G gates here vs the reference's 11.17 G for its own vk)"
+                               if args.circuit == "groth16_verify_compressed" else ""),
+                "kernel": kernel_name, "plan_s": round(t_plan, 1),
                 "gates_per_instance": prog.n_gates, "ciphertexts_per_instance": prog.n_ciphertexts,
                 "instances_per_gpu": B, "l2": "inputs larger than L2 (label + ciphertext state >> 126 MB)",
                 "parallelism": f"instances sharded over {world} GPU(s); NCCL all-gather of commitments only",
             },
             "phases_ms_per_step": {"seed_expand": seed_ms / args.steps, "garble": garble_ms / args.steps,
-                                   "chain_commit": "fused into the garble kernel (chain CTAs)"},
+                                   "commit_tail_after_kernel": commit_ms / args.steps},
             "e2e": {"value": e2e, "unit": "gates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "clocks": clocks,
@@ -279,10 +325,10 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            rate, dt, _, aesni = cpu_garble_rate(args.circuit, args.cpu_baseline_instances, cores)
+            rate, dt, _, aesni = cpu_garble_rate(args.cpu_circuit, args.cpu_baseline_instances, cores)
             line["cpu_baseline"] = {
                 "value": rate, "unit": "gates/s", "cores": cores, "kind": "port",
-                "sample": f"{args.cpu_baseline_instances} instance(s) of {args.circuit} per core on {cores} threads "
+                "sample": f"{args.cpu_baseline_instances} instance(s) of {args.cpu_circuit} per core on {cores} threads "
                           f"({dt:.1f} s), garble + chain commitment, {'AES-NI' if aesni else 'portable AES'} oracle",
             }
         print(json.dumps(line), flush=True)

@@ -4,6 +4,8 @@
 #include <immintrin.h>
 #include <wmmintrin.h>
 
+#include <cstdlib>
+
 namespace gsv {
 namespace {
 
@@ -58,6 +60,41 @@ void fold_w(uint8_t* h, const uint8_t* base, size_t pos_bytes, size_t inst_bytes
   for (int i = 0; i < W; i++) _mm_storeu_si128(reinterpret_cast<__m128i*>(h) + i, s[i]);
 }
 
+// VAES (AVX-512): four chains per 512-bit register, Z registers interleaved -> 4 * Z chains per thread
+// at one vaesenc per cycle instead of 8 chains of 128-bit aesenc.
+template <int Z>
+__attribute__((target("avx512f,avx512vl,vaes"))) void fold_vaes(uint8_t* h, const uint8_t* base, size_t pos_bytes,
+                                                                size_t inst_bytes, size_t n_pos, const RoundKeys& rk) {
+  __m512i k[11];
+  for (int r = 0; r < 11; r++) k[r] = _mm512_broadcast_i32x4(rk.k[r]);
+  __m512i s[Z];
+  const uint8_t* src[Z][4];
+  for (int z = 0; z < Z; z++) {
+    s[z] = _mm512_loadu_si512(h + 64 * z);
+    for (int j = 0; j < 4; j++) src[z][j] = base + (size_t)(4 * z + j) * inst_bytes;
+  }
+  for (size_t p = 0; p < n_pos; p++) {
+    for (int z = 0; z < Z; z++) {
+      __m512i c = _mm512_castsi128_si512(_mm_loadu_si128(reinterpret_cast<const __m128i*>(src[z][0])));
+      c = _mm512_inserti32x4(c, _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[z][1])), 1);
+      c = _mm512_inserti32x4(c, _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[z][2])), 2);
+      c = _mm512_inserti32x4(c, _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[z][3])), 3);
+      s[z] = _mm512_xor_si512(_mm512_xor_si512(s[z], c), k[0]);
+      for (int j = 0; j < 4; j++) src[z][j] += pos_bytes;
+    }
+    for (int r = 1; r < 10; r++)
+      for (int z = 0; z < Z; z++) s[z] = _mm512_aesenc_epi128(s[z], k[r]);
+    for (int z = 0; z < Z; z++) s[z] = _mm512_aesenclast_epi128(s[z], k[10]);
+  }
+  for (int z = 0; z < Z; z++) _mm512_storeu_si512(h + 64 * z, s[z]);
+}
+
+bool have_vaes() {
+  static const bool v = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl") &&
+                        __builtin_cpu_supports("vaes") && !getenv("GSV_HOST_CHAIN_NO_VAES");
+  return v;
+}
+
 }  // namespace
 
 bool host_chain_available() { return __builtin_cpu_supports("aes") && __builtin_cpu_supports("sse4.1"); }
@@ -67,6 +104,17 @@ void host_chain_fold(uint8_t* h, const uint8_t* base, size_t pos_stride, size_t 
   static const RoundKeys rk = make_keys();
   const size_t pb = pos_stride * 16, ib = inst_stride * 16;
   uint32_t i = 0;
+  if (have_vaes()) {
+    for (; i + 16 <= n_inst; i += 16) fold_vaes<4>(h + 16 * i, base + ib * i, pb, ib, n_pos, rk);
+    if (i + 8 <= n_inst) {
+      fold_vaes<2>(h + 16 * i, base + ib * i, pb, ib, n_pos, rk);
+      i += 8;
+    }
+    if (i + 4 <= n_inst) {
+      fold_vaes<1>(h + 16 * i, base + ib * i, pb, ib, n_pos, rk);
+      i += 4;
+    }
+  }
   for (; i + 8 <= n_inst; i += 8) fold_w<8>(h + 16 * i, base + ib * i, pb, ib, n_pos, rk);
   if (i + 4 <= n_inst) {
     fold_w<4>(h + 16 * i, base + ib * i, pb, ib, n_pos, rk);
