@@ -482,8 +482,10 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
     const unsigned long long ct_pos0 = p.ct_ring ? call.ct_base % p.ct_ring : call.ct_base;
     // ---- gather inputs (and the two constant wires) into shared memory
     const size_t gbase = (size_t)grp * p.n_global_slots;
-    uint4 delta = make_uint4(0, 0, 0, 0);
-    if (MODE == 0) delta = p.delta[grp * G + inst];
+    // garbling: the lane pair (wt >> 1) serves instance pinst of the group
+    const uint32_t pinst = (wt >> 1) % G;
+    uint4 pdelta = make_uint4(0, 0, 0, 0);
+    if (MODE == 0) pdelta = p.delta[grp * G + pinst];
     if (wt < 2 * G) {
       const uint32_t s = wt / G;
       lab[s * G + inst] = __ldcg(p.labels + (gbase + s) * G + inst);
@@ -506,6 +508,58 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
     uint32_t pos = 0, released = 0;
     for (uint32_t lvl = 0; lvl < task.n_levels; ++lvl) {
       const uint32_t n = (((ring[pos & (GATE_RING - 1)].y >> 25) & 0x7Fu) + 1u) * G;
+      if (MODE == 0) {
+        // Garbling: a PAIR of adjacent lanes serves one (gate, instance).  The two hashes of a
+        // half-gate, H(A_sel) and H(A_sel ^ delta), run one per lane and are exchanged by shuffle:
+        // half the dependent instruction stream per level, which is what bounds a run that sits on
+        // the circuit's critical path (one warp issues at most one instruction per cycle).
+        constexpr uint32_t FULL = 0xFFFFFFFFu;
+        const uint32_t half = wt & 1u;
+        for (uint32_t base = 0; base < n; base += NT / 2) {  // uniform trip count: shuffles are full-warp
+          const uint32_t u = base + (wt >> 1);
+          const bool active = u < n;
+          uint4 graw = make_uint4(0, 10u << 16, 0, 0);
+          if (active) graw = ring[(pos + u / G) & (GATE_RING - 1)];
+          const uint32_t sa = graw.x & 0xFFFFu, sb = graw.x >> 16, sc = graw.y & 0xFFFFu;
+          const uint32_t type = (graw.y >> 16) & 0xFFu;
+          uint4 la = make_uint4(0, 0, 0, 0), lb = la, lc = la, hs = la;
+          if (active) {
+            la = lab[sa * G + pinst];
+            lb = lab[sb * G + pinst];
+          }
+          const bool nonfree = active && type < 8;
+          const unsigned long long gid = call.gid_base + graw.z;
+          const uint32_t ma = 0u - ((type >> 2) & 1u), mb = 0u - ((type >> 1) & 1u), mc = 0u - (type & 1u);
+          if (nonfree) {
+            uint4 x = xor4(la, and4(pdelta, ma));  // selected label; the odd lane hashes the other one
+            if (half) x = xor4(x, pdelta);
+            hs = hash1<HASH>(te, x, gid);
+          } else if (active) {
+            lc = (type == 10) ? xor4(la, pdelta) : xor4(la, lb);
+            if (type == 9) lc = xor4(lc, pdelta);
+          }
+          uint4 ho;
+          ho.x = __shfl_xor_sync(FULL, hs.x, 1);
+          ho.y = __shfl_xor_sync(FULL, hs.y, 1);
+          ho.z = __shfl_xor_sync(FULL, hs.z, 1);
+          ho.w = __shfl_xor_sync(FULL, hs.w, 1);
+          if (nonfree) {
+            const uint4 h0 = half ? ho : hs;
+            if (half) {
+              if (p.write_ct) {
+                const uint4 ct = xor4(xor4(hs, ho), xor4(lb, and4(pdelta, mb)));
+                unsigned long long cpos = ct_pos0 + graw.w;
+                if (p.ct_ring && cpos >= p.ct_ring) cpos -= p.ct_ring;
+                __stcg(p.ct + (size_t)cpos * p.ct_pos_stride + (size_t)(grp * G + pinst) * p.ct_inst_stride, ct);
+              }
+            } else {
+              lab[sc * G + pinst] = xor4(h0, and4(pdelta, mc));
+            }
+          } else if (active && !half) {
+            lab[sc * G + pinst] = lc;
+          }
+        }
+      } else
       for (uint32_t idx = wt; idx < n; idx += NT) {
         const uint4 graw = ring[(pos + idx / G) & (GATE_RING - 1)];
         const uint32_t sa = graw.x & 0xFFFFu, sb = graw.x >> 16, sc = graw.y & 0xFFFFu;
@@ -513,23 +567,7 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
         const uint4 la = lab[sa * G + inst];
         const uint4 lb = lab[sb * G + inst];
         uint4 lc;
-        if (MODE == 0) {
-          if (type >= 8) {
-            // free gates: Xor, Xnor (^delta), Not (a ^ delta)
-            lc = (type == 10) ? xor4(la, delta) : xor4(la, lb);
-            if (type == 9) lc = xor4(lc, delta);
-          } else {
-            const unsigned long long gid = call.gid_base + graw.z;
-            uint4 ct;
-            lc = garble_nonfree<HASH>(te, type, la, lb, delta, gid, ct);
-            if (p.write_ct)
-            {
-              unsigned long long cpos = ct_pos0 + graw.w;
-              if (p.ct_ring && cpos >= p.ct_ring) cpos -= p.ct_ring;
-              __stcg(p.ct + (size_t)cpos * p.ct_pos_stride + (size_t)(grp * G + inst) * p.ct_inst_stride, ct);
-            }
-          }
-        } else {
+        {
           const uint32_t va = sval[sa * G + inst], vb = sval[sb * G + inst];
           if (type >= 8) {
             lc = (type == 10) ? la : xor4(la, lb);

@@ -151,6 +151,14 @@ gsv_program* finish_program(std::unique_ptr<gsv::Builder> b, uint32_t root, cons
   p->builder = std::move(b);
   p->root = root;
   for (const auto& t : p->prog.tasks) p->max_task_levels = std::max(p->max_task_levels, t.n_levels);
+  if (getenv("GSV_PLAN_DEBUG")) {  // largest working sets, for choosing max_task_slots
+    std::vector<const gsv::Task*> ts;
+    for (const auto& t : p->prog.tasks) ts.push_back(&t);
+    std::sort(ts.begin(), ts.end(), [](const gsv::Task* a, const gsv::Task* b) { return a->n_slots > b->n_slots; });
+    for (size_t i = 0; i < ts.size() && i < 12; i++)
+      fprintf(stderr, "[plan] slots %u levels %u gates %llu in %u out %u  %s\n", ts[i]->n_slots, ts[i]->n_levels,
+              (unsigned long long)ts[i]->n_gates_total, ts[i]->n_in, ts[i]->n_out, ts[i]->key.substr(0, 80).c_str());
+  }
   for (const auto& c : p->prog.calls) p->sum_call_levels += p->prog.tasks[c.task].n_levels;
   {
     // dependency-chain lengths: what bounds one instance's latency however many SMs there are
