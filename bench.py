@@ -8,7 +8,7 @@ garbling stage of the reference's cut-and-choose (src/cut_and_choose/garbler.rs:
 
 Workloads (--workload):
   verifier (default) : groth16_verify_compressed (11.46 G gates, 2.98 G ciphertexts; BASELINE.json
-          configs 2/4) x 32 instances per GPU, levelised kernel, commitment in GSV_CT_COMMIT_HOST mode:
+          configs 2/4) x 32 instances per GPU, levelised kernel (4 instances per worker), commitment in GSV_CT_COMMIT_HOST mode:
           every gate hash on the GPU, the strictly serial AES chain folded by host AES-NI threads that
           drain the ciphertext ring while the kernel runs (a GPU folds one dependent AES per 0.46 us:
           23 min for 2.98 G ciphertexts, whatever the batch).
@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     # workload presets (explicit flags win)
-    preset = {"verifier": dict(circuit="groth16_verify_compressed", instances=32, exec_mode=1, group=2,
+    preset = {"verifier": dict(circuit="groth16_verify_compressed", instances=32, exec_mode=1, group=4,
                                ct_mode="commit_host", steps=1),
               "batch": dict(circuit="fq12_mul", instances=6144, exec_mode=2, group=0, ct_mode="commit", steps=3)}[args.workload]
     for k, v in preset.items():
