@@ -99,12 +99,15 @@ class Garbler:
     """`Garbler::create` + `commit` for the instances of one rank on one GPU."""
 
     def __init__(self, program, total: int, master_seed: int, device: int = 0, rank: int = 0, world: int = 1,
-                 hasher: int = 0, ct_mode: Optional[int] = None, **session_kw):
+                 hasher: int = 0, ct_mode: Optional[int] = None, seeds: Optional[np.ndarray] = None, **session_kw):
         from . import CT_COMMIT, Session
 
         self.program, self.total, self.rank, self.world, self.device = program, total, rank, world, device
         self.hasher = hasher
-        self.seeds_all = instance_seeds(master_seed, total)
+        # `seeds` overrides the master-seed draw (the evaluator re-garbles from revealed seeds)
+        self.seeds_all = instance_seeds(master_seed, total) if seeds is None else np.asarray(seeds, dtype=np.uint64)
+        if self.seeds_all.shape != (total,):
+            raise ValueError("need one seed per instance")
         self.first, self.count = shard(total, world, rank)
         self.seeds = self.seeds_all[self.first:self.first + self.count]
         self.session = Session(program, max(self.count, 1), device=device,
@@ -160,3 +163,190 @@ def gather_commits(local: CommitRecords, total: int, group=None) -> CommitRecord
     out = out.cpu().numpy().reshape(world, per, rec_len)
     parts = [out[r, : shard(total, world, r)[1]] for r in range(world)]
     return CommitRecords(np.concatenate(parts, axis=0), local.n_inputs, local.n_outputs)
+
+
+# ======================================================================================================
+# The rest of the protocol surface: open / re-garble / evaluate_from (garbler.rs:259-319,
+# evaluator.rs:45-181, 338-476).  Host logic only; every garbling, evaluation and label commitment below is
+# a batched call into libgsv_cuda.so.
+# ======================================================================================================
+class ConsistencyError(Exception):
+    """evaluator.rs:222-336 `ConsistencyError`: `kind` is the variant name, `index` the instance."""
+
+    def __init__(self, kind: str, index: int, detail: str = ""):
+        super().__init__(f"{kind} (instance {index}) {detail}".strip())
+        self.kind, self.index = kind, index
+
+
+class _ChaChaU64:
+    """`ChaCha20Rng::seed_from_u64(seed)` as a stream of `next_u64` draws."""
+
+    def __init__(self, seed: int):
+        self.key, self.blk, self.words = _seed_key(seed), 0, []
+
+    def next_u64(self) -> int:
+        if len(self.words) < 2:
+            self.words += _chacha20_block(self.key, self.blk)
+            self.blk += 1
+        lo, hi = self.words[0], self.words[1]
+        del self.words[:2]
+        return lo | (hi << 32)
+
+    def gen_range_inclusive(self, high: int) -> int:
+        """`rng.gen_range(0..=high)` for usize: rand 0.8.5 `UniformInt::sample_single_inclusive`
+        (widening multiply, rejection zone `(range << lz) - 1`).  Parity unpinned (crate not vendored)."""
+        rng_range = (high + 1) & _M64
+        if rng_range == 0:
+            return self.next_u64()
+        lz = 64 - rng_range.bit_length()
+        zone = ((rng_range << lz) & _M64) - 1
+        while True:
+            m = self.next_u64() * rng_range
+            if (m & _M64) <= zone:
+                return m >> 64
+
+
+def choose_to_finalize(rng_seed: int, total: int, to_finalize: int) -> List[int]:
+    """`Evaluator::create` (evaluator.rs:45-70): Fisher-Yates over 0..total with `gen_range(0..=i)`,
+    first `to_finalize` entries, sorted."""
+    if to_finalize > total:
+        raise ValueError("to_finalize must be <= total")
+    rng, idx = _ChaChaU64(rng_seed), list(range(total))
+    for i in range(total - 1, 0, -1):
+        j = rng.gen_range_inclusive(i)
+        idx[i], idx[j] = idx[j], idx[i]
+    return sorted(idx[:to_finalize])
+
+
+@dataclass
+class EvaluatorCaseInput:
+    """`EvaluatorCaseInput` (cut_and_choose/mod.rs): what the garbler hands over for one finalized
+    instance -- the active input labels with their bits, and the two constant labels."""
+
+    index: int
+    input_active: np.ndarray  # [n_inputs, 16]
+    input_bits: np.ndarray    # [n_inputs]
+    true_label: np.ndarray    # [16]  true.select(true)
+    false_label: np.ndarray   # [16]  false.select(false)
+
+
+def open_commit(garbler: "Garbler", to_finalize: List[int]):
+    """`Garbler::open_commit` for the local shard: seeds of the opened instances, and for the finalized
+    ones a re-garbling whose ciphertext stream stays on the GPU (the `Sender<S>` handler; the stream must
+    fit HBM -- 87 MB per Fq12-mul instance, 47.7 GB per verifier instance).  Returns
+    (open: [(index, seed)], closed: {index: ciphertext stream [n_ct, 16] on the host})."""
+    from . import CT_KEEP_RAW, Session
+
+    mine = [i for i in to_finalize if garbler.first <= i < garbler.first + garbler.count]
+    open_ = [(garbler.first + k, int(garbler.seeds[k])) for k in range(garbler.count)
+             if garbler.first + k not in mine]
+    closed = {}
+    if mine:
+        sess = Session(garbler.program, len(mine), device=garbler.device, ct_mode=CT_KEEP_RAW)
+        sess.garble([int(garbler.seeds_all[i]) for i in mine], garbler.hasher, want_inputs=False, want_outputs=False)
+        for k, i in enumerate(mine):
+            closed[i] = sess.read_ciphertexts(k)   # the bytes of gc_{i}.bin (ciphertext_repository.rs:94-106)
+        sess.close()
+    return open_, closed
+
+
+def prepare_input_labels(garbler: "Garbler", to_finalize: List[int], input_bits: np.ndarray) -> List[EvaluatorCaseInput]:
+    """`Garbler::prepare_input_labels` (cut_and_choose/groth16.rs:71-101): active labels of the real input
+    for every finalized local instance."""
+    r = garbler.result if garbler.result is not None else garbler.create()
+    bits = np.ascontiguousarray(input_bits, np.uint8).reshape(garbler.program.n_inputs)
+    cases = []
+    for i in to_finalize:
+        k = i - garbler.first
+        if not 0 <= k < garbler.count:
+            continue
+        act = r.input_label0[k].copy()
+        act[bits.astype(bool)] ^= r.delta[k]
+        cases.append(EvaluatorCaseInput(i, act, bits.copy(), r.true_label0[k] ^ r.delta[k], r.false_label0[k].copy()))
+    return cases
+
+
+class Evaluator:
+    """`Evaluator` (src/cut_and_choose/evaluator.rs): holds the garbler's commit records, picks the
+    instances to finalize, checks the opened ones by re-garbling and evaluates the finalized ones."""
+
+    def __init__(self, program, total: int, to_finalize: int, rng_seed: int, commits: CommitRecords,
+                 device: int = 0, hasher: int = 0):
+        if commits.records.shape[0] != total:
+            raise ValueError("need one commit record per instance")
+        self.program, self.total, self.commits, self.device, self.hasher = program, total, commits, device, hasher
+        self.to_finalize = choose_to_finalize(rng_seed, total, to_finalize)
+
+    def run_regarbling(self, open_seeds: List[Tuple[int, int]], closed_streams) -> None:
+        """evaluator.rs:83-181.  Opened instances: full re-garble from the revealed seed (ONE batched GPU
+        call for all of them), rebuild the commit record, compare.  Finalized instances: fold the received
+        ciphertext stream and compare with the committed chain hash."""
+        from . import host_chain_fold
+
+        seeds = dict(open_seeds)
+        opened = [i for i in range(self.total) if i not in self.to_finalize]
+        for i in opened:
+            if i not in seeds:
+                raise ConsistencyError("MissingSeed", i)
+        if opened:
+            g = Garbler(self.program, len(opened), 0, device=self.device, hasher=self.hasher,
+                        seeds=np.array([seeds[i] for i in opened], dtype=np.uint64))
+            rec = g.commit().records
+            g.session.close()
+            for k, i in enumerate(opened):
+                if not np.array_equal(rec[k], self.commits.records[i]):
+                    raise ConsistencyError("RegarblingMismatch", i)
+        for i in self.to_finalize:
+            if i not in closed_streams:
+                raise ConsistencyError("MissingCiphertextHash", i)
+            st = np.ascontiguousarray(closed_streams[i], np.uint8).reshape(-1, 1, 16)
+            h = host_chain_fold(np.zeros((1, 16), np.uint8), st)[0]
+            if not np.array_equal(h, self.commits.ct_commit()[i]):
+                raise ConsistencyError("CiphertextMismatch", i, "ciphertext corrupted")
+
+    def evaluate_from(self, closed_streams, cases: List[EvaluatorCaseInput]):
+        """evaluator.rs:338-476: for every finalized instance check the constant and input-label commits,
+        evaluate from its ciphertext stream (one batched GPU call), re-check the chain hash and the output
+        label commit.  Returns [(index, output bits [n_out], active output labels [n_out, 16])]."""
+        from . import CT_KEEP, Session, commit_labels
+
+        p, n = self.program, len(cases)
+        if n == 0:
+            return []
+        for c in cases:
+            if c.index not in self.to_finalize:
+                raise ConsistencyError("NotFinalized", c.index)
+            if c.index not in closed_streams:
+                raise ConsistencyError("MissingCiphertextHash", c.index)
+            if c.input_active.shape[0] != p.n_inputs:
+                raise ConsistencyError("InputLabelsCountMismatch", c.index)
+        idx = [c.index for c in cases]
+        consts = commit_labels(np.stack([np.stack([c.true_label, c.false_label]) for c in cases]), device=self.device)
+        in_c = commit_labels(np.stack([c.input_active for c in cases]), device=self.device).reshape(n, p.n_inputs, 16)
+        for k, c in enumerate(cases):
+            want = self.commits.constant_commits()[c.index]
+            if not np.array_equal(consts.reshape(n, 2, 16)[k, 0], want[0]):
+                raise ConsistencyError("TrueConstantMismatch", c.index)
+            if not np.array_equal(consts.reshape(n, 2, 16)[k, 1], want[1]):
+                raise ConsistencyError("FalseConstantMismatch", c.index)
+            exp = self.commits.input_commits()[c.index]            # [n_in, 2, 16]: (c(l0), c(l1))
+            sel = exp[np.arange(p.n_inputs), c.input_bits.astype(np.int64)]
+            bad = np.nonzero((sel != in_c[k]).any(axis=1))[0]
+            if bad.size:
+                raise ConsistencyError("InputLabelsMismatch", c.index, f"label_index {int(bad[0])}")
+        sess = Session(p, n, device=self.device, ct_mode=CT_KEEP)
+        ev = sess.evaluate(self.hasher, np.stack([c.true_label for c in cases]), np.stack([c.false_label for c in cases]),
+                           np.stack([c.input_active for c in cases]), np.stack([c.input_bits for c in cases]),
+                           ct_streams=[closed_streams[i] for i in idx])
+        sess.close()
+        out_c = commit_labels(ev.output_active, device=self.device).reshape(n, p.n_outputs, 16)
+        res = []
+        for k, c in enumerate(cases):
+            if not np.array_equal(ev.ct_commit[k], self.commits.ct_commit()[c.index]):
+                raise ConsistencyError("CiphertextMismatch", c.index)
+            exp = self.commits.output_commits()[c.index]           # [n_out, 2, 16]: (c(label1), c(label0))
+            sel = exp[np.arange(p.n_outputs), 1 - ev.output_bits[k].astype(np.int64)]
+            if (sel != out_c[k]).any():
+                raise ConsistencyError("OutputLabelMismatch", c.index)
+            res.append((c.index, ev.output_bits[k].copy(), ev.output_active[k].copy()))
+        return res

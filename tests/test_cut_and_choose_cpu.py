@@ -71,3 +71,38 @@ def test_gather_commits_gloo_world2(built, total):
     for rank, col, shape in res:
         assert shape[0] == total
         assert col == [(i + 1) % 251 for i in range(total)]  # instance order, ragged shards handled
+
+
+def test_choose_to_finalize_is_a_seeded_sample_without_replacement():
+    """Evaluator::create (evaluator.rs:45-70): sorted, distinct, in range, deterministic per seed."""
+    import importlib
+
+    cc = importlib.import_module("garbled-snark-verifier_b200.cut_and_choose")
+    for total, k in ((5, 2), (16, 7), (181, 7), (1, 1), (4, 0)):
+        a = cc.choose_to_finalize(1234, total, k)
+        assert a == sorted(set(a)) and len(a) == k and all(0 <= i < total for i in a)
+        assert a == cc.choose_to_finalize(1234, total, k)
+    assert cc.choose_to_finalize(1, 181, 7) != cc.choose_to_finalize(2, 181, 7)
+    with pytest.raises(ValueError):
+        cc.choose_to_finalize(0, 3, 4)
+    # every index is reachable and roughly uniform (Fisher-Yates with an unbiased gen_range)
+    hits = np.zeros(10, int)
+    for s in range(400):
+        for i in cc.choose_to_finalize(s, 10, 3):
+            hits[i] += 1
+    assert hits.min() > 80 and hits.max() < 160
+
+
+def test_rng_u64_stream_matches_instance_seeds_and_gen_range_zone():
+    import importlib
+
+    cc = importlib.import_module("garbled-snark-verifier_b200.cut_and_choose")
+    r = cc._ChaChaU64(1234)
+    assert [r.next_u64() for _ in range(40)] == [int(x) for x in cc.instance_seeds(1234, 40)]
+    # rand 0.8.5 sample_single_inclusive: v*range >> 64, rejected when the low half exceeds the zone
+    r = cc._ChaChaU64(7)
+    draws = [r.gen_range_inclusive(5) for _ in range(2000)]
+    assert set(draws) == set(range(6))
+    r2 = cc._ChaChaU64(7)
+    v = r2.next_u64()
+    assert draws[0] == (v * 6) >> 64 or ((v * 6) & ((1 << 64) - 1)) > ((6 << 61) - 1)

@@ -328,3 +328,56 @@ def test_host_folded_commitment_matches_gpu_chain(gsv, orc, circuit, mode, B, mo
     monkeypatch.delenv("GSV_HOST_CHAIN_BUF_MB")
     again = gsv.Session(p, B, ct_mode=gsv.CT_COMMIT_HOST, exec_mode=mode).garble(seeds, gsv.HASH_AES)  # whole stream resident
     assert np.array_equal(again.ct_commit, dev.ct_commit)
+
+
+def test_cut_and_choose_protocol_round_trip(gsv, circuit):
+    """The whole flow of src/cut_and_choose/tests.rs (total 5 / finalize 2) on Fq mul: create + commit,
+    evaluator picks, open_commit, run_regarbling, prepare_input_labels, evaluate_from; then the reference's
+    tamper cases (corrupted ciphertext, wrong seed, wrong input label, wrong constant)."""
+    import importlib
+
+    cc = importlib.import_module("garbled-snark-verifier_b200.cut_and_choose")
+    import bn254_ref as bn
+
+    p, _ = circuit("fq_mul")
+    total, fin = 5, 2
+    garbler = cc.Garbler(p, total, master_seed=1234)
+    garbler.create()
+    commits = garbler.commit()
+    ev = cc.Evaluator(p, total, fin, rng_seed=99, commits=commits)
+    assert len(ev.to_finalize) == fin
+    open_, closed = cc.open_commit(garbler, ev.to_finalize)
+    assert sorted(i for i, _ in open_) == [i for i in range(total) if i not in ev.to_finalize]
+    assert sorted(closed) == ev.to_finalize and all(c.shape == (p.n_ciphertexts, 16) for c in closed.values())
+    ev.run_regarbling(open_, closed)
+
+    a, b = 123456789123456789 % bn.P, (bn.P - 987654321)
+    bits = np.array(bn.bits_le(bn.to_mont(a)) + bn.bits_le(bn.to_mont(b)), np.uint8)
+    cases = cc.prepare_input_labels(garbler, ev.to_finalize, bits)
+    res = ev.evaluate_from(closed, cases)
+    assert [i for i, _, _ in res] == ev.to_finalize
+    for _, out_bits, _ in res:
+        assert bn.from_bits(list(out_bits)) == bn.to_mont(a * b % bn.P)
+
+    # --- tamper cases
+    bad = {i: c.copy() for i, c in closed.items()}
+    bad[ev.to_finalize[0]][1000, 3] ^= 1
+    with pytest.raises(cc.ConsistencyError) as e:
+        ev.run_regarbling(open_, bad)
+    assert e.value.kind == "CiphertextMismatch" and e.value.index == ev.to_finalize[0]
+    with pytest.raises(cc.ConsistencyError) as e:
+        ev.evaluate_from(bad, cases)
+    assert e.value.kind == "CiphertextMismatch"
+    wrong = [(i, s ^ 1) if k == 1 else (i, s) for k, (i, s) in enumerate(open_)]
+    with pytest.raises(cc.ConsistencyError) as e:
+        ev.run_regarbling(wrong, closed)
+    assert e.value.kind == "RegarblingMismatch" and e.value.index == open_[1][0]
+    c0 = cases[0]
+    flipped = c0.input_active.copy()
+    flipped[7, 0] ^= 0x80
+    with pytest.raises(cc.ConsistencyError) as e:
+        ev.evaluate_from(closed, [cc.EvaluatorCaseInput(c0.index, flipped, c0.input_bits, c0.true_label, c0.false_label)] + cases[1:])
+    assert e.value.kind == "InputLabelsMismatch" and "label_index 7" in str(e.value)
+    with pytest.raises(cc.ConsistencyError) as e:
+        ev.evaluate_from(closed, [cc.EvaluatorCaseInput(c0.index, c0.input_active, c0.input_bits, c0.false_label, c0.false_label)] + cases[1:])
+    assert e.value.kind == "TrueConstantMismatch"
