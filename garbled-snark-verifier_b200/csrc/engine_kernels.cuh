@@ -3,21 +3,24 @@
 // Execution model:
 //   grid  = one CTA per SM (persistent); a CTA = NW garble workers of NT threads
 //           + NC chain warps (commitment consumers);
-//   work  = items (call, instance-group) claimed in emission order by an atomic ticket;
-//           a worker spins on the done-flags of the call's producer calls (RAW) before it
-//           starts, so independent calls of one instance and all instances run concurrently;
+//   work  = items (call, instance-group) scheduled by dataflow: an item becomes ready when its last
+//           RAW / WAR predecessor completes (per-item counters, reverse-edge lists); the finishing
+//           worker keeps one ready successor, the rest go through a global FIFO ready queue;
 //   task  = gather the call's input labels from the instance's global slot array into shared
 //           memory, run the task level by level (named barrier per level, labels never leave
-//           shared memory), write ciphertexts straight to their stream position (a ring when
-//           the stream is not kept), scatter the produced labels back, publish the done-flag;
-//   chain = each chain warp owns 32 instances (one per lane) and folds their ciphertext
+//           shared memory, gate records streamed through a cp.async ring), write ciphertexts
+//           straight to their stream position (a ring when the stream is not kept), scatter the
+//           produced labels back, release the successors;
+//   chain = each chain warp owns 8 instances (a lane quad per instance) and folds their ciphertext
 //           streams into the bit-exact commitment h <- AES_K(h ^ ct) in emission order, call by
 //           call, as soon as the producing items are done; its progress counter is the ring's
-//           back-pressure.  This is the "commitment fused into the garbling kernel" of the
-//           north star: the serial chain runs concurrently with garbling instead of after it.
-// Thread mapping inside a level: idx -> (gate = idx / G, instance = idx % G); G instances of a
-// gate sit in adjacent lanes so label accesses are contiguous 16-byte vectors and the gate
-// record load is a broadcast.
+//           back-pressure (ring governor).  This is the "commitment fused into the garbling kernel"
+//           of the north star: the serial chain runs concurrently with garbling instead of after
+//           it.  GSV_CT_COMMIT_HOST replaces the chain warps by a publisher warp and host threads.
+// Thread mapping inside a level (garbling): lane pair u -> (gate = u / G, instance = u % G), the two
+// half-gate hashes on the two lanes of the pair; evaluation: thread idx -> (idx / G, idx % G).  The G
+// instances of a gate sit in adjacent lanes so label accesses are contiguous 16-byte vectors and the
+// gate record load is a broadcast.
 #pragma once
 #include "device_hash.cuh"
 

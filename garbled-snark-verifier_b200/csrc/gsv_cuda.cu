@@ -897,7 +897,7 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
       s->d_queue.alloc((size_t)1 << s->queue_log2);
     }
     if (s->ct_mode != GSV_CT_NONE) {
-      // GSV_CT_KEEP: the whole interleaved stream stays resident.  GSV_CT_COMMIT: a power-of-two
+      // GSV_CT_KEEP: the whole interleaved stream stays resident.  GSV_CT_COMMIT(_HOST): a
       // ring the chain warps drain (back-pressure through chain_progress).
       uint64_t total = std::max<uint64_t>(g.total_ct, 1);
       uint64_t max_task_ct = 1;

@@ -1,6 +1,9 @@
 // planner.cpp -- cuts the template DAG into shared-memory-sized tasks, levelises them and
 // emits the call list with global slots and dependencies.  See program.h.
 #include <algorithm>
+#include <atomic>
+#include <memory>
+#include <thread>
 #include <cassert>
 #include <map>
 #include <stdexcept>
@@ -241,6 +244,69 @@ struct Planner {
   std::vector<uint64_t> mult;     // occurrences of each template in the flattened circuit
   uint32_t next_global = 0;
   uint64_t gid = 0, ct = 0;
+  // task bodies compiled ahead of classify() by precompile(), on all host cores
+  std::unordered_map<uint32_t, std::unique_ptr<Task>> compiled;
+
+  // the size / sharing rules of classify() that need no compilation: true = structural
+  bool structural_by_rule(uint32_t ti) const {
+    const Template& t = b.tmpl(ti);
+    const bool can_split = !t.calls.empty();
+    if (t.total_gates > opt.max_task_gates && can_split) return true;
+    return can_split && t.total_gates > opt.small_task_gates && mult[ti] < opt.min_shared_calls;
+  }
+
+  // Flattening + levelising + colouring a task body is independent of every other body, and is where
+  // planning time goes.  Walk the template DAG top-down in waves: compile this wave's task candidates
+  // in parallel, descend into the ones that turn out structural.  classify() then only looks up.
+  void precompile(uint32_t root) {
+    std::vector<uint8_t> seen(b.n_templates(), 0);
+    std::vector<uint32_t> wave{root};
+    seen[root] = 1;
+    unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+    while (!wave.empty()) {
+      std::vector<uint32_t> cand;
+      for (uint32_t ti : wave)
+        if (!structural_by_rule(ti) && b.tmpl(ti).total_gates > 0) cand.push_back(ti);
+      std::vector<std::unique_ptr<Task>> out(cand.size());
+      std::vector<std::string> errs(cand.size());
+      std::atomic<size_t> next{0};
+      auto work = [&]() {
+        for (size_t i; (i = next.fetch_add(1)) < cand.size();) {
+          try {
+            const Template& t = b.tmpl(cand[i]);
+            FlatStream fs = flatten(b, cand[i], std::max<uint64_t>(opt.max_task_gates, t.total_gates) + 1);
+            out[i] = std::make_unique<Task>(compile_flat(fs, t.key, opt));
+          } catch (const std::exception& e) {
+            errs[i] = e.what();
+          }
+        }
+      };
+      std::vector<std::thread> th;
+      for (unsigned k = 1; k < std::min<size_t>(nt, cand.size()); k++) th.emplace_back(work);
+      work();
+      for (auto& x : th) x.join();
+      for (size_t i = 0; i < cand.size(); i++) {
+        if (!errs[i].empty()) throw std::runtime_error(errs[i]);
+        compiled[cand[i]] = std::move(out[i]);
+      }
+      std::vector<uint32_t> nextw;
+      for (uint32_t ti : wave) {
+        const Template& t = b.tmpl(ti);
+        bool structural = structural_by_rule(ti);
+        auto it = compiled.find(ti);
+        if (!structural && it != compiled.end() && opt.build_levelised && it->second->n_slots > opt.max_task_slots &&
+            !t.calls.empty())
+          structural = true;
+        if (!structural) continue;
+        for (const CallRec& c : t.calls)
+          if (!seen[c.tmpl]) {
+            seen[c.tmpl] = 1;
+            nextw.push_back(c.tmpl);
+          }
+      }
+      wave.swap(nextw);
+    }
+  }
 
   Planner(const Builder& b_, const PlanOptions& o, uint32_t root) : b(b_), opt(o), kind(b_.n_templates(), -2) {
     // children are created before their parents, so a descending sweep propagates multiplicities
@@ -276,8 +342,15 @@ struct Planner {
       prog.tasks.push_back(std::move(e));
       return kind[ti] = (int64_t)prog.tasks.size() - 1;
     }
-    FlatStream fs = flatten(b, ti, std::max<uint64_t>(opt.max_task_gates, t.total_gates) + 1);
-    Task task = compile_flat(fs, t.key, opt);
+    Task task;
+    auto pre = compiled.find(ti);
+    if (pre != compiled.end()) {
+      task = std::move(*pre->second);
+      compiled.erase(pre);
+    } else {
+      FlatStream fs = flatten(b, ti, std::max<uint64_t>(opt.max_task_gates, t.total_gates) + 1);
+      task = compile_flat(fs, t.key, opt);
+    }
     if (opt.build_levelised && task.n_slots > opt.max_task_slots && can_split) return kind[ti] = -1;
     // an unsplittable body above the slot budget stays a task: it runs in lane mode only (the
     // session refuses the levelised mode when max_task_slots does not fit shared memory)
@@ -488,6 +561,7 @@ Program plan_program(const Builder& b, uint32_t root, const PlanOptions& opt) {
   std::vector<uint32_t> ins(rt.n_in);
   for (uint32_t i = 0; i < rt.n_in; i++) ins[i] = WIRE_MIN + i;
   std::vector<uint32_t> outs;
+  p.precompile(root);
   int64_t kd = p.classify(root);
   if (kd >= 0) {
     // the whole circuit is one task
