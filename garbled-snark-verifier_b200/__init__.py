@@ -214,6 +214,18 @@ class Program:
         _check(lib.gsv_program_execute_plan(self._h, 1 if lane_form else 0, _ptr(ib), _ptr(ob)))
         return ob
 
+    def export_templates(self):
+        """(root, tmpl, gates, calls, items, call_wires, outs): the recorded template DAG, for checkers that
+        walk circuits too large to flatten (see gsv_program_export_templates)."""
+        lib = load_library()
+        sizes = (C.c_uint64 * 6)()
+        root = C.c_uint32(0)
+        lib.gsv_program_export_templates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_void_p] * 6
+        _check(lib.gsv_program_export_templates(self._h, sizes, C.byref(root), None, None, None, None, None, None))
+        arrs = [np.zeros(max(int(n), 1), np.uint32) for n in sizes]
+        _check(lib.gsv_program_export_templates(self._h, sizes, C.byref(root), *[_ptr(a) for a in arrs]))
+        return (int(root.value),) + tuple(a[: int(n)] for a, n in zip(arrs, sizes))
+
     def flat_stream(self):
         """Emission-order gate stream (type, a, b, c, outputs, n_wires) for checkers."""
         lib = load_library()

@@ -198,6 +198,21 @@ typedef struct {
   uint32_t reserved;
 } gsv_garble_result;
 
+/* The recorded circuit as its memoised template DAG (what gsv_program_flat_stream expands), for checkers
+ * that walk circuits too large to flatten (the 11 G-gate verifier is a few MB in this form).
+ *   tmpl   : 12 words per template: n_in, n_wires, gate_off, n_gates, call_off, n_calls, item_off,
+ *            n_items, call_wire_off, n_call_wires, out_off, n_outs (offsets into the arrays below)
+ *   gates  : 4 words per gate: a, b, c (template-local wire ids; c = GSV_WIRE_UNREACHABLE when dead), type
+ *   calls  : 3 words per call: callee template, in_off, out_off (relative to the template's call wires)
+ *   items  : emission order inside a template: bit 31 = call, low bits = index into its gates / calls
+ *   call_wires, outs : local wire ids (0/1 constants, 2.. inputs, then internal)
+ * Pass NULL arrays to query the six sizes (in words) in sizes[0..5]; root = index of the circuit's template.
+ * Local ids: 0 / 1 constants, [2, 2 + n_in) inputs.  A callee output that is one of the callee's own
+ * inputs or constants is a pass-through: the caller already aliases it. */
+int gsv_program_export_templates(const gsv_program* p, uint64_t sizes[6], uint32_t* root, uint32_t* tmpl,
+                                 uint32_t* gates, uint32_t* calls, uint32_t* items, uint32_t* call_wires,
+                                 uint32_t* outs);
+
 /* Host half of GSV_CT_COMMIT_HOST, exposed for checkers: folds n_pos stream positions of n_inst
  * instances, h[i] <- AES_K(h[i] ^ block(p, i)), block(p, i) = base + (p * pos_stride + i * inst_stride)
  * * 16 (src/ciphertext_hasher.rs:22-29).  Needs AES-NI (GSV_ERR_INVALID otherwise). */

@@ -629,3 +629,108 @@ int gsvo_compact_stream(const gsvo_stream* s, uint32_t* a2, uint32_t* b2, uint32
   free(last); free(slot); free(free_list);
   return 0;
 }
+
+
+/* ---- garbling over the template DAG (see gsv_oracle.h) ------------------------------------- */
+typedef struct {
+  const gsvo_templates* t;
+  int hasher;
+  uint8_t delta[16];
+  uint8_t h[16];
+  uint64_t gid, n_ct;
+  uint8_t* arena;   /* label frames, 16 bytes per local wire */
+  size_t cap;       /* in labels */
+  int rc;
+} walk_state;
+
+static int walk_reserve(walk_state* w, size_t n) {
+  if (n <= w->cap) return 0;
+  size_t nc = w->cap * 2 > n ? w->cap * 2 : n;
+  uint8_t* na = (uint8_t*)realloc(w->arena, nc * 16);
+  if (!na) return -3;
+  w->arena = na;
+  w->cap = nc;
+  return 0;
+}
+
+/* runs template ti whose frame starts at label index `base`; inputs already sit at base+2.. */
+static void walk_run(walk_state* w, uint32_t ti, size_t base) {
+  const uint32_t* T = w->t->tmpl + 12 * (size_t)ti;
+  const uint32_t n_wires = T[1];
+  const uint32_t* gates = w->t->gates + 4 * (size_t)T[2];
+  const uint32_t* calls = w->t->calls + 3 * (size_t)T[4];
+  const uint32_t* items = w->t->items + T[6];
+  const uint32_t* cw = w->t->call_wires + T[8];
+  for (uint32_t k = 0; k < T[7] && w->rc == 0; k++) {
+    const uint32_t it = items[k];
+    if (!(it & 0x80000000u)) {
+      const uint32_t* g = gates + 4 * (size_t)it;
+      const uint64_t gid = w->gid++;            /* every gate advances the index (garble_mode.rs:192) */
+      if (g[2] == GSVO_WIRE_DEAD) continue;
+      uint8_t c0[16], ct[16];
+      if (gsvo_garble_gate(w->hasher, (int)g[3], w->arena + 16 * (base + g[0]), w->arena + 16 * (base + g[1]),
+                           w->delta, gid, c0, ct)) {
+        gsvo_chain_update(w->h, ct);
+        w->n_ct++;
+      }
+      memcpy(w->arena + 16 * (base + g[2]), c0, 16);
+    } else {
+      const uint32_t* c = calls + 3 * (size_t)(it & 0x7FFFFFFFu);
+      const uint32_t* C = w->t->tmpl + 12 * (size_t)c[0];
+      const size_t cb = base + n_wires;
+      if (walk_reserve(w, cb + C[1]) != 0) { w->rc = -3; return; }
+      memcpy(w->arena + 16 * cb, w->arena + 16 * base, 32);  /* the two constant labels */
+      for (uint32_t i = 0; i < C[0]; i++) {
+        const uint32_t src = cw[c[1] + i];
+        if (src == GSVO_WIRE_DEAD) memset(w->arena + 16 * (cb + 2 + i), 0, 16);
+        else memcpy(w->arena + 16 * (cb + 2 + i), w->arena + 16 * (base + src), 16);
+      }
+      walk_run(w, c[0], cb);
+      const uint32_t* couts = w->t->outs + C[10];
+      for (uint32_t j = 0; j < C[11]; j++) {
+        const uint32_t p = cw[c[2] + j], o = couts[j];
+        if (p == GSVO_WIRE_DEAD || p < 2 || o == GSVO_WIRE_DEAD) continue;
+        if (o >= 2 + C[0]) memcpy(w->arena + 16 * (base + p), w->arena + 16 * (cb + o), 16);  /* pass-throughs alias */
+      }
+    }
+  }
+}
+
+int gsvo_garble_templates(int hasher, uint64_t seed, const gsvo_templates* t, uint8_t* input_label0_out,
+                          uint8_t* output_label0_out, gsvo_garble_summary* sum) {
+  oracle_init();
+  if (!t || t->root >= t->n_templates) return -1;
+  const uint32_t* R = t->tmpl + 12 * (size_t)t->root;
+  walk_state w;
+  memset(&w, 0, sizeof(w));
+  w.t = t;
+  w.hasher = hasher;
+  if (walk_reserve(&w, (size_t)R[1] + (1u << 16)) != 0) return -3;
+  gsvo_rng rng;
+  gsvo_rng_init(&rng, seed);
+  gsvo_rng_label(&rng, w.delta);               /* garble_mode.rs:81-85: delta, false, true, then inputs */
+  gsvo_rng_label(&rng, w.arena);
+  gsvo_rng_label(&rng, w.arena + 16);
+  for (uint32_t i = 0; i < R[0]; i++) gsvo_rng_label(&rng, w.arena + 16 * (size_t)(2 + i));
+  if (input_label0_out) memcpy(input_label0_out, w.arena + 32, (size_t)R[0] * 16);
+  uint8_t consts[32];
+  memcpy(consts, w.arena, 32);
+  walk_run(&w, t->root, 0);
+  if (w.rc == 0 && output_label0_out) {
+    const uint32_t* outs = t->outs + R[10];
+    for (uint32_t j = 0; j < R[11]; j++) {
+      if (outs[j] == GSVO_WIRE_DEAD) memset(output_label0_out + 16 * (size_t)j, 0, 16);
+      else memcpy(output_label0_out + 16 * (size_t)j, w.arena + 16 * (size_t)outs[j], 16);
+    }
+  }
+  if (sum) {
+    memcpy(sum->delta, w.delta, 16);
+    memcpy(sum->false_label0, consts, 16);
+    memcpy(sum->true_label0, consts + 16, 16);
+    memcpy(sum->ct_commit, w.h, 16);
+    sum->n_ct = w.n_ct;
+    sum->n_gates = w.gid;
+  }
+  free(w.arena);
+  return w.rc;
+}

@@ -131,6 +131,25 @@ int gsvo_garble_stream(int hasher, uint64_t seed, const gsvo_stream* s, uint8_t*
                        gsvo_garble_summary* sum);
 
 /*
+ * The same garbling run over a circuit given as its template DAG (the product's
+ * gsv_program_export_templates format) instead of a flat stream: a depth-first walk in emission
+ * order with one label frame per active component, so circuits far too large to flatten (the
+ * 11 G-gate Groth16 verifier) garble in a few MB.  Same RNG draw order, gate index (every gate,
+ * dead ones included), ciphertext order and chain commitment as gsvo_garble_stream.
+ */
+typedef struct {
+  uint32_t n_templates, root;
+  const uint32_t* tmpl;       /* 12 words per template */
+  const uint32_t* gates;      /* 4 words per gate */
+  const uint32_t* calls;      /* 3 words per call */
+  const uint32_t* items;
+  const uint32_t* call_wires;
+  const uint32_t* outs;
+} gsvo_templates;
+int gsvo_garble_templates(int hasher, uint64_t seed, const gsvo_templates* t, uint8_t* input_label0_out,
+                          uint8_t* output_label0_out, gsvo_garble_summary* sum);
+
+/*
  * EvaluateMode (evaluate_mode.rs:70-158).  input_active: n_inputs*16, input_bits: n_inputs.
  * cts: the garbler's stream.  Outputs: active label + bit per output wire, chain hash of
  * the consumed ciphertexts (what FileSource computes, ciphertext_source.rs:35-106).

@@ -63,6 +63,7 @@ def lib() -> C.CDLL:
         L.gsvo_evaluate_stream.argtypes = [C.c_int, C.c_void_p] + [C.c_void_p] * 5 + [C.c_uint64] + [C.c_void_p] * 4
         L.gsvo_execute_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.gsvo_compact_stream.argtypes = [C.c_void_p] * 6
+        L.gsvo_garble_templates.argtypes = [C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -233,3 +234,33 @@ class Stream:
         rc = lib().gsvo_execute_stream(C.byref(self._s), ib.ctypes.data, ob.ctypes.data)
         assert rc == 0
         return ob
+
+
+class _Templates(C.Structure):
+    _fields_ = [("n_templates", C.c_uint32), ("root", C.c_uint32), ("tmpl", C.c_void_p), ("gates", C.c_void_p),
+                ("calls", C.c_void_p), ("items", C.c_void_p), ("call_wires", C.c_void_p), ("outs", C.c_void_p)]
+
+
+class TemplateDag:
+    """A circuit as the product's exported template DAG (`Program.export_templates()`): the oracle walks
+    it depth-first in emission order, so the 11 G-gate verifier garbles on the CPU in a few MB."""
+
+    def __init__(self, root: int, tmpl, gates, calls, items, call_wires, outs):
+        self.arrays = [np.ascontiguousarray(x, np.uint32) for x in (tmpl, gates, calls, items, call_wires, outs)]
+        self.root = int(root)
+        self.n_templates = self.arrays[0].shape[0] // 12
+        r = self.arrays[0][12 * self.root:12 * self.root + 12]
+        self.n_inputs, self.n_outputs = int(r[0]), int(r[11])
+        self._t = _Templates(self.n_templates, self.root, *[a.ctypes.data for a in self.arrays])
+
+    def garble(self, hasher: int, seed: int):
+        inl = np.zeros((self.n_inputs, 16), np.uint8)
+        outl = np.zeros((self.n_outputs, 16), np.uint8)
+        sm = _Summary()
+        rc = lib().gsvo_garble_templates(hasher, C.c_uint64(seed), C.byref(self._t), inl.ctypes.data, outl.ctypes.data,
+                                         C.byref(sm))
+        if rc != 0:
+            raise RuntimeError(f"oracle garble failed: {rc}")
+        return {"delta": bytes(sm.delta), "false_label0": bytes(sm.false_label0), "true_label0": bytes(sm.true_label0),
+                "ct_commit": bytes(sm.ct_commit), "n_ct": int(sm.n_ct), "n_gates": int(sm.n_gates),
+                "input_label0": inl, "output_label0": outl}

@@ -59,3 +59,49 @@ def test_cuda_path_reproduces_golden(gsv, name, hasher):
         for i, v in enumerate(vs):
             _check(v, res.delta[i], res.false_label0[i], res.true_label0[i], res.input_label0[i], res.output_label0[i],
                    sess.read_ciphertexts(i), res.ct_commit[i])
+
+
+# ---- the full Groth16 verifier --------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["gate_zoo", "fq_mul", "fq12_mul", "g1_add"])
+def test_template_walk_oracle_equals_flat_stream_oracle(gsv, orc, circuit, name):
+    """The oracle's depth-first walk over the exported template DAG (what pins the verifier, too large to
+    flatten) is the same garbling as its flat-stream loop: same labels, ciphertext count, commitment."""
+    p, st = circuit(name)
+    dag = orc.TemplateDag(*p.export_templates())
+    assert dag.n_inputs == p.n_inputs and dag.n_outputs == p.n_outputs
+    for hasher in (0, 1):
+        a, b = dag.garble(hasher, 1234), st.garble(hasher, 1234, want_ct=False)
+        assert a["n_gates"] == p.n_gates and a["n_ct"] == p.n_ciphertexts
+        assert a["ct_commit"] == b["ct_commit"] and a["delta"] == b["delta"]
+        assert np.array_equal(a["input_label0"], b["input_label0"])
+        assert np.array_equal(a["output_label0"], b["output_label0"])
+
+
+def _verifier_vectors():
+    with open(os.path.join(HERE, "golden", "verifier_vectors.json")) as f:
+        return json.load(f)
+
+
+def test_verifier_fixture_shape():
+    d = _verifier_vectors()
+    assert d["n_gates"] == 11457232209 and d["n_ciphertexts"] == 2980239027
+    assert [v["seed"] for v in d["vectors"]] == [1234, 1235]
+
+
+@pytest.mark.gpu
+def test_full_verifier_garbling_matches_oracle_fixture(gsv):
+    """BASELINE.json config 2 at full size: the 11.46 G-gate Groth16 verifier garbled on the GPU (levelised
+    kernel, host-folded commitment) gives the CPU oracle's delta, constants, first input label, output label
+    and -- over all 2 980 239 027 ciphertexts -- chain commitment (tests/golden/make_verifier_golden.py)."""
+    d = _verifier_vectors()
+    p = gsv.Program("groth16_verify_compressed")
+    assert p.n_gates == d["n_gates"] and p.n_ciphertexts == d["n_ciphertexts"]
+    vs = d["vectors"]
+    sess = gsv.Session(p, len(vs), ct_mode=gsv.CT_COMMIT_HOST, exec_mode=1, group=2)
+    res = sess.garble([v["seed"] for v in vs], gsv.HASH_AES)
+    for i, v in enumerate(vs):
+        assert bytes(res.delta[i]).hex() == v["delta"]
+        assert bytes(res.false_label0[i]).hex() == v["false_label0"] and bytes(res.true_label0[i]).hex() == v["true_label0"]
+        assert bytes(res.input_label0[i, 0]).hex() == v["input_label0_first"]
+        assert bytes(res.output_label0[i, 0]).hex() == v["output_label0"]
+        assert bytes(res.ct_commit[i]).hex() == v["ct_commit"]
