@@ -638,6 +638,7 @@ typedef struct {
   uint8_t delta[16];
   uint8_t h[16];
   uint64_t gid, n_ct;
+  uint64_t max_gates; /* stop after this many gates (bounded CPU-baseline samples); 0 = whole circuit */
   uint8_t* arena;   /* label frames, 16 bytes per local wire */
   size_t cap;       /* in labels */
   int rc;
@@ -663,6 +664,7 @@ static void walk_run(walk_state* w, uint32_t ti, size_t base) {
   const uint32_t* cw = w->t->call_wires + T[8];
   for (uint32_t k = 0; k < T[7] && w->rc == 0; k++) {
     const uint32_t it = items[k];
+    if (w->max_gates && w->gid >= w->max_gates) { w->rc = 1; return; }
     if (!(it & 0x80000000u)) {
       const uint32_t* g = gates + 4 * (size_t)it;
       const uint64_t gid = w->gid++;            /* every gate advances the index (garble_mode.rs:192) */
@@ -696,8 +698,17 @@ static void walk_run(walk_state* w, uint32_t ti, size_t base) {
   }
 }
 
+int gsvo_garble_templates_prefix(int hasher, uint64_t seed, const gsvo_templates* t, uint64_t max_gates,
+                                 uint8_t* input_label0_out, uint8_t* output_label0_out, gsvo_garble_summary* sum);
 int gsvo_garble_templates(int hasher, uint64_t seed, const gsvo_templates* t, uint8_t* input_label0_out,
                           uint8_t* output_label0_out, gsvo_garble_summary* sum) {
+  return gsvo_garble_templates_prefix(hasher, seed, t, 0, input_label0_out, output_label0_out, sum);
+}
+
+/* max_gates > 0: garble only the first max_gates gates of the emission order (returns 1, outputs not
+ * written; the summary holds the gate / ciphertext counts and the chain hash so far). */
+int gsvo_garble_templates_prefix(int hasher, uint64_t seed, const gsvo_templates* t, uint64_t max_gates,
+                                 uint8_t* input_label0_out, uint8_t* output_label0_out, gsvo_garble_summary* sum) {
   oracle_init();
   if (!t || t->root >= t->n_templates) return -1;
   const uint32_t* R = t->tmpl + 12 * (size_t)t->root;
@@ -705,6 +716,7 @@ int gsvo_garble_templates(int hasher, uint64_t seed, const gsvo_templates* t, ui
   memset(&w, 0, sizeof(w));
   w.t = t;
   w.hasher = hasher;
+  w.max_gates = max_gates;
   if (walk_reserve(&w, (size_t)R[1] + (1u << 16)) != 0) return -3;
   gsvo_rng rng;
   gsvo_rng_init(&rng, seed);

@@ -148,6 +148,10 @@ typedef struct {
 } gsvo_templates;
 int gsvo_garble_templates(int hasher, uint64_t seed, const gsvo_templates* t, uint8_t* input_label0_out,
                           uint8_t* output_label0_out, gsvo_garble_summary* sum);
+/* max_gates > 0: only the first max_gates gates of the emission order (bounded CPU-baseline samples);
+ * returns 1, outputs not written, the summary holds the counts and the chain hash so far. */
+int gsvo_garble_templates_prefix(int hasher, uint64_t seed, const gsvo_templates* t, uint64_t max_gates,
+                                 uint8_t* input_label0_out, uint8_t* output_label0_out, gsvo_garble_summary* sum);
 
 /*
  * EvaluateMode (evaluate_mode.rs:70-158).  input_active: n_inputs*16, input_bits: n_inputs.

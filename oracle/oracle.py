@@ -64,6 +64,7 @@ def lib() -> C.CDLL:
         L.gsvo_execute_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.gsvo_compact_stream.argtypes = [C.c_void_p] * 6
         L.gsvo_garble_templates.argtypes = [C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gsvo_garble_templates_prefix.argtypes = [C.c_int, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -253,13 +254,14 @@ class TemplateDag:
         self.n_inputs, self.n_outputs = int(r[0]), int(r[11])
         self._t = _Templates(self.n_templates, self.root, *[a.ctypes.data for a in self.arrays])
 
-    def garble(self, hasher: int, seed: int):
+    def garble(self, hasher: int, seed: int, max_gates: int = 0):
+        """max_gates > 0: only the first max_gates gates of the emission order (CPU-baseline samples)."""
         inl = np.zeros((self.n_inputs, 16), np.uint8)
         outl = np.zeros((self.n_outputs, 16), np.uint8)
         sm = _Summary()
-        rc = lib().gsvo_garble_templates(hasher, C.c_uint64(seed), C.byref(self._t), inl.ctypes.data, outl.ctypes.data,
-                                         C.byref(sm))
-        if rc != 0:
+        rc = lib().gsvo_garble_templates_prefix(hasher, C.c_uint64(seed), C.byref(self._t), C.c_uint64(max_gates),
+                                                inl.ctypes.data, outl.ctypes.data, C.byref(sm))
+        if rc != 0 and not (rc == 1 and max_gates):
             raise RuntimeError(f"oracle garble failed: {rc}")
         return {"delta": bytes(sm.delta), "false_label0": bytes(sm.false_label0), "true_label0": bytes(sm.true_label0),
                 "ct_commit": bytes(sm.ct_commit), "n_ct": int(sm.n_ct), "n_gates": int(sm.n_gates),
