@@ -206,6 +206,14 @@ class Program:
         _check(lib.gsv_program_execute(self._h, _ptr(ib), _ptr(ob), C.byref(n)))
         return ob
 
+    def depth(self):
+        """(all gates, non-free gates only): gate-level dependency depth of the outputs."""
+        lib = load_library()
+        a, n = C.c_uint64(0), C.c_uint64(0)
+        lib.gsv_program_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _check(lib.gsv_program_depth(self._h, C.byref(a), C.byref(n)))
+        return int(a.value), int(n.value)
+
     def execute_plan(self, input_bits, lane_form: bool = False) -> np.ndarray:
         """Boolean evaluation of the PLANNED program (tasks / calls / recycled slots): planner self-check."""
         lib = load_library()

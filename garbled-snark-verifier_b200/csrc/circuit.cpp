@@ -307,6 +307,59 @@ struct Executor {
 };
 }  // namespace
 
+namespace {
+// dependency depth of every wire (all gates / non-free gates only), same walk as Executor
+struct DepthWalker {
+  const Builder& b;
+  std::vector<uint64_t> arena;  // hi 32 bits: depth counting every gate, lo 32: non-free gates only
+  void run(uint32_t ti, size_t base) {
+    const Template& t = b.tmpl(ti);
+    if (arena.size() < base + t.n_wires) arena.resize(std::max(arena.size() * 2, base + t.n_wires));
+    arena[base] = arena[base + 1] = 0;
+    for (const Item& it : t.items) {
+      if (!it.is_call) {
+        const GateRec& g = t.gates[it.idx];
+        if (g.c == WIRE_DEAD) continue;
+        const uint64_t x = arena[base + g.a], y = arena[base + g.b];
+        const uint64_t all = std::max(x >> 32, y >> 32) + 1;
+        const uint64_t nf = std::max(x & 0xFFFFFFFFu, y & 0xFFFFFFFFu) + (is_free(g.type) ? 0 : 1);
+        arena[base + g.c] = (all << 32) | nf;
+      } else {
+        const CallRec& c = t.calls[it.idx];
+        const Template& ch = b.tmpl(c.tmpl);
+        const size_t cb = base + t.n_wires;
+        if (arena.size() < cb + ch.n_wires) arena.resize(std::max(arena.size() * 2, cb + ch.n_wires));
+        for (uint32_t i = 0; i < ch.n_in; i++) {
+          Wire w = t.call_wires[c.in_off + i];
+          arena[cb + WIRE_MIN + i] = (w == WIRE_DEAD) ? 0 : arena[base + w];
+        }
+        run(c.tmpl, cb);
+        for (size_t j = 0; j < ch.outs.size(); j++) {
+          Wire p = t.call_wires[c.out_off + j];
+          Wire o = ch.outs[j];
+          if (p == WIRE_DEAD || p < WIRE_MIN || o == WIRE_DEAD) continue;
+          if (o >= WIRE_MIN + ch.n_in) arena[base + p] = arena[cb + o];
+        }
+      }
+    }
+  }
+};
+}  // namespace
+
+void circuit_depth(const Builder& b, uint32_t root, uint64_t* depth_all, uint64_t* depth_nonfree) {
+  const Template& t = b.tmpl(root);
+  DepthWalker w{b, std::vector<uint64_t>(std::max<size_t>(1 << 20, t.n_wires), 0)};
+  w.run(root, 0);
+  uint64_t a = 0, n = 0;
+  for (Wire o : t.outs)
+    if (o != WIRE_DEAD) {
+      a = std::max(a, w.arena[o] >> 32);
+      n = std::max<uint64_t>(n, w.arena[o] & 0xFFFFFFFFu);
+    }
+  if (depth_all) *depth_all = a;
+  if (depth_nonfree) *depth_nonfree = n;
+}
+
 std::vector<uint8_t> execute(const Builder& b, uint32_t root, const std::vector<uint8_t>& input_bits,
                              uint64_t* gates_executed) {
   const Template& t = b.tmpl(root);

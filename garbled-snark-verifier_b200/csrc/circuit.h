@@ -143,4 +143,9 @@ FlatStream flatten(const Builder& b, uint32_t root, uint64_t max_gates = (1ull <
 std::vector<uint8_t> execute(const Builder& b, uint32_t root, const std::vector<uint8_t>& input_bits,
                              uint64_t* gates_executed = nullptr);
 
+
+// Gate-level dependency depth of the circuit outputs: counting every live gate, and counting only the
+// non-free (AND-family, one dependent hash each) gates -- the floor of any schedule's critical path.
+void circuit_depth(const Builder& b, uint32_t root, uint64_t* depth_all, uint64_t* depth_nonfree);
+
 }  // namespace gsv

@@ -323,6 +323,16 @@ int gsv_host_chain_fold(uint8_t* h, const uint8_t* base, uint64_t pos_stride, ui
   return GSV_OK;
 }
 
+int gsv_program_depth(const gsv_program* p, uint64_t* depth_all, uint64_t* depth_nonfree) {
+  if (!p) return fail(GSV_ERR_INVALID, "null argument");
+  try {
+    gsv::circuit_depth(*p->builder, p->root, depth_all, depth_nonfree);
+    return GSV_OK;
+  } catch (const std::exception& e) {
+    return fail(GSV_ERR_INVALID, e.what());
+  }
+}
+
 int gsv_program_execute_plan(const gsv_program* p, int lane_form, const uint8_t* input_bits, uint8_t* output_bits) {
   if (!p || !input_bits || !output_bits) return fail(GSV_ERR_INVALID, "null argument");
   try {

@@ -8,6 +8,7 @@
 #include <map>
 #include <stdexcept>
 #include <unordered_map>
+#include <unordered_set>
 
 #include "program.h"
 
@@ -246,6 +247,7 @@ struct Planner {
   uint64_t gid = 0, ct = 0;
   // task bodies compiled ahead of classify() by precompile(), on all host cores
   std::unordered_map<uint32_t, std::unique_ptr<Task>> compiled;
+  std::unordered_set<uint32_t> too_big;  // bodies whose working set overflows the 16-bit slot ids
 
   // the size / sharing rules of classify() that need no compilation: true = structural
   bool structural_by_rule(uint32_t ti) const {
@@ -269,6 +271,7 @@ struct Planner {
         if (!structural_by_rule(ti) && b.tmpl(ti).total_gates > 0) cand.push_back(ti);
       std::vector<std::unique_ptr<Task>> out(cand.size());
       std::vector<std::string> errs(cand.size());
+      std::vector<uint8_t> oversize(cand.size(), 0);
       std::atomic<size_t> next{0};
       auto work = [&]() {
         for (size_t i; (i = next.fetch_add(1)) < cand.size();) {
@@ -276,6 +279,9 @@ struct Planner {
             const Template& t = b.tmpl(cand[i]);
             FlatStream fs = flatten(b, cand[i], std::max<uint64_t>(opt.max_task_gates, t.total_gates) + 1);
             out[i] = std::make_unique<Task>(compile_flat(fs, t.key, opt));
+          } catch (const std::length_error&) {
+            out[i] = nullptr;  // working set beyond the 16-bit slot ids: cannot be a task
+            oversize[i] = 1;
           } catch (const std::exception& e) {
             errs[i] = e.what();
           }
@@ -287,12 +293,13 @@ struct Planner {
       for (auto& x : th) x.join();
       for (size_t i = 0; i < cand.size(); i++) {
         if (!errs[i].empty()) throw std::runtime_error(errs[i]);
-        compiled[cand[i]] = std::move(out[i]);
+        if (oversize[i]) too_big.insert(cand[i]);
+        else compiled[cand[i]] = std::move(out[i]);
       }
       std::vector<uint32_t> nextw;
       for (uint32_t ti : wave) {
         const Template& t = b.tmpl(ti);
-        bool structural = structural_by_rule(ti);
+        bool structural = structural_by_rule(ti) || (too_big.count(ti) && !t.calls.empty());
         auto it = compiled.find(ti);
         if (!structural && it != compiled.end() && opt.build_levelised && it->second->n_slots > opt.max_task_slots &&
             !t.calls.empty())
@@ -342,6 +349,7 @@ struct Planner {
       prog.tasks.push_back(std::move(e));
       return kind[ti] = (int64_t)prog.tasks.size() - 1;
     }
+    if (too_big.count(ti) && can_split) return kind[ti] = -1;
     Task task;
     auto pre = compiled.find(ti);
     if (pre != compiled.end()) {

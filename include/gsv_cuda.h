@@ -121,6 +121,10 @@ gsv_program* gsv_program_build(const char* circuit, const gsv_plan_options* opt)
  * garbling path.  input_bits: n_inputs bytes (0/1), output_bits: n_outputs bytes. */
 int gsv_program_execute(const gsv_program* p, const uint8_t* input_bits, uint8_t* output_bits,
                         uint64_t* gates_executed);
+/* Gate-level dependency depth of the circuit's outputs: over all live gates and over the non-free gates
+ * only (each a dependent gate hash): the floor of any schedule's critical path. */
+int gsv_program_depth(const gsv_program* p, uint64_t* depth_all, uint64_t* depth_nonfree);
+
 /* The same boolean evaluation, but over the PLANNED program (tasks, calls, task-local slots, recycled
  * global slots) in call order, in the levelised (lane_form = 0) or emission-order (lane_form = 1)
  * task form: a host-side planner self-check that needs no GPU.  Fails if the plan ever reads a
