@@ -144,7 +144,10 @@ gsv_program* finish_program(std::unique_ptr<gsv::Builder> b, uint32_t root, cons
   if (opt) {
     if (opt->max_task_gates) po.max_task_gates = opt->max_task_gates;
     if (opt->max_task_slots) po.max_task_slots = opt->max_task_slots;
-    if (opt->lane_only) po.build_levelised = false;
+    if (opt->lane_only) {
+      po.build_levelised = false;
+      po.max_global_slots = 1u << 20;  // lane mode serves thousands of instances: memory before critical path
+    }
   }
   auto p = std::make_unique<gsv_program>();
   p->prog = gsv::plan_program(*b, root, po);
@@ -176,6 +179,52 @@ gsv_program* finish_program(std::unique_ptr<gsv::Builder> b, uint32_t root, cons
       p->critical_path_gates = std::max(p->critical_path_gates, fg[i]);
       p->critical_path_levels = std::max(p->critical_path_levels, fl[i]);
     }
+  }
+  if (getenv("GSV_PLAN_DEBUG") && p->prog.has_levelised) {
+    // what the critical path would be if a consumer level only waited for the producer LEVELS it needs
+    const auto& g = p->prog;
+    std::vector<uint64_t> slot_time(g.n_global_slots, 0);
+    uint64_t crit = 0, crit_plain = 0;
+    std::vector<uint64_t> slot_end(g.n_global_slots, 0);
+    for (const auto& c : g.calls) {
+      const gsv::Task& t = g.tasks[c.task];
+      uint64_t S = 0, S_plain = 0;
+      for (uint32_t i = 0; i < t.n_in; i++) {
+        if (t.in_slot[i] == 0xFFFF) continue;
+        const uint32_t sl = g.call_slots[c.in_off + i];
+        const uint64_t need = i < t.pipe_in_need.size() ? t.pipe_in_need[i] : 1;
+        if (slot_time[sl] + 1 > need) S = std::max(S, slot_time[sl] + 1 - need);
+        S_plain = std::max(S_plain, slot_end[sl]);
+      }
+      for (uint32_t k = 0; k < t.n_out; k++) {
+        const uint32_t sl = g.call_slots[c.out_off + k];
+        slot_time[sl] = S + (k < t.pipe_out_ready.size() ? t.pipe_out_ready[k] : t.pipe_depth);
+        slot_end[sl] = S_plain + t.pipe_depth;
+      }
+      crit = std::max(crit, S + t.pipe_depth);
+      crit_plain = std::max(crit_plain, S_plain + t.pipe_depth);
+    }
+    // the same call-granular chain over the explicit edges (RAW + WAR), true depths vs device levels
+    std::vector<uint64_t> f1(g.calls.size()), f2(g.calls.size());
+    uint64_t c1 = 0, c2 = 0, sum_true = 0, sum_dev = 0;
+    for (size_t i = 0; i < g.calls.size(); i++) {
+      const auto& c = g.calls[i];
+      uint64_t a = 0, b2 = 0;
+      for (uint32_t d = 0; d < c.n_deps; d++) {
+        a = std::max(a, f1[g.deps[c.dep_off + d]]);
+        b2 = std::max(b2, f2[g.deps[c.dep_off + d]]);
+      }
+      f1[i] = a + g.tasks[c.task].pipe_depth;
+      f2[i] = b2 + g.tasks[c.task].n_levels;
+      c1 = std::max(c1, f1[i]);
+      c2 = std::max(c2, f2[i]);
+      sum_true += g.tasks[c.task].pipe_depth;
+      sum_dev += g.tasks[c.task].n_levels;
+    }
+    fprintf(stderr, "[plan] critical path in levels: RAW only / true depths %llu, RAW+WAR / true depths %llu, "
+            "RAW+WAR / device levels (128-gate cap) %llu; level-pipelined %llu; sum of call levels true %llu device %llu\n",
+            (unsigned long long)crit_plain, (unsigned long long)c1, (unsigned long long)c2, (unsigned long long)crit,
+            (unsigned long long)sum_true, (unsigned long long)sum_dev);
   }
   return p.release();
 }
@@ -350,9 +399,40 @@ int gsv_program_execute_plan(const gsv_program* p, int lane_form, const uint8_t*
     glob[0] = 0;
     glob[1] = 1;
     for (uint32_t i = 0; i < g.n_inputs; i++) glob[2 + i] = input_bits[i] & 1;
+    // Dependency audit: under the dataflow scheduler only the explicit edges order the calls, so every
+    // read must list the slot's last writer (RAW) and every write the slot's readers since then, or the
+    // last writer if nobody read it (WAR / WAW), directly in the call's dependency list.
+    std::vector<int64_t> last_writer(g.n_global_slots, -1);
+    std::vector<std::vector<uint32_t>> readers_since(g.n_global_slots);
+    auto has_dep = [&](const gsv::Call& c, uint32_t d) {
+      return std::binary_search(g.deps.begin() + c.dep_off, g.deps.begin() + c.dep_off + c.n_deps, d);
+    };
     for (size_t ci = 0; ci < g.calls.size(); ci++) {
       const gsv::Call& c = g.calls[ci];
       const gsv::Task& t = g.tasks[c.task];
+      for (uint32_t i = 0; i < t.n_in; i++) {
+        if ((lane_form ? t.seq_in_slot[i] : t.in_slot[i]) == 0xFFFF) continue;
+        const uint32_t sl = g.call_slots[c.in_off + i];
+        if (last_writer[sl] >= 0 && !has_dep(c, (uint32_t)last_writer[sl]))
+          throw std::runtime_error("plan misses a RAW edge: call " + std::to_string(ci) + " reads slot " +
+                                   std::to_string(sl) + " of call " + std::to_string(last_writer[sl]));
+        if (readers_since[sl].empty() || readers_since[sl].back() != (uint32_t)ci) readers_since[sl].push_back((uint32_t)ci);
+      }
+      for (uint32_t k = 0; k < t.n_out; k++) {
+        const uint32_t sl = g.call_slots[c.out_off + k];
+        for (uint32_t r : readers_since[sl])
+          if (r != (uint32_t)ci && !has_dep(c, r))
+            throw std::runtime_error("plan misses a WAR edge: call " + std::to_string(ci) + " overwrites slot " +
+                                     std::to_string(sl) + " read by call " + std::to_string(r));
+        if (readers_since[sl].empty() && last_writer[sl] >= 0 && last_writer[sl] != (int64_t)ci &&
+            !has_dep(c, (uint32_t)last_writer[sl]))
+          throw std::runtime_error("plan misses a WAW edge on slot " + std::to_string(sl));
+      }
+      for (uint32_t k = 0; k < t.n_out; k++) {
+        const uint32_t sl = g.call_slots[c.out_off + k];
+        last_writer[sl] = (int64_t)ci;
+        readers_since[sl].clear();
+      }
       const auto& gates = lane_form ? t.seq_gates : t.gates;
       const auto& in_slot = lane_form ? t.seq_in_slot : t.in_slot;
       const auto& out_slot = lane_form ? t.seq_out_slot : t.out_slot;

@@ -49,6 +49,23 @@ Task compile_flat(const FlatStream& fs, const std::string& key, const PlanOption
 
   if (!opt.build_levelised) goto lane_form;
   {
+  // ---- pipelining analysis: outputs at their ASAP level, the rest as late as that allows
+  {
+    std::vector<uint32_t> req(nw, depth);
+    for (uint32_t o : fs.outputs)
+      if (o != WIRE_DEAD && o >= first_def) req[o] = wlevel[o];
+    for (size_t gi = ng; gi-- > 0;) {
+      if (fs.c[gi] == WIRE_DEAD) continue;
+      const uint32_t l = std::max(req[fs.c[gi]], asap[gi]);
+      req[fs.a[gi]] = std::min(req[fs.a[gi]], l - 1);
+      req[fs.b[gi]] = std::min(req[fs.b[gi]], l - 1);
+    }
+    t.pipe_in_need.assign(fs.n_inputs, depth + 1);
+    for (uint32_t i = 0; i < fs.n_inputs; i++) t.pipe_in_need[i] = req[WIRE_MIN + i] + 1;
+    for (uint32_t o : fs.outputs)
+      if (o != WIRE_DEAD && o >= first_def) t.pipe_out_ready.push_back(wlevel[o]);
+    t.pipe_depth = depth;
+  }
   // ---- ALAP levels: as late as the consumers allow; sinks (outputs, unread wires) at `depth`
   if (opt.alap) {
     std::vector<uint32_t> req(nw, depth);  // latest level at which the wire must be available
@@ -620,18 +637,38 @@ Program plan_program(const Builder& b, uint32_t root, const PlanOptions& opt) {
       for (uint32_t k = 0; k < task.n_out; k++)
         if (pinned[prog.call_slots[call.out_off + k]]) block_pinned[c] = 1;
     }
+    // Which free block a call takes over matters: the WAR edges it inherits (the old occupant's readers)
+    // are FALSE dependencies, and with first-fit they nearly doubled the verifier's critical path (two
+    // independent sub-circuits emitted one after the other got chained through their slots).  So the
+    // choice is depth-aware: finish[] is every call's earliest completion over the edges chosen so far
+    // (in levels; gates for lane-only plans), and a call only takes a block whose readers have finished
+    // by the time its own inputs are there -- the WAR edges then never delay anything.  If no such block
+    // is free, fresh slots are used until max_global_slots, then the block that delays it least.
     struct FreeBlock { uint32_t base, producer, free_at; };
-    std::map<uint32_t, std::vector<FreeBlock>> pool;       // size class -> FIFO (push back, pop front index)
-    std::map<uint32_t, size_t> pool_head;
+    std::map<uint32_t, std::vector<FreeBlock>> waiting;          // size class -> FIFO by free_at
+    std::map<uint32_t, size_t> waiting_head;
+    std::map<uint32_t, std::multimap<uint64_t, FreeBlock>> ready;  // size class -> readers' finish time -> block
     std::vector<std::vector<uint32_t>> release_at(n_calls + 1);
     std::vector<uint32_t> slot_of(n_w, UNSET), block_base(n_calls, 0), block_size(n_calls, 0);
     for (uint32_t w = 0; w < first_wire; w++) slot_of[w] = w;
     uint32_t next_slot = first_wire;
     std::vector<std::vector<uint32_t>> war(n_calls);
+    std::vector<uint64_t> finish(n_calls, 0);
+    auto weight = [&](uint32_t c) -> uint64_t {
+      const Task& t = prog.tasks[prog.calls[c].task];
+      return std::max<uint64_t>(1, opt.build_levelised ? t.n_levels : t.n_gates_total);
+    };
+    auto readers_finish = [&](uint32_t prev) {
+      uint64_t f = finish[prev];
+      for (uint32_t r : readers[prev]) f = std::max(f, finish[r]);
+      return f;
+    };
     for (uint32_t c = 0; c < n_calls; c++) {
-      for (uint32_t pc : release_at[c]) pool[block_size[pc]].push_back(FreeBlock{block_base[pc], pc, c});
+      for (uint32_t pc : release_at[c]) waiting[block_size[pc]].push_back(FreeBlock{block_base[pc], pc, c});
       const Call& call = prog.calls[c];
       const Task& task = prog.tasks[call.task];
+      uint64_t start = 0;  // earliest start over the RAW edges
+      for (uint32_t d = 0; d < call.n_deps; d++) start = std::max(start, finish[prog.deps[call.dep_off + d]]);
       // unique produced wires of this call, in output order
       std::vector<uint32_t> uniq;
       for (uint32_t k = 0; k < task.n_out; k++) {
@@ -642,20 +679,43 @@ Program plan_program(const Builder& b, uint32_t root, const PlanOptions& opt) {
         }
       }
       const uint32_t size = (uint32_t)uniq.size();
-      if (size == 0) continue;
+      if (size == 0) {
+        finish[c] = start + weight(c);
+        continue;
+      }
+      // blocks become eligible `reuse_distance` calls after their last reader
+      {
+        auto& q = waiting[size];
+        size_t& head = waiting_head[size];
+        auto& rd = ready[size];
+        while (head < q.size() && q[head].free_at + opt.reuse_distance <= c) {
+          rd.emplace(readers_finish(q[head].producer), q[head]);
+          head++;
+        }
+      }
       uint32_t base;
-      auto& q = pool[size];
-      size_t& head = pool_head[size];
-      if (head < q.size() && q[head].free_at + opt.reuse_distance <= c) {
-        base = q[head].base;
-        const uint32_t prev = q[head].producer;
+      auto& rd = ready[size];
+      auto it = rd.upper_bound(start);  // first block whose readers finish AFTER `start`
+      bool take = false;
+      if (it != rd.begin()) {           // the latest-finishing block that still costs nothing
+        --it;
+        take = true;
+      } else if (!rd.empty() && (uint64_t)next_slot + size > opt.max_global_slots) {
+        it = rd.begin();                // out of fresh slots: the block that delays this call least
+        take = true;
+      }
+      if (take) {
+        base = it->second.base;
+        const uint32_t prev = it->second.producer;
+        start = std::max(start, it->first);
         war[c] = readers[prev];
         if (war[c].empty()) war[c].push_back(prev);  // never read: at least wait for the old writer
-        head++;
+        rd.erase(it);
       } else {
         base = next_slot;
         next_slot += size;
       }
+      finish[c] = start + weight(c);
       for (uint32_t k = 0; k < size; k++) slot_of[uniq[k]] = base + k;
       block_base[c] = base;
       block_size[c] = size;

@@ -58,6 +58,12 @@ struct Task {
   std::vector<DevGate> seq_gates;
   std::vector<uint16_t> seq_in_slot, seq_out_slot;
   uint32_t n_seq_slots = 0;
+  // Pipelining analysis (levelised form): under a schedule that keeps every output at its earliest level
+  // and everything else as late as that allows, the level before which input i is first read and the
+  // level at which produced output k is complete.  Feeds Program-level "what if calls overlapped level by
+  // level" statistics; the device programs do not use it yet.
+  std::vector<uint32_t> pipe_in_need, pipe_out_ready;
+  uint32_t pipe_depth = 0;
 };
 
 struct Call {
@@ -95,6 +101,8 @@ struct PlanOptions {
   bool alap = true;                  // schedule gates as late as possible (smaller live sets)
   uint32_t reuse_distance = 512;     // global slot blocks are recycled no sooner than this many calls
                                      // after their last reader (0: never recycle)
+  uint32_t max_global_slots = 6u << 20;  // fresh global slots are preferred over delaying WAR edges up to here
+                                         // (16 B x instances each: 3 GB at 32 instances)
   uint64_t small_task_gates = 8192;  // bodies up to this size are tasks even when they occur once
   uint64_t min_shared_calls = 4;     // larger bodies become tasks only if they occur this often
   bool build_levelised = true;       // false: lane-mode form only (large circuits)

@@ -128,7 +128,9 @@ int gsv_program_depth(const gsv_program* p, uint64_t* depth_all, uint64_t* depth
 /* The same boolean evaluation, but over the PLANNED program (tasks, calls, task-local slots, recycled
  * global slots) in call order, in the levelised (lane_form = 0) or emission-order (lane_form = 1)
  * task form: a host-side planner self-check that needs no GPU.  Fails if the plan ever reads a
- * slot that was not written. */
+ * slot that was not written, or if a read / overwrite of a (recycled) global slot is not ordered by an
+ * explicit dependency edge on the slot's last writer / its readers (the dataflow scheduler orders calls
+ * by those edges alone). */
 int gsv_program_execute_plan(const gsv_program* p, int lane_form, const uint8_t* input_bits,
                              uint8_t* output_bits);
 
