@@ -40,53 +40,70 @@ RoundKeys make_keys() {
   return r;
 }
 
+// The chain's critical path is one AES per ciphertext.  aesenclast(s, rk) = SubBytes(ShiftRows(s)) ^ rk, so
+// the last round of step p and the whitening of step p + 1 (h ^ ct ^ k0) fold into ONE instruction with the
+// round key k10 ^ k0 ^ ct[p + 1], which does not depend on the chain: 10 dependent AES instructions per
+// ciphertext and nothing else.  `t` below is the state after round 9 of the pending step.
 template <int W>
 void fold_w(uint8_t* h, const uint8_t* base, size_t pos_bytes, size_t inst_bytes, size_t n_pos, const RoundKeys& rk) {
-  __m128i s[W];
+  if (n_pos == 0) return;
+  __m128i t[W];
   const uint8_t* src[W];
+  const __m128i k10_0 = _mm_xor_si128(rk.k[10], rk.k[0]);
   for (int i = 0; i < W; i++) {
-    s[i] = _mm_loadu_si128(reinterpret_cast<const __m128i*>(h) + i);
     src[i] = base + i * inst_bytes;
+    t[i] = _mm_xor_si128(_mm_xor_si128(_mm_loadu_si128(reinterpret_cast<const __m128i*>(h) + i),
+                                       _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[i]))), rk.k[0]);
+    src[i] += pos_bytes;
   }
-  for (size_t p = 0; p < n_pos; p++) {
+  for (size_t p = 1;; p++) {
+    for (int r = 1; r < 10; r++)
+      for (int i = 0; i < W; i++) t[i] = _mm_aesenc_si128(t[i], rk.k[r]);
+    if (p == n_pos) break;
     for (int i = 0; i < W; i++) {
-      s[i] = _mm_xor_si128(_mm_xor_si128(s[i], _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[i]))), rk.k[0]);
+      const __m128i key = _mm_xor_si128(k10_0, _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[i])));
+      t[i] = _mm_aesenclast_si128(t[i], key);
       src[i] += pos_bytes;
     }
-    for (int r = 1; r < 10; r++)
-      for (int i = 0; i < W; i++) s[i] = _mm_aesenc_si128(s[i], rk.k[r]);
-    for (int i = 0; i < W; i++) s[i] = _mm_aesenclast_si128(s[i], rk.k[10]);
   }
-  for (int i = 0; i < W; i++) _mm_storeu_si128(reinterpret_cast<__m128i*>(h) + i, s[i]);
+  for (int i = 0; i < W; i++)
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(h) + i, _mm_aesenclast_si128(t[i], rk.k[10]));
 }
 
 // VAES (AVX-512): four chains per 512-bit register, Z registers interleaved -> 4 * Z chains per thread
 // at one vaesenc per cycle instead of 8 chains of 128-bit aesenc.
+// the 16-byte blocks of four instance streams side by side in one 512-bit register
+__attribute__((target("avx512f,avx512vl,vaes"))) static inline __m512i load4(const uint8_t* const* s) {
+  __m512i c = _mm512_castsi128_si512(_mm_loadu_si128(reinterpret_cast<const __m128i*>(s[0])));
+  c = _mm512_inserti32x4(c, _mm_loadu_si128(reinterpret_cast<const __m128i*>(s[1])), 1);
+  c = _mm512_inserti32x4(c, _mm_loadu_si128(reinterpret_cast<const __m128i*>(s[2])), 2);
+  return _mm512_inserti32x4(c, _mm_loadu_si128(reinterpret_cast<const __m128i*>(s[3])), 3);
+}
+
 template <int Z>
 __attribute__((target("avx512f,avx512vl,vaes"))) void fold_vaes(uint8_t* h, const uint8_t* base, size_t pos_bytes,
                                                                 size_t inst_bytes, size_t n_pos, const RoundKeys& rk) {
+  if (n_pos == 0) return;
   __m512i k[11];
   for (int r = 0; r < 11; r++) k[r] = _mm512_broadcast_i32x4(rk.k[r]);
-  __m512i s[Z];
+  const __m512i k10_0 = _mm512_xor_si512(k[10], k[0]);
+  __m512i t[Z];
   const uint8_t* src[Z][4];
   for (int z = 0; z < Z; z++) {
-    s[z] = _mm512_loadu_si512(h + 64 * z);
     for (int j = 0; j < 4; j++) src[z][j] = base + (size_t)(4 * z + j) * inst_bytes;
+    t[z] = _mm512_xor_si512(_mm512_xor_si512(_mm512_loadu_si512(h + 64 * z), load4(src[z])), k[0]);
+    for (int j = 0; j < 4; j++) src[z][j] += pos_bytes;
   }
-  for (size_t p = 0; p < n_pos; p++) {
+  for (size_t p = 1;; p++) {
+    for (int r = 1; r < 10; r++)
+      for (int z = 0; z < Z; z++) t[z] = _mm512_aesenc_epi128(t[z], k[r]);
+    if (p == n_pos) break;
     for (int z = 0; z < Z; z++) {
-      __m512i c = _mm512_castsi128_si512(_mm_loadu_si128(reinterpret_cast<const __m128i*>(src[z][0])));
-      c = _mm512_inserti32x4(c, _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[z][1])), 1);
-      c = _mm512_inserti32x4(c, _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[z][2])), 2);
-      c = _mm512_inserti32x4(c, _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[z][3])), 3);
-      s[z] = _mm512_xor_si512(_mm512_xor_si512(s[z], c), k[0]);
+      t[z] = _mm512_aesenclast_epi128(t[z], _mm512_xor_si512(k10_0, load4(src[z])));  // see fold_w
       for (int j = 0; j < 4; j++) src[z][j] += pos_bytes;
     }
-    for (int r = 1; r < 10; r++)
-      for (int z = 0; z < Z; z++) s[z] = _mm512_aesenc_epi128(s[z], k[r]);
-    for (int z = 0; z < Z; z++) s[z] = _mm512_aesenclast_epi128(s[z], k[10]);
   }
-  for (int z = 0; z < Z; z++) _mm512_storeu_si512(h + 64 * z, s[z]);
+  for (int z = 0; z < Z; z++) _mm512_storeu_si512(h + 64 * z, _mm512_aesenclast_epi128(t[z], k[10]));
 }
 
 bool have_vaes() {

@@ -99,6 +99,13 @@ def test_host_chain_fold_matches_cbc_mac(gsv):
         h = gsv.host_chain_fold(h, blocks[20:])
         h2 = gsv.host_chain_fold(np.zeros((n_inst, 16), np.uint8), blocks.transpose(1, 0, 2), instance_major=True)
         assert np.array_equal(h, h2)
+        # one position at a time (the last round of a step is merged with the next step's whitening inside a
+        # call, so single-position calls exercise the unmerged ends), and an empty fold
+        h3 = np.zeros((n_inst, 16), np.uint8)
+        for p in range(blocks.shape[0]):
+            h3 = gsv.host_chain_fold(h3, blocks[p:p + 1])
+        assert np.array_equal(h, h3)
+        assert np.array_equal(gsv.host_chain_fold(h, blocks[:0]), h)
         for i in range(n_inst):
             enc = Cipher(algorithms.AES(bytes([0x42]) * 16), modes.CBC(bytes(16))).encryptor()
             want = enc.update(blocks[:, i, :].tobytes())[-16:]
