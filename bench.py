@@ -356,6 +356,23 @@ def main():
                     "note": "same kernel, ciphertexts dropped: not paced by the host fold / PCIe drain"}
             except Exception as e:  # pragma: no cover
                 roofline["kernel_without_commitment"] = {"error": str(e)}
+        if world == 1 and args.workload == "verifier" and args.ct_mode == "commit_host" and not args.no_unthrottled:
+            # The all-GPU counterpart in the same run: the large-batch regime (Fq12 mul x 6144 instances, lane
+            # kernel, chain commitment fused on the GPU), 1 warm-up + 2 timed steps.  Not part of `value`.
+            try:
+                p2 = g.Program("fq12_mul")
+                s3 = g.Session(p2, 6144, device=local, ct_mode=g.CT_COMMIT, exec_mode=2)
+                sd = lambda i: (np.arange(6144, dtype=np.uint64) + np.uint64(i * 6144)) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(7)
+                s3.garble(sd(0), hasher, want_inputs=False, want_outputs=False)
+                ms = [s3.garble(sd(1 + i), hasher, want_inputs=False, want_outputs=False).ms_total for i in range(2)]
+                s3.close()
+                rate3 = p2.n_gates * 6144 * len(ms) / (sum(ms) * 1e-3)
+                line["gpu_fused_commit_batch"] = {
+                    "workload": "fq12_mul x 6144 instances, k_lane, AES chain commitment folded by chain CTAs on the GPU",
+                    "value": rate3, "unit": "gates/s", "ms_per_step": sum(ms) / len(ms),
+                    "roofline_frac_hbm": rate3 * ALGO_BYTES_PER_GATE / 1e9 / peak}
+            except Exception as e:  # pragma: no cover
+                line["gpu_fused_commit_batch"] = {"error": str(e)}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             try:
