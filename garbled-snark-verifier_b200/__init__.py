@@ -71,6 +71,9 @@ class _SessionOptions(C.Structure):
         ("ct_mode", C.c_uint32),
         ("ct_ring_log2", C.c_uint32),
         ("exec_mode", C.c_uint32),
+        ("sm_limit", C.c_uint32),
+        ("ct_buffer_bytes", C.c_uint64),
+        ("host_threads", C.c_uint32),
         ("reserved", C.c_uint32),
     ]
 
@@ -288,13 +291,14 @@ class Session:
 
     def __init__(self, program: Program, n_instances: int, device: int = 0, group: int = 0,
                  worker_threads: int = 0, ct_mode: int = CT_KEEP, ct_ring_log2: int = 0,
-                 exec_mode: int = 0):
+                 exec_mode: int = 0, sm_limit: int = 0, ct_buffer_bytes: int = 0, host_threads: int = 0):
         lib = load_library()
         self.program = program
         self.n_instances = n_instances
         self.device = device
         self.ct_mode = ct_mode
-        opt = _SessionOptions(device, n_instances, group, worker_threads, ct_mode, ct_ring_log2, exec_mode)
+        opt = _SessionOptions(device, n_instances, group, worker_threads, ct_mode, ct_ring_log2, exec_mode,
+                              sm_limit, ct_buffer_bytes, host_threads, 0)
         self._h = lib.gsv_session_create(program._h, C.byref(opt))
         if not self._h:
             msg = lib.gsv_last_error().decode()
@@ -377,11 +381,25 @@ def host_chain_fold(h: np.ndarray, blocks: np.ndarray, instance_major: bool = Fa
     return out
 
 
-def groth16_synthetic_inputs(public_x: int = 424242, flip_public: bool = False) -> np.ndarray:
-    """1273 input bits of a synthetic proof for the "groth16_verify_compressed" circuit."""
+def host_chain_fold_quads(h: np.ndarray, rows: np.ndarray) -> np.ndarray:
+    """The fold over CT_COMMIT_HOST's drain layout: rows[n_quads, n_pos, 4, 16] folded into
+    h[4 * n_quads, 16] (returns a copy)."""
     lib = load_library()
-    bits = np.zeros(1273, np.uint8)
-    _check(lib.gsv_groth16_synthetic_inputs(public_x, 1 if flip_public else 0, _ptr(bits), 1273))
+    rows = np.ascontiguousarray(rows, np.uint8)
+    n_quads, n_pos = rows.shape[0], rows.shape[1]
+    out = np.ascontiguousarray(h, np.uint8).reshape(4 * n_quads, 16).copy()
+    lib.gsv_host_chain_fold_quads.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32]
+    _check(lib.gsv_host_chain_fold_quads(_ptr(out), _ptr(rows), n_pos * 64, n_pos, n_quads))
+    return out
+
+
+def groth16_synthetic_inputs(public_x: int = 424242, flip_public: bool = False, compressed: bool = True) -> np.ndarray:
+    """Input bits of a synthetic proof: 1273 for "groth16_verify_compressed", 2286 (affine x, y per point,
+    src/garbled_groth16.rs:141-176) for "groth16_verify"."""
+    lib = load_library()
+    n = 1273 if compressed else 2286
+    bits = np.zeros(n, np.uint8)
+    _check(lib.gsv_groth16_synthetic_inputs(public_x, 1 if flip_public else 0, _ptr(bits), n))
     return bits
 
 
@@ -407,6 +425,15 @@ def bench_hash(hasher: int, n_blocks: int = 1 << 30, iters: int = 3, device: int
     lib = load_library()
     r = C.c_double(0)
     _check(lib.gsv_bench_hash(device, hasher, n_blocks, iters, C.byref(r)))
+    return r.value
+
+
+def bench_hash_latency(hasher: int, warps_per_sm: int = 1, n: int = 20000, device: int = 0) -> float:
+    """SM cycles per dependent gate hash with `warps_per_sm` warps chaining hashes on every SM."""
+    lib = load_library()
+    r = C.c_double(0)
+    lib.gsv_bench_hash_latency.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.POINTER(C.c_double)]
+    _check(lib.gsv_bench_hash_latency(device, hasher, warps_per_sm, n, C.byref(r)))
     return r.value
 
 

@@ -48,8 +48,13 @@ struct EngineParams {
   uint8_t* vals;        // evaluate: plaintext bit per label, same indexing
   const uint4* delta;   // [B]
   uint4* ct;            // [ct position][B]  (garble: written, evaluate: read)
-  unsigned long long ct_pos_stride, ct_inst_stride;  // garble stores: (B, 1); GSV_CT_COMMIT_HOST keeps
-                                                     // the ring instance-major, (1, ring capacity)
+  // garble stores: ciphertext (position, instance) lives at
+  //   ct[position * ct_pos_stride + (instance >> ct_qshift) * ct_quad_stride + (instance & ((1 << ct_qshift) - 1))]
+  // position-major [position][B] (qshift 31, pos stride B) for the GPU consumers; GSV_CT_COMMIT_HOST keeps
+  // [instance quad][ring position][4] (qshift 2, pos stride 4, quad stride 4 * ring capacity): each quad of
+  // chains drains as ONE sequential host stream of 64-byte rows, a 512-bit VAES load per fold step
+  unsigned long long ct_pos_stride, ct_quad_stride;
+  uint32_t ct_qshift;
   uint32_t* flags;      // [call][group] == epoch when done
   // dataflow scheduler: ready queue of work items (call * n_groups + group)
   unsigned long long* queue;  // [1 << queue_log2]: (round + 1) << 32 | item
@@ -89,7 +94,11 @@ struct EngineParams {
   uint4* scratch;             // [worker warp][scratch slot][32]
   uint8_t* scratch_vals;
   uint32_t scratch_stride;    // scratch slots per worker warp
+  // GSV_PROFILE=1: per-phase cycle totals of the levelised workers (thread 0 of each worker), see PROF_*
+  unsigned long long* prof;
 };
+enum { PROF_WAIT = 0, PROF_GATHER, PROF_AES_LEVELS, PROF_FREE_LEVELS, PROF_SCATTER, PROF_COMPLETE, PROF_N_AES_LEVELS,
+       PROF_N_FREE_LEVELS, PROF_N_ITEMS, PROF_N_PASSES, PROF_TOTAL, PROF_WORDS };
 
 // Gate-record staging of the levelised mode: a task's records are contiguous in level order, so
 // they are streamed global -> shared with cp.async in chunks of GATE_CHUNK records, GATE_CHUNKS
@@ -449,6 +458,22 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
   const uint32_t inst = wt % G;  // NT % G == 0, so a thread always serves the same instance lane
   const uint32_t n_items = p.n_calls * p.n_groups;
 
+  // GSV_PROFILE: thread 0 of each worker accumulates per-phase cycles in its shared-memory area (a few
+  // instructions per level; global reductions per level measurably slowed the run they were measuring)
+  const bool prof = p.prof != nullptr && wt == 0;
+  volatile unsigned long long* wprof = reinterpret_cast<volatile unsigned long long*>(
+      reinterpret_cast<uint4*>(tail + tail_bytes) + n_workers * GATE_RING) + worker * PROF_WORDS;
+  if (prof)
+    for (int i = 0; i < PROF_WORDS; i++) wprof[i] = 0;
+  long long t_prev = prof ? clock64() : 0;
+  const long long t_begin = t_prev;
+  auto lap = [&](int slot) {
+    if (prof) {
+      const long long t = clock64();
+      wprof[slot] += (unsigned long long)(t - t_prev);
+      t_prev = t;
+    }
+  };
   for (;;) {
     if (wt == 0) {
       uint32_t it = *keep;
@@ -462,6 +487,7 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
     }
     named_bar(bar_id, NT);
     const uint32_t item = *ctrl;
+    lap(PROF_WAIT);
     if (item == SCHED_DONE) break;
     const uint32_t call_i = item / p.n_groups;
     const uint32_t grp = item - call_i * p.n_groups;
@@ -485,10 +511,13 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
     const unsigned long long ct_pos0 = p.ct_ring ? call.ct_base % p.ct_ring : call.ct_base;
     // ---- gather inputs (and the two constant wires) into shared memory
     const size_t gbase = (size_t)grp * p.n_global_slots;
-    // garbling: the lane pair (wt >> 1) serves instance pinst of the group
-    const uint32_t pinst = (wt >> 1) % G;
-    uint4 pdelta = make_uint4(0, 0, 0, 0);
-    if (MODE == 0) pdelta = p.delta[grp * G + pinst];
+    uint4 delta = make_uint4(0, 0, 0, 0);
+    uint4* ct_out = nullptr;  // garbling: this thread's instance column of the ciphertext buffer
+    if (MODE == 0) {
+      delta = p.delta[grp * G + inst];
+      const uint32_t gi = grp * G + inst;
+      ct_out = p.ct + (size_t)(gi >> p.ct_qshift) * p.ct_quad_stride + (gi & ((1u << p.ct_qshift) - 1u));
+    }
     if (wt < 2 * G) {
       const uint32_t s = wt / G;
       lab[s * G + inst] = __ldcg(p.labels + (gbase + s) * G + inst);
@@ -503,96 +532,127 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
         if (MODE == 1) sval[s * G + inst] = __ldcg(p.vals + gi);
       }
     }
-    cp_async_wait<1>();  // chunks 0..2 have landed
+    cp_async_wait<0>();  // chunks 0..3 have landed
     named_bar(bar_id, NT);
+    lap(PROF_GATHER);
+    if (prof) wprof[PROF_N_ITEMS]++;
 
-    // ---- level loop.  Invariant at a level start: `pos` lies in chunk j = released, chunks up to
-    // j + 3 are requested, chunks j and j + 1 (all a level can touch) have landed.
-    uint32_t pos = 0, released = 0;
+    // ---- level loop.  A level = its non-free gates (first), then its free gates; the header in the
+    // level's first record gives both counts.  What does not depend on the previous level -- the header
+    // and each thread's first gate records of the NEXT level -- is read from the record ring BEFORE the
+    // level barrier, so the dependent path after a barrier is: label loads, hash / XOR, label store.
+    // Ring invariant at a level start (pos in chunk c): chunks <= c + 2 are visible, chunk c + 3 is
+    // requested.  A level spans at most two chunks, so the prefetch only touches visible records.
+    //   garbling  : AES gates on lane pairs (lane, lane ^ G): the two hashes of a half-gate, H(A_sel) and
+    //               H(A_sel ^ delta), run one per lane and the odd lane fetches the other by shuffle
+    //               (it forms the ciphertext, the even lane the output label); free gates one thread
+    //               per (gate, instance);
+    //   evaluating: one thread per (gate, instance) for both kinds.
+    constexpr uint32_t RMASK = GATE_RING - 1;
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t f_idx = wt / G;                            // gate index inside a free pass
+    const uint32_t f_per_pass = NT / G;
+    const uint32_t a_idx = MODE == 0 ? wt / (2 * G) : f_idx;  // gate index inside an AES pass
+    const uint32_t a_per_pass = MODE == 0 ? NT / (2 * G) : f_per_pass;
+    const uint32_t half = (wt / G) & 1u;                      // garbling: which of the two hashes
+    uint32_t pos = 0, chunk = 0;
+    uint32_t n_tot, n_nf;
+    uint4 rec_a = make_uint4(0, 0, 0, 0), rec_f = rec_a;
+    {
+      const uint4 h = ring[0];
+      n_tot = ((h.y >> 25) & 0x7Fu) + 1u;
+      n_nf = h.w >> 24;
+      if (a_idx < n_nf) rec_a = ring[a_idx];
+      if (n_nf + f_idx < n_tot) rec_f = ring[n_nf + f_idx];
+    }
     for (uint32_t lvl = 0; lvl < task.n_levels; ++lvl) {
-      const uint32_t n = (((ring[pos & (GATE_RING - 1)].y >> 25) & 0x7Fu) + 1u) * G;
-      if (MODE == 0) {
-        // Garbling: a PAIR of adjacent lanes serves one (gate, instance).  The two hashes of a
-        // half-gate, H(A_sel) and H(A_sel ^ delta), run one per lane and are exchanged by shuffle:
-        // half the dependent instruction stream per level, which is what bounds a run that sits on
-        // the circuit's critical path (one warp issues at most one instruction per cycle).
-        constexpr uint32_t FULL = 0xFFFFFFFFu;
-        const uint32_t half = wt & 1u;
-        for (uint32_t base = 0; base < n; base += NT / 2) {  // uniform trip count: shuffles are full-warp
-          const uint32_t u = base + (wt >> 1);
-          const bool active = u < n;
-          uint4 graw = make_uint4(0, 10u << 16, 0, 0);
-          if (active) graw = ring[(pos + u / G) & (GATE_RING - 1)];
-          const uint32_t sa = graw.x & 0xFFFFu, sb = graw.x >> 16, sc = graw.y & 0xFFFFu;
-          const uint32_t type = (graw.y >> 16) & 0xFFu;
-          uint4 la = make_uint4(0, 0, 0, 0), lb = la, lc = la, hs = la;
-          if (active) {
-            la = lab[sa * G + pinst];
-            lb = lab[sb * G + pinst];
-          }
-          const bool nonfree = active && type < 8;
-          const unsigned long long gid = call.gid_base + graw.z;
-          const uint32_t ma = 0u - ((type >> 2) & 1u), mb = 0u - ((type >> 1) & 1u), mc = 0u - (type & 1u);
-          if (nonfree) {
-            uint4 x = xor4(la, and4(pdelta, ma));  // selected label; the odd lane hashes the other one
-            if (half) x = xor4(x, pdelta);
+      // ---- non-free gates
+      for (uint32_t g0 = 0; g0 < n_nf; g0 += a_per_pass) {  // uniform trip count: shuffles are full-warp
+        const uint32_t gi = g0 + a_idx;
+        const bool act = gi < n_nf;
+        uint4 r = rec_a;
+        if (g0 != 0 && act) r = ring[(pos + gi) & RMASK];
+        const uint32_t sa = r.x & 0xFFFFu, sb = r.x >> 16, sc = r.y & 0xFFFFu;
+        const uint32_t type = (r.y >> 16) & 0xFFu;
+        const unsigned long long gid = call.gid_base + r.z;
+        if (MODE == 0) {
+          uint4 hs = make_uint4(0, 0, 0, 0);
+          if (act) {
+            uint4 x = xor4(lab[sa * G + inst], and4(delta, 0u - ((type >> 2) & 1u)));  // selected label
+            if (half) x = xor4(x, delta);                                             // the other one
             hs = hash1<HASH>(te, x, gid);
-          } else if (active) {
-            lc = (type == 10) ? xor4(la, pdelta) : xor4(la, lb);
-            if (type == 9) lc = xor4(lc, pdelta);
           }
           uint4 ho;
-          ho.x = __shfl_xor_sync(FULL, hs.x, 1);
-          ho.y = __shfl_xor_sync(FULL, hs.y, 1);
-          ho.z = __shfl_xor_sync(FULL, hs.z, 1);
-          ho.w = __shfl_xor_sync(FULL, hs.w, 1);
-          if (nonfree) {
-            const uint4 h0 = half ? ho : hs;
+          ho.x = __shfl_xor_sync(FULL, hs.x, G);
+          ho.y = __shfl_xor_sync(FULL, hs.y, G);
+          ho.z = __shfl_xor_sync(FULL, hs.z, G);
+          ho.w = __shfl_xor_sync(FULL, hs.w, G);
+          if (act) {
             if (half) {
               if (p.write_ct) {
-                const uint4 ct = xor4(xor4(hs, ho), xor4(lb, and4(pdelta, mb)));
-                unsigned long long cpos = ct_pos0 + graw.w;
+                const uint4 ct = xor4(xor4(hs, ho), xor4(lab[sb * G + inst], and4(delta, 0u - ((type >> 1) & 1u))));
+                unsigned long long cpos = ct_pos0 + (r.w & 0xFFFFFFu);
                 if (p.ct_ring && cpos >= p.ct_ring) cpos -= p.ct_ring;
-                __stcg(p.ct + (size_t)cpos * p.ct_pos_stride + (size_t)(grp * G + pinst) * p.ct_inst_stride, ct);
+                __stcg(ct_out + (size_t)cpos * p.ct_pos_stride, ct);
               }
             } else {
-              lab[sc * G + pinst] = xor4(h0, and4(pdelta, mc));
+              lab[sc * G + inst] = xor4(hs, and4(delta, 0u - (type & 1u)));
             }
-          } else if (active && !half) {
-            lab[sc * G + pinst] = lc;
           }
-        }
-      } else
-      for (uint32_t idx = wt; idx < n; idx += NT) {
-        const uint4 graw = ring[(pos + idx / G) & (GATE_RING - 1)];
-        const uint32_t sa = graw.x & 0xFFFFu, sb = graw.x >> 16, sc = graw.y & 0xFFFFu;
-        const uint32_t type = (graw.y >> 16) & 0xFFu;
-        const uint4 la = lab[sa * G + inst];
-        const uint4 lb = lab[sb * G + inst];
-        uint4 lc;
-        {
+        } else if (act) {
+          const uint4 la = lab[sa * G + inst], lb = lab[sb * G + inst];
           const uint32_t va = sval[sa * G + inst], vb = sval[sb * G + inst];
-          if (type >= 8) {
-            lc = (type == 10) ? la : xor4(la, lb);
-          } else {
-            const unsigned long long gid = call.gid_base + graw.z;
-            const unsigned long long cti = call.ct_base + graw.w;
-            uint4 ct = make_uint4(0, 0, 0, 0);
-            if (cti < p.ct_capacity) ct = __ldcs(p.ct + (size_t)cti * p.B + grp * G + inst);
-            else *p.error_flag = 1u;
-            lc = degarble_nonfree<HASH>(te, type, ct, la, va, lb, gid);
-          }
+          const unsigned long long cti = call.ct_base + (r.w & 0xFFFFFFu);
+          uint4 ct = make_uint4(0, 0, 0, 0);
+          if (cti < p.ct_capacity) ct = __ldcs(p.ct + (size_t)cti * p.B + grp * G + inst);
+          else *p.error_flag = 1u;
+          lab[sc * G + inst] = degarble_nonfree<HASH>(te, type, ct, la, va, lb, gid);
           sval[sc * G + inst] = (uint8_t)gate_value(type, va, vb);
         }
-        lab[sc * G + inst] = lc;
       }
-      pos += n / G;
-      cp_async_wait<1>();  // everything but the newest chunk: covers chunk(pos) + 1
+      // ---- free gates
+      for (uint32_t g0 = n_nf; g0 < n_tot; g0 += f_per_pass) {
+        const uint32_t gi = g0 + f_idx;
+        if (gi < n_tot) {
+          uint4 r = rec_f;
+          if (g0 != n_nf) r = ring[(pos + gi) & RMASK];
+          const uint32_t sa = r.x & 0xFFFFu, sb = r.x >> 16, sc = r.y & 0xFFFFu;
+          const uint32_t type = (r.y >> 16) & 0xFFu;
+          const uint4 la = lab[sa * G + inst], lb = lab[sb * G + inst];
+          uint4 lc = (type == 10) ? la : xor4(la, lb);
+          if (MODE == 0) {
+            if (type != 8) lc = xor4(lc, delta);  // Xnor / Not flip the zero label
+          } else {
+            sval[sc * G + inst] = (uint8_t)gate_value(type, sval[sa * G + inst], sval[sb * G + inst]);
+          }
+          lab[sc * G + inst] = lc;
+        }
+      }
+      // ---- next level's header and first records (independent of this level's results)
+      const uint32_t pos_n = pos + n_tot;
+      uint32_t n_tot_n = 0, n_nf_n = 0;
+      if (lvl + 1 < task.n_levels) {
+        const uint4 h = ring[pos_n & RMASK];
+        n_tot_n = ((h.y >> 25) & 0x7Fu) + 1u;
+        n_nf_n = h.w >> 24;
+        if (a_idx < n_nf_n) rec_a = ring[(pos_n + a_idx) & RMASK];
+        if (n_nf_n + f_idx < n_tot_n) rec_f = ring[(pos_n + n_nf_n + f_idx) & RMASK];
+      }
+      const bool cross = pos_n / GATE_CHUNK != chunk;  // uniform over the worker; at most one chunk per level
+      if (cross) cp_async_wait<0>();                   // chunk c + 3, requested one crossing ago
       named_bar(bar_id, NT);
-      while (released < pos / GATE_CHUNK) {  // chunks behind `pos` are free: request the next ones
+      if (cross) {                                     // the chunk left behind is free: request chunk c + 4
         issue_chunk();
-        released++;
+        chunk++;
       }
+      if (prof) {
+        lap(n_nf ? PROF_AES_LEVELS : PROF_FREE_LEVELS);
+        wprof[n_nf ? PROF_N_AES_LEVELS : PROF_N_FREE_LEVELS]++;
+        wprof[PROF_N_PASSES] += (n_nf + a_per_pass - 1) / a_per_pass;
+      }
+      pos = pos_n;
+      n_tot = n_tot_n;
+      n_nf = n_nf_n;
     }
     cp_async_wait<0>();
 
@@ -606,8 +666,14 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
     }
     __threadfence();
     named_bar(bar_id, NT);
+    lap(PROF_SCATTER);
     sched_complete_cta(p, call_i, grp, wt, NT, keep);
     named_bar(bar_id, NT);
+    lap(PROF_COMPLETE);
+  }
+  if (prof) {
+    wprof[PROF_TOTAL] = (unsigned long long)(clock64() - t_begin);
+    for (int i = 0; i < PROF_WORDS; i++) atomicAdd(p.prof + i, wprof[i]);
   }
 }
 
@@ -676,6 +742,7 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
     const uint8_t* gval = p.vals + gbase * 32u + lane;
     uint4 delta = make_uint4(0, 0, 0, 0);
     if (MODE == 0) delta = p.delta[instance];
+    uint4* const ct_out = p.ct + (size_t)(instance >> p.ct_qshift) * p.ct_quad_stride + (instance & ((1u << p.ct_qshift) - 1u));
     my[0] = __ldcg(glab);
     my[32] = __ldcg(glab + 32);
     if (MODE == 1) { myv[0] = 0; myv[32] = 1; }
@@ -734,7 +801,7 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
             if (p.ct_ring && pos >= p.ct_ring) pos -= p.ct_ring;
             uint4 ct;
             lc = garble_nonfree<HASH>(te, type, la, lb, delta, gid, ct);
-            if (p.write_ct && act) __stcg(p.ct + (size_t)pos * p.ct_pos_stride + (size_t)instance * p.ct_inst_stride, ct);
+            if (p.write_ct && act) __stcg(ct_out + (size_t)pos * p.ct_pos_stride, ct);
           }
         } else {
           const uint32_t va = myv[sa * 32u], vb = myv[sb * 32u];
@@ -945,6 +1012,22 @@ __global__ void __launch_bounds__(1024, 1) k_bench_hash(unsigned long long per_t
     a.x ^= b.w;
   }
   if (a.x == 0x12345678u && b.y == 0x9abcdef0u) sink[0] = xor4(a, b);  // defeat DCE
+}
+
+// dependent-hash latency probe: every thread chains n one-block gate hashes; thread 0 of block 0 reports
+// the cycles (what one barrier-separated level of dependent non-free gates costs at the least)
+template <int HASH>
+__global__ void k_hash_latency(unsigned long long n, unsigned long long* out) {
+  extern __shared__ uint4 smem[];
+  uint32_t* te = reinterpret_cast<uint32_t*>(smem);
+  load_tables(te, threadIdx.x, blockDim.x);
+  __syncthreads();
+  uint4 x = make_uint4(threadIdx.x, blockIdx.x, 2, 3);
+  const long long t0 = clock64();
+  for (unsigned long long i = 0; i < n; i++) x = hash1<HASH>(te, x, i);
+  const long long t1 = clock64();
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = (unsigned long long)(t1 - t0);
+  if (x.x == 0x12345678u && x.y == 0x9abcdef0u) out[1] = x.z;  // defeat DCE
 }
 
 }  // namespace gsvdev

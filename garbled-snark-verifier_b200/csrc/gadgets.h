@@ -111,6 +111,10 @@ Wire groth16_verify(Builder& c, const std::vector<Wires>& publics, const G1P& a,
                     const host::VerifyingKey& vk);
 Wire groth16_verify_compressed(Builder& c, const Wires& in, size_t n_public, const host::VerifyingKey& vk);
 uint32_t build_groth16_verify_compressed(Builder& b, const host::VerifyingKey& vk, size_t n_public);
+// groth16_verify on uncompressed points (src/gadgets/groth16.rs:57-110; inputs per src/garbled_groth16.rs:141-176)
+uint32_t build_groth16_verify(Builder& b, const host::VerifyingKey& vk, size_t n_public);
+// dispatch over the circuit names documented at gsv_program_build (include/gsv_cuda.h)
+uint32_t build_named_circuit(Builder& b, const std::string& name);
 uint32_t build_fq_inverse(Builder& b);
 uint32_t build_fq_sqrt(Builder& b);
 uint32_t build_fq2_sqrt(Builder& b);

@@ -1165,6 +1165,24 @@ uint32_t build_groth16_verify_compressed(Builder& b, const host::VerifyingKey& v
     return Wires{groth16_verify_compressed(c, in, n_public, vk)};
   });
 }
+// groth16_verify on uncompressed affine points with z = 1 constants (src/garbled_groth16.rs:108-176):
+// inputs in EncodeInput order: public (254 each), a.x, a.y, b.x (c0, c1), b.y (c0, c1), c.x, c.y = 2 286 wires
+// for one public input -- what examples/groth16_garble.rs garbles.
+uint32_t build_groth16_verify(Builder& b, const host::VerifyingKey& vk, size_t n_public) {
+  size_t n_in = n_public * 254 + 8 * 254;
+  return b.build_root("groth16_verify", n_in, [vk, n_public](Builder& c, const Wires& in) {
+    size_t o = 0;
+    std::vector<Wires> publics;
+    for (size_t i = 0; i < n_public; i++, o += 254) publics.push_back(slice(in, o, o + 254));
+    const Fq one = fq_constant(mont254(U256(1))), zero = fq_constant(mont254(U256()));
+    G1P a{slice(in, o, o + 254), slice(in, o + 254, o + 508), one};
+    o += 508;
+    G2P bq{fq2_from_wires(in.data() + o), fq2_from_wires(in.data() + o + 508), Fq2{one, zero}};
+    o += 1016;
+    G1P cc{slice(in, o, o + 254), slice(in, o + 254, o + 508), one};
+    return Wires{groth16_verify(c, publics, a, bq, cc, vk)};
+  });
+}
 uint32_t build_fq_inverse(Builder& b) {
   return b.build_root("fq_inverse_montgomery", 254, [](Builder& c, const Wires& in) { return fq_inverse_montgomery(c, in); });
 }

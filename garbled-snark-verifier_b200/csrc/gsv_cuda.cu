@@ -277,36 +277,7 @@ gsv_program* gsv_program_build(const char* circuit, const gsv_plan_options* opt)
   try {
     auto b = std::make_unique<gsv::Builder>();
     std::string c = circuit ? circuit : "";
-    uint32_t r;
-    if (c == "fq12_mul") r = gsv::build_fq12_mul(*b);
-    else if (c == "fq6_mul") r = gsv::build_fq6_mul(*b);
-    else if (c == "fq2_mul") r = gsv::build_fq2_mul(*b);
-    else if (c == "fq_mul") r = gsv::build_fq_mul(*b);
-    else if (c == "fq_add") r = gsv::build_fq_add(*b);
-    else if (c == "fq_expr") r = gsv::build_fq_expr(*b);
-    else if (c == "gate_zoo") r = gsv::build_gate_zoo(*b);
-    else if (c.rfind("bn_mul", 0) == 0) r = gsv::build_bn_mul(*b, (size_t)std::stoul(c.substr(6)));
-    else if (c == "fq_inverse") r = gsv::build_fq_inverse(*b);
-    else if (c == "fq_sqrt") r = gsv::build_fq_sqrt(*b);
-    else if (c == "fq2_sqrt") r = gsv::build_fq2_sqrt(*b);
-    else if (c == "g1_add") r = gsv::build_g1_add(*b);
-    else if (c == "g1_msm1") r = gsv::build_g1_msm1(*b, gsv::host::g1_to_affine(gsv::host::g1_mul(gsv::host::g1_from_affine(gsv::host::g1_generator()), gsv::U256(0xC0FFEE))));
-    else if (c == "fq12_square") r = gsv::build_fq12_square(*b);
-    else if (c == "fq12_cyclotomic_square") r = gsv::build_fq12_cyclotomic_square(*b);
-    else if (c == "fq12_inverse") r = gsv::build_fq12_inverse(*b);
-    else if (c.rfind("fq12_frobenius", 0) == 0) r = gsv::build_fq12_frobenius(*b, (size_t)std::stoul(c.substr(14)));
-    else if (c == "final_exponentiation") r = gsv::build_final_exponentiation(*b);
-    else if (c == "miller_loop_groth16" || c == "groth16_verify_compressed") {
-      gsv::host::VerifyingKey vk;
-      gsv::host::Proof pr;
-      gsv::host::synthetic_groth16(7, gsv::U256(424242), vk, pr);
-      if (c == "miller_loop_groth16") r = gsv::build_miller_loop_groth16(*b, gsv::host::g2_neg(vk.gamma_g2), gsv::host::g2_neg(vk.delta_g2));
-      else r = gsv::build_groth16_verify_compressed(*b, vk, 1);
-    }
-    else {
-      fail(GSV_ERR_INVALID, "unknown circuit: " + c);
-      return nullptr;
-    }
+    const uint32_t r = gsv::build_named_circuit(*b, c);
     return finish_program(std::move(b), r, opt);
   } catch (const std::exception& e) {
     fail(GSV_ERR_INVALID, e.what());
@@ -369,6 +340,13 @@ int gsv_host_chain_fold(uint8_t* h, const uint8_t* base, uint64_t pos_stride, ui
   if (!h || (!base && n_pos)) return fail(GSV_ERR_INVALID, "null argument");
   if (!gsv::host_chain_available()) return fail(GSV_ERR_INVALID, "host CPU has no AES-NI");
   gsv::host_chain_fold(h, base, pos_stride, inst_stride, n_pos, n_inst);
+  return GSV_OK;
+}
+
+int gsv_host_chain_fold_quads(uint8_t* h, const uint8_t* base, uint64_t quad_bytes, uint64_t n_pos, uint32_t n_quads) {
+  if (!h || (!base && n_pos)) return fail(GSV_ERR_INVALID, "null argument");
+  if (!gsv::host_chain_available()) return fail(GSV_ERR_INVALID, "host CPU has no AES-NI");
+  gsv::host_chain_fold_quads(h, base, quad_bytes, n_pos, n_quads);
   return GSV_OK;
 }
 
@@ -459,12 +437,23 @@ int gsv_program_execute_plan(const gsv_program* p, int lane_form, const uint8_t*
 }
 
 int gsv_groth16_synthetic_inputs(uint64_t public_x, int flip_public, uint8_t* bits, uint32_t n_bits) {
-  if (!bits || n_bits != 1273) return fail(GSV_ERR_INVALID, "need a 1273-bit buffer");
+  // 1273 bits: groth16_verify_compressed (x + sign flag per point); 2286 bits: groth16_verify (affine x, y)
+  if (!bits || (n_bits != 1273 && n_bits != 2286)) return fail(GSV_ERR_INVALID, "need a 1273-bit (compressed) or 2286-bit buffer");
   try {
     using namespace gsv::host;
     VerifyingKey vk;
     Proof pr;
     synthetic_groth16(7, gsv::U256(public_x), vk, pr);
+    size_t o = 0;
+    auto put = [&](const gsv::U256& v) { for (unsigned i = 0; i < 254; i++) bits[o++] = v.bit(i); };
+    put(gsv::U256(flip_public ? public_x + 1 : public_x));
+    if (n_bits == 2286) {
+      put(gsv::mont254(pr.a.x.to_u256())); put(gsv::mont254(pr.a.y.to_u256()));
+      put(gsv::mont254(pr.b.x.c0.to_u256())); put(gsv::mont254(pr.b.x.c1.to_u256()));
+      put(gsv::mont254(pr.b.y.c0.to_u256())); put(gsv::mont254(pr.b.y.c1.to_u256()));
+      put(gsv::mont254(pr.c.x.to_u256())); put(gsv::mont254(pr.c.y.to_u256()));
+      return GSV_OK;
+    }
     const gsv::U256 e_sqrt = gsv::U256::from_dec("5472060717959818805561601436314318772174077789324455915672259473661306552146");
     const gsv::U256& pm = FpCtx::get().p;
     auto g1flag = [&](const G1Affine& a) { return fp_pow(a.x * a.x * a.x + Fp::from_u64(3), e_sqrt) == a.y; };
@@ -478,9 +467,6 @@ int gsv_groth16_synthetic_inputs(uint64_t public_x, int flip_public, uint8_t* bi
     Fp c0 = fp_pow(delta_final, e_sqrt);
     Fp c1 = fp_inv(c0) * (y2.c1 * half);
     bool bflag = (c0 == pr.b.y.c0) && (c1 == pr.b.y.c1);
-    size_t o = 0;
-    auto put = [&](const gsv::U256& v) { for (unsigned i = 0; i < 254; i++) bits[o++] = v.bit(i); };
-    put(gsv::U256(flip_public ? public_x + 1 : public_x));
     put(gsv::mont254(pr.a.x.to_u256())); bits[o++] = g1flag(pr.a);
     put(gsv::mont254(pr.b.x.c0.to_u256())); put(gsv::mont254(pr.b.x.c1.to_u256())); bits[o++] = bflag;
     put(gsv::mont254(pr.c.x.to_u256())); bits[o++] = g1flag(pr.c);
@@ -548,6 +534,7 @@ struct gsv_session {
   size_t smem_garble = 0, smem_eval = 0;
   uint32_t n_chain_warps = 0;      // chain warps per chain CTA
   uint32_t n_chain_ctas = 0;       // trailing CTAs dedicated to the commitment chain
+  uint32_t host_threads = 1;       // GSV_CT_COMMIT_HOST: fold threads
   uint64_t ct_ring = 0;  // ring capacity in ciphertexts (0 = whole stream kept)
   uint32_t epoch = 0;
   cudaStream_t stream = nullptr;
@@ -569,6 +556,7 @@ struct gsv_session {
   uint32_t queue_log2 = 0;
   DevBuf<unsigned long long> d_progress;
   DevBuf<unsigned long long> d_seeds;
+  DevBuf<unsigned long long> d_prof;  // GSV_PROFILE=1: per-phase worker cycle totals
   // lane mode (one warp = 32 instances, emission-order tasks)
   bool lane_mode = false;
   uint32_t B_pad = 0;            // B rounded up to whole groups
@@ -729,12 +717,15 @@ EngineParams make_params(gsv_session* s) {
   p.scratch_stride = s->scratch_stride;
   p.host_chain = s->ct_mode == GSV_CT_COMMIT_HOST ? 1u : 0u;
   p.ct_pos_stride = s->B;
-  p.ct_inst_stride = 1;
-  if (p.host_chain) {  // instance-major ring: each chain drains as one sequential host stream
-    p.ct_pos_stride = 1;
-    p.ct_inst_stride = s->d_ct.n / s->B;
+  p.ct_quad_stride = 0;
+  p.ct_qshift = 31;
+  if (p.host_chain) {  // [instance quad][ring position][4]: each quad of chains drains as one sequential host stream
+    p.ct_pos_stride = 4;
+    p.ct_quad_stride = s->d_ct.n / ((s->B + 3) / 4);
+    p.ct_qshift = 2;
   }
   p.host_ready = s->hc_ready_dev;
+  p.prof = s->d_prof.p;
   return p;
 }
 
@@ -789,22 +780,20 @@ void launch_engine(gsv_session* s, int hasher, const EngineParams& p) {
 
 // Drains the ciphertext ring of a running GSV_CT_COMMIT_HOST garbling kernel and folds the B chains
 // on host threads.  Called right after the kernel launch; returns when every chain is complete.
+// Device layout [instance quad][ring position][4] (make_params): every drain is one 2-D copy of
+// n_quads rows of n * 64 contiguous bytes, and a fold step of a quad is one 64-byte load.
+// Waiting threads sleep (the drain loop and the fold threads of several sessions / ranks share the
+// host cores; spinning on yield() would take the cores the folds need).
 void run_host_chain(gsv_session* s, uint8_t* commits) {
   const gsv::Program& g = s->prog->prog;
-  const uint32_t B = s->B;
+  const uint32_t B = s->B, nq = (B + 3) / 4;
   const uint64_t total = g.total_ct;
-  const size_t pos_bytes = (size_t)B * 16;
-  const uint64_t chunk_pos = std::max<uint64_t>(1, s->hc_buf_bytes / pos_bytes);
-  const uint64_t cap = s->d_ct.n / B;  // device ring (or whole stream) positions per instance
+  const size_t row_bytes = (size_t)nq * 64;
+  const uint64_t chunk_pos = std::max<uint64_t>(1, s->hc_buf_bytes / row_bytes);
+  const uint64_t cap = s->d_ct.n / ((size_t)nq * 4);  // device ring (or whole stream) positions per instance
   constexpr int NB = gsv_session::HC_BUFS;
-  unsigned hw = std::thread::hardware_concurrency();
-  if (hw == 0) hw = 4;
-  // 4+ interleaved chains per thread keep the AES pipeline busy; one thread per physical core
-  // (hardware threads / 2) leaves the SMT siblings to the drain loop and the caller
-  uint32_t T = std::min<uint32_t>((B + 3) / 4, std::max(1u, hw / 2));
-  if (const char* e = getenv("GSV_HOST_CHAIN_THREADS")) T = std::max(1, atoi(e));
-  T = std::max<uint32_t>(1, std::min(T, B));
-  std::vector<uint8_t> h((size_t)B * 16, 0);
+  const uint32_t T = std::max<uint32_t>(1, std::min(s->host_threads, nq));
+  std::vector<uint8_t> h((size_t)nq * 64, 0);
   std::atomic<uint64_t> slot_job[NB];   // 1 + index of the job whose copy was enqueued into the slot
   std::atomic<uint64_t> slot_done[NB];  // hasher completions on the slot, over all jobs
   uint64_t slot_npos[NB] = {0, 0, 0, 0};
@@ -814,21 +803,24 @@ void run_host_chain(gsv_session* s, uint8_t* commits) {
   }
   std::atomic<int64_t> n_jobs{-1};
   std::atomic<bool> abort{false};
+  const auto nap = [] { std::this_thread::sleep_for(std::chrono::microseconds(50)); };
   auto hasher = [&](uint32_t t) {
-    const uint32_t i0 = (uint32_t)((uint64_t)B * t / T), i1 = (uint32_t)((uint64_t)B * (t + 1) / T);
+    const uint32_t q0 = (uint32_t)((uint64_t)nq * t / T), q1 = (uint32_t)((uint64_t)nq * (t + 1) / T);
     cudaSetDevice(s->device);
     for (uint64_t j = 0;; j++) {
       const int b = (int)(j % NB);
       while (slot_job[b].load(std::memory_order_acquire) != j + 1) {
         const int64_t nj = n_jobs.load(std::memory_order_acquire);
         if (abort.load() || (nj >= 0 && (int64_t)j >= nj)) return;
-        std::this_thread::yield();
+        nap();
       }
       if (cudaEventSynchronize(s->hc_ev[b]) != cudaSuccess) {
         abort.store(true);
         return;
       }
-      if (i1 > i0) gsv::host_chain_fold(h.data() + (size_t)i0 * 16, s->hc_buf[b] + (size_t)i0 * chunk_pos * 16, 1, chunk_pos, slot_npos[b], i1 - i0);
+      if (q1 > q0)
+        gsv::host_chain_fold_quads(h.data() + (size_t)q0 * 64, s->hc_buf[b] + (size_t)q0 * chunk_pos * 64, chunk_pos * 64,
+                                   slot_npos[b], q1 - q0);
       slot_done[b].fetch_add(1, std::memory_order_release);
     }
   };
@@ -840,35 +832,36 @@ void run_host_chain(gsv_session* s, uint8_t* commits) {
     auto last_query = std::chrono::steady_clock::now();
     while (copied < total) {
       const uint64_t ready = *reinterpret_cast<volatile unsigned long long*>(s->hc_ready);
-      if (ready <= copied) {
-        auto now = std::chrono::steady_clock::now();
-        if (now - last_query > std::chrono::milliseconds(5)) {
-          last_query = now;
-          cudaError_t q = cudaStreamQuery(s->stream);
-          if (q != cudaSuccess && q != cudaErrorNotReady) throw std::runtime_error(std::string("garbling kernel failed: ") + cudaGetErrorString(q));
-          if (q == cudaSuccess && *reinterpret_cast<volatile unsigned long long*>(s->hc_ready) <= copied)
-            throw std::runtime_error("garbling kernel ended before the stream was complete");
-        }
-        std::this_thread::yield();
-        continue;
-      }
-      uint64_t n = std::min<uint64_t>(ready - copied, chunk_pos);
+      uint64_t n = ready > copied ? std::min<uint64_t>(ready - copied, chunk_pos) : 0;
       uint64_t pos = copied;
       if (s->ct_ring) {
         pos = copied % s->ct_ring;
         n = std::min<uint64_t>(n, s->ct_ring - pos);
       }
-      // small drains waste DMA launches: unless the stream is ending, wait for half a buffer
-      if (n < chunk_pos / 2 && copied + n < total && ready - copied < chunk_pos / 2 && !(s->ct_ring && pos + n == s->ct_ring)) {
-        std::this_thread::yield();
+      // small drains waste DMA launches: unless the stream or the ring ends, wait for half a buffer (or a
+      // quarter of a small ring: the kernel stalls once the ring is full, so never wait for more than it holds)
+      uint64_t thresh = chunk_pos / 2;
+      if (s->ct_ring) thresh = std::min<uint64_t>(thresh, std::max<uint64_t>(1, s->ct_ring / 4));
+      const bool worth = n > 0 && (n >= thresh || copied + n == total || (s->ct_ring && pos + n == s->ct_ring));
+      if (!worth) {
+        auto now = std::chrono::steady_clock::now();
+        if (now - last_query > std::chrono::milliseconds(5)) {
+          last_query = now;
+          cudaError_t q = cudaStreamQuery(s->stream);
+          if (q != cudaSuccess && q != cudaErrorNotReady) throw std::runtime_error(std::string("garbling kernel failed: ") + cudaGetErrorString(q));
+          if (q == cudaSuccess && *reinterpret_cast<volatile unsigned long long*>(s->hc_ready) < total)
+            throw std::runtime_error("garbling kernel ended before the stream was complete");
+        }
+        nap();
         continue;
       }
       const int b = (int)(jobs % NB);
       while (slot_done[b].load(std::memory_order_acquire) != (uint64_t)T * (jobs / NB)) {
         if (abort.load()) throw std::runtime_error("host chain thread failed");
-        std::this_thread::yield();
+        nap();
       }
-      CUDA_TRY(cudaMemcpy2DAsync(s->hc_buf[b], (size_t)chunk_pos * 16, s->d_ct.p + pos, (size_t)cap * 16, (size_t)n * 16, B, cudaMemcpyDeviceToHost, s->copy_stream));
+      CUDA_TRY(cudaMemcpy2DAsync(s->hc_buf[b], (size_t)chunk_pos * 64, s->d_ct.p + pos * 4, (size_t)cap * 64, (size_t)n * 64, nq,
+                                 cudaMemcpyDeviceToHost, s->copy_stream));
       s->hc_consumed[b] = copied + n;
       CUDA_TRY(cudaMemcpyAsync(s->d_progress.p, s->hc_consumed + b, 8, cudaMemcpyHostToDevice, s->copy_stream));
       CUDA_TRY(cudaEventRecord(s->hc_ev[b], s->copy_stream));
@@ -884,8 +877,16 @@ void run_host_chain(gsv_session* s, uint8_t* commits) {
   }
   for (auto& t : threads) t.join();
   if (err.empty() && abort.load()) err = "host chain thread failed";
-  if (!err.empty()) throw std::runtime_error(err);
-  memcpy(commits, h.data(), h.size());
+  if (!err.empty()) {
+    // unblock the persistent kernel before reporting: with a ring its workers park behind the progress
+    // word nobody advances any more; "everything consumed" lets it run to completion
+    s->hc_consumed[0] = ~0ull >> 1;
+    cudaMemcpyAsync(s->d_progress.p, s->hc_consumed, 8, cudaMemcpyHostToDevice, s->copy_stream);
+    cudaStreamSynchronize(s->copy_stream);
+    cudaStreamSynchronize(s->stream);
+    throw std::runtime_error(err);
+  }
+  for (uint32_t i = 0; i < B; i++) memcpy(commits + (size_t)i * 16, h.data() + (size_t)i * 16, 16);
 }
 
 }  // namespace
@@ -908,6 +909,9 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
     s->sm_count = prop.multiProcessorCount;
+    // spatial sharing: several sessions (e.g. software-pipelined cut-and-choose batches) each run their
+    // persistent grid on a slice of the SMs
+    if (opt->sm_limit) s->sm_count = std::max(2, std::min<int>(s->sm_count, (int)opt->sm_limit));
     const gsv::Program& g = p->prog;
     const size_t smem_max = prop.sharedMemPerBlockOptin;
     uint32_t slots = std::max<uint32_t>(g.max_task_slots, 4);
@@ -933,13 +937,20 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
       if (!gsv::host_chain_available()) throw std::runtime_error("GSV_CT_COMMIT_HOST needs a host CPU with AES-NI");
       n_chain = 1;  // one publisher warp on one trailing CTA
       s->n_chain_ctas = 1;
+      // fold threads: one per quad of chains up to half the hardware threads (the SMT siblings share the
+      // AES units); callers that run several sessions or ranks per host pass their share explicitly
+      unsigned hw = std::thread::hardware_concurrency();
+      if (hw == 0) hw = 4;
+      s->host_threads = opt->host_threads ? opt->host_threads : std::max(1u, hw / 2);
+      if (const char* e = getenv("GSV_HOST_CHAIN_THREADS")) s->host_threads = std::max(1, atoi(e));
     }
-    uint32_t n_workers = 1024 / s->NT;
+    uint32_t n_workers = std::min<uint32_t>(1024 / s->NT, 15);  // worker w syncs on named barrier w + 1 (ids 1..15)
     if (n_workers == 0) throw std::runtime_error("worker_threads too large");
     // largest G (power of two dividing B, <= 8) whose label working set fits next to the tables
     auto smem_for = [&](uint32_t G, uint32_t nw, bool eval) {
       size_t lab = (size_t)slots * G;
-      return (size_t)AES_TABLE_BYTES + nw * lab * 16 + (((eval ? nw * lab : 0) + nw * 8 + 15) & ~(size_t)15) + (size_t)nw * GATE_RING * 16;
+      return (size_t)AES_TABLE_BYTES + nw * lab * 16 + (((eval ? nw * lab : 0) + nw * 8 + 15) & ~(size_t)15) + (size_t)nw * GATE_RING * 16 +
+             (size_t)nw * PROF_WORDS * 8;
     };
     // execution mode: lane mode (warp = 32 instances) for batches that fill warps, the levelised
     // shared-memory mode otherwise
@@ -1032,17 +1043,20 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
       CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
       // The ring bounds how far garbling may run ahead of the (serial, emission-ordered) chain, and
       // with it the task parallelism available inside one instance: make it as large as HBM allows.
-      const uint64_t budget = (uint64_t)(free_b * 0.85);
-      uint64_t ring = std::max<uint64_t>(budget / ((uint64_t)s->B * 16), 1);
+      uint64_t budget = (uint64_t)(free_b * 0.85);
+      if (opt->ct_buffer_bytes) budget = std::min<uint64_t>(budget, opt->ct_buffer_bytes);
+      // the host-fold layout stores whole quads of instances
+      const uint64_t B_ct = s->ct_mode == GSV_CT_COMMIT_HOST ? (uint64_t)((s->B + 3) / 4) * 4 : s->B;
+      uint64_t ring = std::max<uint64_t>(budget / (B_ct * 16), 1);
       if (opt->ct_ring_log2) ring = std::min<uint64_t>(ring, 1ull << opt->ct_ring_log2);
       if (s->ct_mode == GSV_CT_KEEP || s->ct_mode == GSV_CT_KEEP_RAW || ring >= total) {
-        if (total * s->B * 16 > (uint64_t)(free_b * 0.9)) throw std::runtime_error("ciphertext stream does not fit in HBM; use GSV_CT_COMMIT");
+        if (total * B_ct * 16 > (uint64_t)(free_b * 0.9)) throw std::runtime_error("ciphertext stream does not fit in HBM; use GSV_CT_COMMIT");
         s->ct_ring = 0;
-        s->d_ct.alloc((size_t)total * s->B);
+        s->d_ct.alloc((size_t)total * B_ct);
       } else {
         if (ring < 2 * max_task_ct) throw std::runtime_error("ciphertext ring smaller than two tasks; fewer instances needed");
         s->ct_ring = ring;
-        s->d_ct.alloc((size_t)ring * s->B);
+        s->d_ct.alloc((size_t)ring * B_ct);
         // ring governor: parking buckets of ring/64 ciphertexts
         s->park_q = std::max<uint64_t>(ring / 64, 1);
         s->d_park_head.alloc((size_t)(total / s->park_q + 2));
@@ -1050,6 +1064,10 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
       }
     }
     s->d_limit.alloc(1);
+    if (getenv("GSV_PROFILE")) {
+      s->d_prof.alloc(PROF_WORDS);
+      CUDA_TRY(cudaMemset(s->d_prof.p, 0, PROF_WORDS * 8));
+    }
     return s.release();
   } catch (const std::exception& e) {
     fail(std::string(e.what()).find("no CUDA device") != std::string::npos ? GSV_ERR_NO_DEVICE : GSV_ERR_CUDA, e.what());
@@ -1141,6 +1159,23 @@ int gsv_garble_batch(gsv_session* s, int hasher, const uint64_t* seeds, gsv_garb
       res->ms_total = (float)host_ms;
     }
     if (s->ct_mode == GSV_CT_COMMIT_HOST) res->ms_commit = res->ms_total - res->ms_seed - res->ms_garble;
+    if (s->d_prof.p) {
+      unsigned long long pc[PROF_WORDS];
+      CUDA_TRY(cudaMemcpy(pc, s->d_prof.p, sizeof(pc), cudaMemcpyDeviceToHost));
+      CUDA_TRY(cudaMemset(s->d_prof.p, 0, sizeof(pc)));
+      const double tot = (double)std::max<unsigned long long>(pc[PROF_TOTAL], 1);
+      fprintf(stderr,
+              "[prof] worker cycles: wait %.1f%% gather %.1f%% aes-levels %.1f%% free-levels %.1f%% scatter %.1f%% complete %.1f%% | "
+              "items %llu aes-levels %llu (%.0f cyc) free-levels %llu (%.0f cyc) passes/level %.2f gather %.0f scatter %.0f complete %.0f cyc/item\n",
+              100 * pc[PROF_WAIT] / tot, 100 * pc[PROF_GATHER] / tot, 100 * pc[PROF_AES_LEVELS] / tot,
+              100 * pc[PROF_FREE_LEVELS] / tot, 100 * pc[PROF_SCATTER] / tot, 100 * pc[PROF_COMPLETE] / tot,
+              pc[PROF_N_ITEMS], pc[PROF_N_AES_LEVELS], (double)pc[PROF_AES_LEVELS] / std::max<unsigned long long>(pc[PROF_N_AES_LEVELS], 1),
+              pc[PROF_N_FREE_LEVELS], (double)pc[PROF_FREE_LEVELS] / std::max<unsigned long long>(pc[PROF_N_FREE_LEVELS], 1),
+              (double)pc[PROF_N_PASSES] / std::max<unsigned long long>(pc[PROF_N_AES_LEVELS] + pc[PROF_N_FREE_LEVELS], 1),
+              (double)pc[PROF_GATHER] / std::max<unsigned long long>(pc[PROF_N_ITEMS], 1),
+              (double)pc[PROF_SCATTER] / std::max<unsigned long long>(pc[PROF_N_ITEMS], 1),
+              (double)pc[PROF_COMPLETE] / std::max<unsigned long long>(pc[PROF_N_ITEMS], 1));
+    }
     res->n_ciphertexts = g.total_ct;
     res->n_launches = launches;
     s->ct_valid = (s->ct_mode != GSV_CT_NONE);
@@ -1155,7 +1190,9 @@ int gsv_session_read_ciphertexts(gsv_session* s, uint32_t instance, uint64_t fir
   try {
     CUDA_TRY(cudaSetDevice(s->device));
     const gsv::Program& g = s->prog->prog;
-    if (!s->ct_valid || s->ct_mode == GSV_CT_NONE || s->ct_ring) return fail(GSV_ERR_INVALID, "no ciphertext stream kept (use GSV_CT_KEEP)");
+    // GSV_CT_COMMIT_HOST lays its buffer out for the host drain (not [position][instance]): never readable here
+    if (!s->ct_valid || s->ct_mode == GSV_CT_NONE || s->ct_mode == GSV_CT_COMMIT_HOST || s->ct_ring)
+      return fail(GSV_ERR_INVALID, "no ciphertext stream kept (use GSV_CT_KEEP)");
     if (instance >= s->B || first + count > g.total_ct) return fail(GSV_ERR_INVALID, "range out of bounds");
     if (count == 0) return GSV_OK;
     if (s->d_stage.n < count) s->d_stage.alloc(count);
@@ -1193,7 +1230,7 @@ int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io) {
         }
       }
       ct_avail = io->ct_stream_len;
-    } else if (!s->ct_valid || s->ct_ring) {
+    } else if (!s->ct_valid || s->ct_ring || s->ct_mode == GSV_CT_COMMIT_HOST) {
       return fail(GSV_ERR_INVALID, "no ciphertext stream in the session (garble with GSV_CT_KEEP first)");
     }
     if (s->d_vals.n < (size_t)s->B_pad * g.n_global_slots) s->d_vals.alloc((size_t)s->B_pad * g.n_global_slots);
@@ -1299,6 +1336,28 @@ int gsv_hash_blocks(int device, int hasher, const uint8_t* x, const uint64_t* gi
     else k_hash_blocks<HASH_BLAKE3><<<hb_grid, 256, AES_TABLE_BYTES>>>(d_in.p, d_gid.p, n, d_out.p);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(out, d_out.p, n * 16, cudaMemcpyDeviceToHost));
+    return GSV_OK;
+  } catch (const std::exception& e) {
+    return fail(std::string(e.what()).find("no CUDA device") != std::string::npos ? GSV_ERR_NO_DEVICE : GSV_ERR_CUDA, e.what());
+  }
+}
+
+int gsv_bench_hash_latency(int device, int hasher, uint32_t warps_per_sm, uint64_t n, double* cycles_per_hash) {
+  if (!cycles_per_hash || warps_per_sm == 0 || warps_per_sm > 32 || n == 0) return fail(GSV_ERR_INVALID, "bad argument");
+  try {
+    ensure_device(device);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    DevBuf<unsigned long long> out;
+    out.alloc(2);
+    CUDA_TRY(cudaFuncSetAttribute(k_hash_latency<HASH_AES>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_hash_latency<HASH_BLAKE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
+    if (hasher == GSV_HASH_AES) k_hash_latency<HASH_AES><<<prop.multiProcessorCount, 32 * warps_per_sm, AES_TABLE_BYTES>>>(n, out.p);
+    else k_hash_latency<HASH_BLAKE3><<<prop.multiProcessorCount, 32 * warps_per_sm, AES_TABLE_BYTES>>>(n, out.p);
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long cyc = 0;
+    CUDA_TRY(cudaMemcpy(&cyc, out.p, 8, cudaMemcpyDeviceToHost));
+    *cycles_per_hash = (double)cyc / (double)n;
     return GSV_OK;
   } catch (const std::exception& e) {
     return fail(std::string(e.what()).find("no CUDA device") != std::string::npos ? GSV_ERR_NO_DEVICE : GSV_ERR_CUDA, e.what());

@@ -106,6 +106,33 @@ __attribute__((target("avx512f,avx512vl,vaes"))) void fold_vaes(uint8_t* h, cons
   for (int z = 0; z < Z; z++) _mm512_storeu_si512(h + 64 * z, _mm512_aesenclast_epi128(t[z], k[10]));
 }
 
+// quad layout: Z quads side by side, each step of a quad is one 64-byte row
+template <int Z>
+__attribute__((target("avx512f,avx512vl,vaes"))) void fold_quads_vaes(uint8_t* h, const uint8_t* base, size_t quad_bytes,
+                                                                      size_t n_pos, const RoundKeys& rk) {
+  if (n_pos == 0) return;
+  __m512i k[11];
+  for (int r = 0; r < 11; r++) k[r] = _mm512_broadcast_i32x4(rk.k[r]);
+  const __m512i k10_0 = _mm512_xor_si512(k[10], k[0]);
+  __m512i t[Z];
+  const uint8_t* src[Z];
+  for (int z = 0; z < Z; z++) {
+    src[z] = base + (size_t)z * quad_bytes;
+    t[z] = _mm512_xor_si512(_mm512_xor_si512(_mm512_loadu_si512(h + 64 * z), _mm512_loadu_si512(src[z])), k[0]);
+    src[z] += 64;
+  }
+  for (size_t p = 1;; p++) {
+    for (int r = 1; r < 10; r++)
+      for (int z = 0; z < Z; z++) t[z] = _mm512_aesenc_epi128(t[z], k[r]);
+    if (p == n_pos) break;
+    for (int z = 0; z < Z; z++) {
+      t[z] = _mm512_aesenclast_epi128(t[z], _mm512_xor_si512(k10_0, _mm512_loadu_si512(src[z])));  // see fold_w
+      src[z] += 64;
+    }
+  }
+  for (int z = 0; z < Z; z++) _mm512_storeu_si512(h + 64 * z, _mm512_aesenclast_epi128(t[z], k[10]));
+}
+
 bool have_vaes() {
   static const bool v = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl") &&
                         __builtin_cpu_supports("vaes") && !getenv("GSV_HOST_CHAIN_NO_VAES");
@@ -142,6 +169,26 @@ void host_chain_fold(uint8_t* h, const uint8_t* base, size_t pos_stride, size_t 
     i += 2;
   }
   if (i < n_inst) fold_w<1>(h + 16 * i, base + ib * i, pb, ib, n_pos, rk);
+}
+
+
+void host_chain_fold_quads(uint8_t* h, const uint8_t* base, size_t quad_bytes, size_t n_pos, uint32_t n_quads) {
+  static const RoundKeys rk = make_keys();
+  uint32_t q = 0;
+  if (have_vaes()) {
+    for (; q + 4 <= n_quads; q += 4) fold_quads_vaes<4>(h + 64 * q, base + quad_bytes * q, quad_bytes, n_pos, rk);
+    if (q + 2 <= n_quads) {
+      fold_quads_vaes<2>(h + 64 * q, base + quad_bytes * q, quad_bytes, n_pos, rk);
+      q += 2;
+    }
+    if (q < n_quads) {
+      fold_quads_vaes<1>(h + 64 * q, base + quad_bytes * q, quad_bytes, n_pos, rk);
+      q++;
+    }
+    return;
+  }
+  // AES-NI only: one quad (4 interleaved chains) at a time; rows are 64 bytes apart, chains 16
+  for (; q < n_quads; q++) fold_w<4>(h + 64 * q, base + quad_bytes * q, 64, 16, n_pos, rk);
 }
 
 }  // namespace gsv

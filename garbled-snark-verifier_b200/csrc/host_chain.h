@@ -22,4 +22,10 @@ bool host_chain_available();
 void host_chain_fold(uint8_t* h, const uint8_t* base, size_t pos_stride, size_t inst_stride, size_t n_pos,
                      uint32_t n_inst);
 
+
+// The drain layout of GSV_CT_COMMIT_HOST: `n_quads` quads of chains, quad q's rows at base + q * quad_bytes,
+// row p = the 16-byte blocks of the quad's four chains at stream position p (64 bytes).  h holds
+// 4 * n_quads chain states.  One 512-bit load per quad and step with VAES; 128-bit AES-NI otherwise.
+void host_chain_fold_quads(uint8_t* h, const uint8_t* base, size_t quad_bytes, size_t n_pos, uint32_t n_quads);
+
 }  // namespace gsv

@@ -162,8 +162,16 @@ Task compile_flat(const FlatStream& fs, const std::string& key, const PlanOption
   }
   t.level_off.push_back((uint32_t)t.gates.size());
   t.n_levels = (uint32_t)t.level_off.size() - 1;
-  for (uint32_t l = 0; l < t.n_levels; l++)
-    t.gates[t.level_off[l]].flags |= (uint8_t)((t.level_off[l + 1] - t.level_off[l] - 1) << 1);
+  // level header, carried by the level's first record: width - 1 in flags bits 1-7 and the number of
+  // non-free gates (they come first) in the top byte of ct_off (a task has < 2^24 ciphertexts)
+  if (n_ct >= (1u << 24)) throw std::length_error("task with 2^24 or more ciphertexts: " + key);
+  for (uint32_t l = 0; l < t.n_levels; l++) {
+    uint32_t nf = 0;
+    for (uint32_t k = t.level_off[l]; k < t.level_off[l + 1] && !is_free(t.gates[k].type); k++) nf++;
+    DevGate& h = t.gates[t.level_off[l]];
+    h.flags |= (uint8_t)((t.level_off[l + 1] - t.level_off[l] - 1) << 1);
+    h.ct_off |= nf << 24;
+  }
   t.n_slots = next_slot;
   for (size_t j = 0; j < fs.outputs.size(); j++) {
     uint32_t o = fs.outputs[j];

@@ -33,7 +33,8 @@ struct alignas(16) DevGate {
   uint8_t type;
   uint8_t flags;    // bit0: has ciphertext; bits 1-7 (levelised form, first gate of a level): level width - 1
   uint32_t gid_off; // gate index relative to the call's gid_base (dead gates counted)
-  uint32_t ct_off;  // ciphertext index relative to the call's ct_base
+  uint32_t ct_off;  // bits 0-23: ciphertext index relative to the call's ct_base; bits 24-31 (levelised form,
+                    // first gate of a level): number of non-free gates in the level (they come first)
 };
 static_assert(sizeof(DevGate) == 16, "DevGate must be 16 bytes");
 

@@ -7,8 +7,8 @@
  *
  *   reference interface                                       -> entry point here
  *   -----------------------------------------------------------------------------------------
- *   CircuitContext::{issue_wire,add_gate,with_named_child}     gsv_rec_*        (record topology once)
- *     (src/circuit/circuit_context_trait.rs:12-27)
+ *   CircuitContext::{issue_wire,add_gate,with_named_child}     gsv_ctx_issue_wire / gsv_ctx_add_gate /
+ *     (src/circuit/circuit_context_trait.rs:12-27)               gsv_ctx_component, gsv_program_record
  *   CircuitBuilder::streaming_garbling<H, CTH>                 gsv_garble_batch (GarbleMode hot loop,
  *     (src/circuit/mod.rs:185-208), GarbleMode::evaluate_gate    src/circuit/modes/garble_mode.rs:160-222)
  *   AESAccumulatingHash as CiphertextHandler                   GSV_CT_COMMIT    (src/ciphertext_hasher.rs:23-29)
@@ -37,7 +37,6 @@
 extern "C" {
 #endif
 
-typedef struct gsv_recorder gsv_recorder;
 typedef struct gsv_program gsv_program;
 typedef struct gsv_session gsv_session;
 
@@ -112,8 +111,10 @@ gsv_program* gsv_program_record(const char* name, uint32_t n_inputs, uint32_t n_
  * (src/gadgets/**): "fq12_mul", "fq6_mul", "fq2_mul", "fq_mul", "fq_add", "fq_expr",
  * "gate_zoo", "bn_mul<N>", "fq_inverse", "fq_sqrt", "fq2_sqrt", "g1_add", "g1_msm1", "fq12_square",
  * "fq12_cyclotomic_square", "fq12_inverse", "fq12_frobenius<i>", "final_exponentiation",
- * "miller_loop_groth16", and "groth16_verify_compressed" (src/gadgets/groth16.rs:250-268 with one
- * public input over the deterministic synthetic verifying key of gsv_groth16_synthetic_inputs). */
+ * "miller_loop_groth16", "groth16_verify_compressed" (src/gadgets/groth16.rs:250-268) and "groth16_verify"
+ * (src/gadgets/groth16.rs:57-110 on uncompressed points, 2 286 inputs, what examples/groth16_garble.rs
+ * garbles), both with one public input over the deterministic synthetic verifying key of
+ * gsv_groth16_synthetic_inputs. */
 gsv_program* gsv_program_build(const char* circuit, const gsv_plan_options* opt);
 
 /* ExecuteMode (src/circuit/modes/execute_mode.rs): plain boolean evaluation of the recorded
@@ -134,9 +135,10 @@ int gsv_program_depth(const gsv_program* p, uint64_t* depth_all, uint64_t* depth
 int gsv_program_execute_plan(const gsv_program* p, int lane_form, const uint8_t* input_bits,
                              uint8_t* output_bits);
 
-/* Input bits (EncodeInput order, 1273 wires: public | a.x a.flag | b.x.c0 b.x.c1 b.flag | c.x c.flag,
- * src/gadgets/groth16.rs:425-490) of a synthetic proof for "groth16_verify_compressed":
- * the proof verifies for `public_x`; pass flip_public = 1 to get the rejecting variant. */
+/* Input bits (EncodeInput order) of a synthetic proof: n_bits = 1273 for "groth16_verify_compressed"
+ * (public | a.x a.flag | b.x.c0 b.x.c1 b.flag | c.x c.flag, src/garbled_groth16.rs:433-494) or 2286 for
+ * "groth16_verify" (public | a.x a.y | b.x b.y | c.x c.y, src/garbled_groth16.rs:141-176).
+ * The proof verifies for `public_x`; pass flip_public = 1 to get the rejecting variant. */
 int gsv_groth16_synthetic_inputs(uint64_t public_x, int flip_public, uint8_t* bits, uint32_t n_bits);
 void gsv_program_destroy(gsv_program* p);
 
@@ -175,11 +177,16 @@ typedef struct {
   int device;             /* CUDA device ordinal */
   uint32_t n_instances;   /* batch size B (cut-and-choose instances on this GPU) */
   uint32_t group;         /* instances per work item: 1,2,4,8; 0 = auto */
-  uint32_t worker_threads;/* threads per worker: 128/256/512; 0 = auto */
+  uint32_t worker_threads;/* threads per worker: 64/128/256/512/1024; 0 = auto (256) */
   uint32_t ct_mode;       /* enum gsv_ct_mode */
   uint32_t ct_ring_log2;  /* GSV_CT_COMMIT: cap the ciphertext ring at 2^n entries per instance; 0 = auto */
   uint32_t exec_mode;     /* 0 = auto, 1 = levelised (labels in shared memory, small batches),
                              2 = lane (one warp = 32 instances, emission order; large batches) */
+  uint32_t sm_limit;      /* 0 = every SM; otherwise the persistent grid takes this many SMs, so that several
+                             sessions (software-pipelined cut-and-choose batches) share one GPU spatially */
+  uint64_t ct_buffer_bytes; /* 0 = auto (85 % of the free HBM); otherwise an upper bound for the ciphertext ring */
+  uint32_t host_threads;  /* GSV_CT_COMMIT_HOST: host fold threads of this session; 0 = auto (half the hardware
+                             threads, at most one per four instances) */
   uint32_t reserved;
 } gsv_session_options;
 
@@ -225,6 +232,12 @@ int gsv_program_export_templates(const gsv_program* p, uint64_t sizes[6], uint32
 int gsv_host_chain_fold(uint8_t* h, const uint8_t* base, uint64_t pos_stride, uint64_t inst_stride,
                         uint64_t n_pos, uint32_t n_inst);
 
+/* The same fold over the drain layout of GSV_CT_COMMIT_HOST: n_quads quads of chains, quad q's rows at
+ * base + q * quad_bytes, row p = the four chains' 16-byte blocks at stream position p (64 bytes); h holds
+ * 4 * n_quads states.  One 512-bit load per quad and step on VAES hosts. */
+int gsv_host_chain_fold_quads(uint8_t* h, const uint8_t* base, uint64_t quad_bytes, uint64_t n_pos,
+                              uint32_t n_quads);
+
 /* streaming_garbling for B instances: instance i uses seeds[i] (garble_mode.rs:80-97). */
 int gsv_garble_batch(gsv_session* s, int hasher, const uint64_t* seeds, gsv_garble_result* res);
 
@@ -267,6 +280,9 @@ int gsv_commit_labels(int device, const uint8_t* labels, uint64_t n, uint8_t* ou
 int gsv_hash_blocks(int device, int hasher, const uint8_t* x, const uint64_t* gid, uint64_t n,
                     uint8_t* out);
 int gsv_bench_hash(int device, int hasher, uint64_t n_blocks, int iters, double* blocks_per_s);
+/* Dependent-hash latency: every thread of `warps_per_sm` warps on each SM chains n gate hashes; returns SM
+ * cycles per hash (the least one barrier-separated level of dependent non-free gates can cost). */
+int gsv_bench_hash_latency(int device, int hasher, uint32_t warps_per_sm, uint64_t n, double* cycles_per_hash);
 
 #ifdef __cplusplus
 }

@@ -110,3 +110,12 @@ def test_host_chain_fold_matches_cbc_mac(gsv):
             enc = Cipher(algorithms.AES(bytes([0x42]) * 16), modes.CBC(bytes(16))).encryptor()
             want = enc.update(blocks[:, i, :].tobytes())[-16:]
             assert bytes(h[i]) == want
+    # the drain layout of the device ring: [quad][position][4 chains][16 bytes]
+    for n_quads in (1, 2, 3, 4, 7):
+        rows = rng.integers(0, 256, (n_quads, 41, 4, 16), dtype=np.uint8)
+        h = gsv.host_chain_fold_quads(np.zeros((4 * n_quads, 16), np.uint8), rows[:, :17])
+        h = gsv.host_chain_fold_quads(h, rows[:, 17:])
+        for q in range(n_quads):
+            for j in range(4):
+                enc = Cipher(algorithms.AES(bytes([0x42]) * 16), modes.CBC(bytes(16))).encryptor()
+                assert bytes(h[4 * q + j]) == enc.update(rows[q, :, j, :].tobytes())[-16:]
