@@ -1,30 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- garbled gates/s of the B200 engine on the Groth16 verifier circuit.
 
-A "step" garbles one batch of B cut-and-choose instances of the workload circuit per GPU from
-seeds (seed expansion -> garbling -> bit-exact ciphertext chain commitment), i.e. the first
-garbling stage of the reference's cut-and-choose (src/cut_and_choose/garbler.rs:191-242) with
-`AesNiHasher` + `AESAccumulatingHash`.
+A "step" garbles one cut-and-choose batch of the workload circuit on every GPU from seeds (seed expansion
+-> garbling -> bit-exact ciphertext chain commitment), i.e. the garbling stage of the reference's
+cut-and-choose (src/cut_and_choose/garbler.rs:191-242) with `AesNiHasher` + `AESAccumulatingHash`; seeds
+are the reference's: consecutive u64 draws of ChaCha20Rng::seed_from_u64(1234) (garbler.rs:201-203).
 
 Workloads (--workload):
-  verifier (default) : groth16_verify_compressed (11.46 G gates, 2.98 G ciphertexts; BASELINE.json
-          configs 2/4) x 32 instances per GPU, levelised kernel (4 instances per worker), commitment in GSV_CT_COMMIT_HOST mode:
-          every gate hash on the GPU, the strictly serial AES chain folded by host AES-NI threads that
-          drain the ciphertext ring while the kernel runs (a GPU folds one dependent AES per 0.46 us:
-          23 min for 2.98 G ciphertexts, whatever the batch).
-  batch   : fq12_mul (20.3 M gates) x 6144 instances per GPU, lane kernel, commitment fused on the GPU
+  verifier (default): groth16_verify_compressed (11.46 G gates, 2.98 G ciphertexts; BASELINE.json configs
+          2 / 4) x 16 instances per step and GPU, levelised kernel, commitment in GSV_CT_COMMIT_HOST mode: every
+          gate hash on the GPU, the strictly serial AES chain folded by host AES-NI threads that drain the
+          ciphertext ring over PCIe while the kernel runs.  One chain advances one block per ~13 ns whatever
+          the hardware, i.e. >= 39 s per instance, so steps are SOFTWARE-PIPELINED: `--sessions` (3) steps are in
+          flight per GPU, each on its own slice of the SMs and of the HBM ring, so that ~48 chains keep the
+          PCIe link and the fold threads busy while no step waits for another.
+  batch : fq12_mul (20.3 M gates) x 6144 instances per step, lane kernel, commitment fused on the GPU
           (GSV_CT_COMMIT): the large-batch regime where thousands of chains run side by side.
 
-  value : whole-job gates/s over the device time of the step (CUDA events inside the library, on its
-          stream), seeds already resident in HBM being the only input.
-  e2e   : same metric over the wall time of the public API call with HOST buffers (seeds H2D; commitments,
-          input / output labels D2H; in the verifier workload also the ciphertext drain and the host
-          fold, which end a few seconds after the kernel) -- the headline.
-  --impl reference : the CPU oracle (AES-NI restatement of the reference's per-gate loop; the
-          reference itself is Rust and cannot be built in this image) on all host cores.
+  value : whole-job gates/s over the device-side span of the K steps (CUDA events around the region; the
+          only input, the seeds, is 8 bytes per instance).
+  e2e   : the same over the wall time of the public API calls with HOST buffers: seeds H2D; commitments and
+          input / output labels D2H; in the verifier workload also the ciphertext drain and the host fold.
+  --impl reference : the reference's CPU path restated (oracle, AES-NI) on all host cores over bounded
+          windows of the same circuit; loads neither libgsv_cuda.so nor torch.
 
-Launch: `python bench.py --gpus 1`, or under torchrun for N > 1 (one rank per GPU, instances
-sharded across ranks, NCCL used only to all-gather the per-instance commitments).
+Launch: `python bench.py --gpus 1`, or under torchrun for N > 1 (one rank per GPU, instances sharded
+across ranks, NCCL used only to all-gather the per-instance commitments).
 """
 import argparse
 import json
@@ -39,6 +40,8 @@ sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_GATE = 52.3   # 48 B free gate, 64 B non-free, 73.2/26.8 mix
 AES_BLOCKS_PER_GATE_GARBLE = 2.0  # per NON-FREE gate; + 1 chain block when committing
+PCIE_D2H_GBS = 57.2          # measured on this pool (profiles/r02_probe.md): pinned D2H, 1 GiB copies
+SM_RESERVE = 4               # SMs left free of persistent CTAs (NCCL / utility kernels must always fit)
 
 
 def measured_peaks():
@@ -49,6 +52,21 @@ def measured_peaks():
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_cpus():
+    """(logical CPUs this process may use, physical cores of the host)."""
+    try:
+        logical = len(os.sched_getaffinity(0))
+    except Exception:
+        logical = os.cpu_count() or 1
+    physical = None
+    try:
+        import psutil
+        physical = psutil.cpu_count(logical=False)
+    except Exception:
+        pass
+    return logical, physical or logical
 
 
 class ClockSampler:
@@ -65,7 +83,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "500"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -95,76 +113,117 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-VERIFIER_SAMPLE_GATES = 600_000_000   # per core and step: the first 5 % of the verifier's emission order
+# ------------------------------------------------------------------------------------------- CPU arm
+WINDOW_GATES = 100_000_000   # gates per sampled window, per thread and step
 
 
-def cpu_garble_rate(circuit, n_instances_per_core, cores, hasher=0, prog=None):
-    """Oracle (CPU restatement, AES-NI when the host has it) on `cores` threads, one instance
-    at a time per core like the reference's pinned rayon pool (cut_and_choose/mod.rs:131-186).
-    Circuits that fit memory as a flat stream run `n_instances_per_core` whole instances per core; the
-    Groth16 verifier is walked over its template DAG and each core garbles the first
-    VERIFIER_SAMPLE_GATES gates of its own instance (a bounded sample of the same workload)."""
-    import gsv_b200 as g
-    from oracle import oracle as o
+class CpuSampler:
+    """The reference's per-gate loop restated (oracle/, AES-NI when the host has it) over BOUNDED WINDOWS of
+    the workload circuit, one instance per thread like the reference's rayon pool pinned to cores
+    (src/cut_and_choose/mod.rs:131-186).  The verifier is walked as its template DAG; each thread garbles
+    the first WINDOW_GATES gates of every major stage (G1 / G2 decompression, MSM, Miller loop, final
+    exponentiation -- the root's children above 100 M gates) with commitment, and the stage rates are
+    combined with the stages' true gate counts: rate = total gates / sum_i (gates_i / rate_i).
+    Loads only oracle/libgsv_oracle.so and oracle/libgsv_circuitgen.so (host-only gadget generator)."""
 
-    if circuit == "groth16_verify_compressed":
-        prog = prog or g.Program(circuit, lane_only=True)
-        dag = o.TemplateDag(*prog.export_templates())
-        done = [0] * cores
+    def __init__(self, circuit):
+        from oracle import oracle as o
+        self.o = o
+        t = time.perf_counter()
+        self.gen = o.CircuitGen(circuit)
+        self.record_s = time.perf_counter() - t
+        self.n_gates = self.gen.n_gates
+        kids = self.gen.children()
+        big = [k for k in kids if int(self.gen.total_gates[k]) >= WINDOW_GATES]
+        if self.n_gates <= 4 * WINDOW_GATES or not big:
+            self.windows = [(self.gen.root, self.n_gates, self.n_gates)]       # whole circuit per sample
+        else:
+            merged = {}
+            for k in big:                                                      # same template twice = same stage
+                merged[k] = merged.get(k, 0) + int(self.gen.total_gates[k])
+            covered = sum(merged.values())
+            scale = self.n_gates / covered                                     # small children ride along pro rata
+            self.windows = [(k, g * scale, min(WINDOW_GATES, int(self.gen.total_gates[k]))) for k, g in merged.items()]
+        self.dags = {k: self.gen.dag(k) for k, _, _ in self.windows}
+        self.aesni = o.have_aesni()
+
+    def describe(self):
+        if len(self.windows) == 1:
+            return f"whole {self.gen.circuit} instances"
+        return (f"{len(self.windows)} windows of {WINDOW_GATES / 1e6:.0f} M gates (the start of each verifier stage: "
+                f"G1 / G2 decompression, MSM, Miller loop, final exponentiation), stage rates weighted by the stages' gate counts")
+
+    def step(self, threads, hasher=0, seed0=0):
+        """One bounded sample on `threads` threads.  Returns (aggregate gates/s, seconds)."""
+        est = [0.0] * threads
 
         def work(k):
-            done[k] = dag.garble(hasher, 1000 * k, max_gates=VERIFIER_SAMPLE_GATES)["n_gates"]  # ctypes releases the GIL
-        sample = f"first {VERIFIER_SAMPLE_GATES / 1e6:.0f} M gates of one {circuit} instance per core"
-    else:
-        prog = prog or g.Program(circuit)
-        t, a, b, c, outs, nw = prog.flat_stream()
-        st = o.Stream(t, a, b, c, outs, nw, prog.n_inputs).compact()  # slab-sized live set, cache resident
-        done = [prog.n_gates * n_instances_per_core] * cores
+            t_inst = 0.0
+            for (tmpl, weight_gates, limit) in self.windows:
+                t = time.perf_counter()
+                whole = limit >= int(self.gen.total_gates[tmpl])
+                r = self.dags[tmpl].garble(hasher, seed0 + 1000 * k, max_gates=0 if whole else limit)  # ctypes releases the GIL
+                dt = time.perf_counter() - t
+                t_inst += weight_gates * dt / max(r["n_gates"], 1)
+            est[k] = self.n_gates / t_inst
 
-        def work(k):
-            for j in range(n_instances_per_core):
-                st.garble(hasher, 1000 * k + j, want_ct=False)
-        sample = f"{n_instances_per_core} instance(s) of {circuit} per core"
+        th = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
+        t0 = time.perf_counter()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return sum(est), time.perf_counter() - t0
 
-    th = [threading.Thread(target=work, args=(k,)) for k in range(cores)]
-    t0 = time.perf_counter()
-    for x in th:
-        x.start()
-    for x in th:
-        x.join()
-    dt = time.perf_counter() - t0
-    return sum(done) / dt, dt, prog, o.have_aesni(), sample
+
+def loaded_repo_libs():
+    """Shared objects of this repository mapped into the process (the reference arm must not hold the engine)."""
+    libs = set()
+    try:
+        with open("/proc/self/maps") as f:
+            for ln in f:
+                path = ln.split()[-1]
+                if path.startswith(ROOT) and ".so" in path:
+                    libs.add(os.path.relpath(path, ROOT))
+    except Exception:
+        pass
+    return sorted(libs)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    logical, physical = host_cpus()
+    sampler = CpuSampler(args.circuit)
     rates = []
-    per_core = max(1, args.ref_instances_per_core)
     for i in range(args.warmup + args.steps):
-        rate, dt, prog, aesni, what = cpu_garble_rate(args.cpu_circuit, per_core, cores)
+        rate, dt = sampler.step(logical, seed0=i)
         if i >= args.warmup:
             rates.append((rate, dt))
     value = sum(r for r, _ in rates) / len(rates)
     ms = 1e3 * sum(d for _, d in rates) / len(rates)
-    sample = (f"{what} on {cores} threads per step, garble + chain "
-              f"commitment, {'AES-NI' if aesni else 'portable AES'}; oracle omits the reference's slab/credit "
-              f"bookkeeping (upper bound on the reference's CPU speed)")
+    sample = (f"{sampler.describe()}, one instance per thread on {logical} threads ({physical} physical cores) per step, "
+              f"garble + chain commitment, {'AES-NI' if sampler.aesni else 'portable AES'}; the oracle omits the reference's "
+              f"slab / credit bookkeeping (upper bound on the reference's CPU speed)")
     line = {
         "impl": "reference", "metric": "garbled_gates_per_s", "value": value, "unit": "gates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{args.circuit} garble+commit, AES hasher (CPU oracle; bounded sample: {what}, "
-                               f"independent per core)",
-                   "gates_per_instance": prog.n_gates},
-        "cpu_baseline": {"value": value, "unit": "gates/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": f"{args.circuit} garble + chain commitment, AES hasher, CPU oracle on all host threads "
+                               f"(bounded sample per step: {sampler.describe()})",
+                   "gates_per_instance": sampler.n_gates, "record_s": round(sampler.record_s, 1),
+                   "same_config_note": "same circuit, hasher and commitment as the GPU arm; each step is a bounded sample "
+                                       "instead of whole instances (a whole instance takes ~270 s per core)"},
+        "cpu_baseline": {"value": value, "unit": "gates/s", "cores": physical, "threads": logical, "kind": "port",
+                         "sample": sample},
         "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "native_libs": loaded_repo_libs(),
     }
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -173,28 +232,29 @@ def main():
     ap.add_argument("--impl", default="gsv", choices=["gsv", "reference"])
     ap.add_argument("--workload", default="verifier", choices=["verifier", "batch"])
     ap.add_argument("--circuit", default=None, help="override the workload's circuit")
-    ap.add_argument("--instances", type=int, default=None, help="cut-and-choose instances per GPU")
+    ap.add_argument("--instances", type=int, default=None, help="cut-and-choose instances per step and GPU")
+    ap.add_argument("--sessions", type=int, default=None, help="steps in flight per GPU (software pipelining)")
     ap.add_argument("--exec-mode", type=int, default=None, help="0 auto, 1 levelised, 2 lane")
     ap.add_argument("--group", type=int, default=None)
     ap.add_argument("--ct-mode", default=None, choices=["commit", "commit_host", "none"])
     ap.add_argument("--worker-threads", type=int, default=0)
+    ap.add_argument("--host-threads", type=int, default=0, help="fold threads per session (0: from the rank's CPU share)")
     ap.add_argument("--hasher", default="aes", choices=["aes", "blake3"])
     ap.add_argument("--no-commit", action="store_true", help="drop ciphertexts (the `()` handler)")
-    ap.add_argument("--ref-instances-per-core", type=int, default=8)
-    ap.add_argument("--cpu-baseline-instances", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-unthrottled", action="store_true", help="skip the extra no-commitment kernel step")
+    ap.add_argument("--extras", action="store_true",
+                    help="after the timed region (N = 1): the same kernel with ciphertexts dropped on the whole GPU")
     args = ap.parse_args()
     # workload presets (explicit flags win)
-    preset = {"verifier": dict(circuit="groth16_verify_compressed", instances=32, exec_mode=1, group=4,
-                               ct_mode="commit_host", steps=1),
-              "batch": dict(circuit="fq12_mul", instances=6144, exec_mode=2, group=0, ct_mode="commit", steps=3)}[args.workload]
+    preset = {"verifier": dict(circuit="groth16_verify_compressed", instances=16, sessions=3, exec_mode=1, group=4,
+                               ct_mode="commit_host", steps=6),
+              "batch": dict(circuit="fq12_mul", instances=6144, sessions=1, exec_mode=2, group=0, ct_mode="commit",
+                            steps=3)}[args.workload]
     for k, v in preset.items():
         if getattr(args, k) is None:
             setattr(args, k, v)
     if args.no_commit:
         args.ct_mode = "none"
-    args.cpu_circuit = args.circuit
 
     if args.impl == "reference":
         run_reference(args)
@@ -205,10 +265,12 @@ def main():
     import torch.distributed as dist
 
     import gsv_b200 as g
+    from gsv_b200 import cut_and_choose as cc
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
@@ -220,21 +282,36 @@ def main():
     t_plan = time.perf_counter()
     prog = g.Program(args.circuit)
     t_plan = time.perf_counter() - t_plan
-    B = args.instances
-    sess = g.Session(prog, B, device=local, group=args.group, worker_threads=args.worker_threads, ct_mode=ct_mode,
-                     exec_mode=args.exec_mode)
+    B, S = args.instances, max(1, args.sessions)
     lane = args.exec_mode == 2 or (args.exec_mode == 0 and args.group == 0 and B >= 128)
     kernel_name = "k_lane" if lane else "k_engine"
+
+    # ---- host threads: every rank gets an equal share of the host's CPUs; inside a rank each session has one
+    # drain thread (mostly asleep) and `fold_threads` AES-NI fold threads
+    logical, physical = host_cpus()
+    cpu_share = max(1, logical // max(1, local_world))
+    fold_threads = args.host_threads or max(1, min((B + 3) // 4, max(1, cpu_share - 1) // S))
+    sm_total = torch.cuda.get_device_properties(local).multi_processor_count
+    sm_limit = 0 if S == 1 else (sm_total - SM_RESERVE) // S
+    free_b, _ = torch.cuda.mem_get_info()
+    sessions = []
+    for k in range(S):
+        sessions.append(g.Session(prog, B, device=local, group=args.group, worker_threads=args.worker_threads,
+                                  ct_mode=ct_mode, exec_mode=args.exec_mode, sm_limit=sm_limit,
+                                  ct_buffer_bytes=0 if S == 1 else int(free_b * 0.80 / S), host_threads=fold_threads))
     commit_txt = {"none": "no commitment (ciphertexts dropped)",
                   "commit": "bit-exact AES chain commitment fused into the kernel (chain CTAs)",
                   "commit_host": "bit-exact AES chain commitment, gate hashes on the GPU, serial chain folded by "
                                  "host AES-NI threads draining the ciphertext ring during the kernel"}[args.ct_mode]
-    # cut-and-choose seeds: instance i of rank r (garbler.rs:201-203 draws them from one RNG;
-    # here a fixed arithmetic pattern so every rank/step is reproducible)
+
+    # cut-and-choose seeds (garbler.rs:201-203): consecutive u64 draws of ChaCha20Rng::seed_from_u64(1234);
+    # step i of rank r takes draws [(i * world + r) * B, +B)
+    n_steps_all = args.warmup + args.steps
+    all_seeds = np.asarray(cc.instance_seeds(1234, n_steps_all * world * B), dtype=np.uint64)
+
     def seeds_for(step):
-        base = np.uint64(0x9E3779B97F4A7C15)
-        idx = np.arange(B, dtype=np.uint64) + np.uint64((rank * 1_000_003 + step) * B)
-        return idx * base + np.uint64(12345)
+        o = (step * world + rank) * B
+        return all_seeds[o:o + B]
 
     def barrier():
         torch.cuda.synchronize()
@@ -245,44 +322,75 @@ def main():
     commits_dev = torch.empty((B, 16), dtype=torch.uint8, device="cuda")
     gathered = torch.empty((world * B, 16), dtype=torch.uint8, device="cuda") if world > 1 else None
 
-    def step(i, want_labels):
-        t1 = time.perf_counter()
-        res = sess.garble(seeds_for(i), hasher, want_inputs=want_labels, want_outputs=want_labels)
-        res.wall_ms = 1e3 * (time.perf_counter() - t1)
-        if world > 1:
-            # the only collective of the path: gather the per-instance commitments
-            commits_dev.copy_(torch.from_numpy(res.ct_commit))
-            dist.all_gather_into_tensor(gathered, commits_dev)
-        return res
+    def run_steps(first, count):
+        """Steps [first, first + count): step i runs on session i % S; the S sessions run concurrently, each from
+        its own host thread (the library call blocks until the step's commitments are final).  The commitments
+        are all-gathered in step order by this thread."""
+        results = [None] * count
+        done = [threading.Event() for _ in range(count)]
+        errors = []
 
-    for i in range(args.warmup):
-        step(i, True)
+        def drive(k):
+            try:
+                torch.cuda.set_device(local)
+                for j in range(k, count, S):
+                    t1 = time.perf_counter()
+                    res = sessions[k].garble(seeds_for(first + j), hasher, want_inputs=True, want_outputs=True)
+                    res.wall_ms = 1e3 * (time.perf_counter() - t1)
+                    results[j] = res
+                    done[j].set()
+            except Exception as e:  # pragma: no cover
+                errors.append(e)
+                for ev in done:
+                    ev.set()
+
+        th = [threading.Thread(target=drive, args=(k,)) for k in range(min(S, count))]
+        for x in th:
+            x.start()
+        for j in range(count):
+            done[j].wait()
+            if errors:
+                break
+            if world > 1:
+                # the only collective of the path: gather the per-instance commitments (SURVEY.md section 8e)
+                commits_dev.copy_(torch.from_numpy(results[j].ct_commit))
+                dist.all_gather_into_tensor(gathered, commits_dev)
+        for x in th:
+            x.join()
+        if errors:
+            raise errors[0]
+        return results
+
+    if args.warmup:
+        run_steps(0, args.warmup)
 
     sampler = ClockSampler(local)
     sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    ev0.record()
     t0 = time.perf_counter()
-    dev_ms = garble_ms = commit_ms = seed_ms = 0.0
-    launches = 0
-    for i in range(args.steps):
-        res = step(args.warmup + i, True)
-        dev_ms += res.ms_total
-        garble_ms += res.ms_garble
-        commit_ms += res.ms_commit
-        seed_ms += res.ms_seed
-        launches += res.n_launches
+    results = run_steps(args.warmup, args.steps)
+    ev1.record()
     barrier()
     wall = time.perf_counter() - t0
+    span_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
 
-    # max over ranks, on-device time for `value`, wall (incl. copies) for e2e
-    tt = torch.tensor([dev_ms, wall * 1e3, garble_ms], dtype=torch.float64, device="cuda")
+    garble_ms = sum(r.ms_garble for r in results)
+    commit_ms = sum(r.ms_commit for r in results)
+    seed_ms = sum(r.ms_seed for r in results)
+    step_ms = sum(r.ms_total for r in results)
+    launches = sum(r.n_launches for r in results)
+
+    # max over ranks: the CUDA-event span for `value`, the wall time (incl. every copy) for e2e
+    tt = torch.tensor([span_ms, wall * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_ms_max, wall_ms_max, garble_ms_max = [float(x) for x in tt.tolist()]
+    span_ms_max, wall_ms_max = [float(x) for x in tt.tolist()]
 
     gates_per_step = prog.n_gates * B * world
-    value = gates_per_step * args.steps / (dev_ms_max * 1e-3)
+    value = gates_per_step * args.steps / (span_ms_max * 1e-3)
     e2e = gates_per_step * args.steps / (wall_ms_max * 1e-3)
     h2d = 8 * B
     d2h = B * 16 * (4 + prog.n_inputs + prog.n_outputs)
@@ -291,99 +399,106 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        # dominant kernel = the persistent engine kernel (garbling + fused chain commitment); its
-        # per-launch device time comes from CUDA events recorded by the library on its own stream
-        k_ms = garble_ms / args.steps
-        k_gates = prog.n_gates * B
-        achieved = k_gates * ALGO_BYTES_PER_GATE / (k_ms * 1e-3) / 1e9
+        # dominant kernel = the persistent engine kernel (garbling; in `commit` mode also the fused chain).  Its
+        # launch durations come from CUDA events recorded by the library on the launching stream.  With S steps in
+        # flight S launches run side by side on disjoint SM slices: the GPU's algorithmic rate is the sum.
+        k_ms = garble_ms / args.steps                      # average duration of one launch
+        conc = min(S, args.steps)
+        k_gates = prog.n_gates * B                         # gates one launch processes
+        per_launch = k_gates * ALGO_BYTES_PER_GATE / (k_ms * 1e-3) / 1e9
+        busy = garble_ms / (span_ms * max(conc, 1))        # share of the span a session's kernel is running
+        achieved = per_launch * conc * min(1.0, busy)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "kernel": kernel_name, "kernel_ms": k_ms, "peak_source": peak_src,
-                    "algorithmic_bytes_per_gate": ALGO_BYTES_PER_GATE}
+                    "algorithmic_bytes_per_gate": ALGO_BYTES_PER_GATE,
+                    "concurrent_launches": conc, "sms_per_launch": sm_limit or sm_total,
+                    "per_launch": {"achieved": per_launch, "frac": per_launch / peak},
+                    "note": "achieved = algorithmic bytes of one launch / its average duration x the launches running side by side "
+                            "(software-pipelined steps on disjoint SM slices); per_launch is the single-launch figure"}
         if prog.critical_path_levels and not lane:
-            # what actually bounds the levelised kernel at this batch size: the circuit's dependency chain
             roofline["latency_floor"] = {
                 "critical_path_levels": prog.critical_path_levels,
                 "us_per_level_at_measured_time": 1e3 * k_ms / prog.critical_path_levels,
-                "note": "one barrier-separated level = a dependent fixed-key AES through shared-memory tables; "
-                        "kernel time / critical-path levels is the per-level latency if nothing else limited the run"}
+                "note": "kernel time / critical-path levels: the per-level latency if nothing else paced the run "
+                        "(in commit_host mode the ring back-pressure of the drain / fold does)"}
         if args.ct_mode == "commit_host":
-            roofline["gpu_chain_floor_s"] = prog.n_ciphertexts * 0.46e-6  # measured dependent-AES step, profiles/r01_chain_poll.md
+            wave_s = (wall / args.steps) * conc            # time one step is in flight
+            drain_gbs = d2h * args.steps / wall / 1e9
+            fold_floor_s = prog.n_ciphertexts * 13e-9      # one dependent AES-NI block per ~13 ns (10 aesenc)
+            pcie_util = drain_gbs / PCIE_D2H_GBS
+            fold_util = fold_floor_s / wave_s
+            limiter = "pcie_drain" if pcie_util >= 0.85 and pcie_util >= fold_util else ("host_fold" if fold_util >= 0.85 else "kernel")
+            roofline["gpu_chain_floor_s"] = prog.n_ciphertexts * 0.46e-6  # measured dependent-AES step on the GPU
+            roofline["pipeline"] = {
+                "limiter": limiter, "steps_in_flight": conc, "step_in_flight_s": wave_s,
+                "d2h_drain_GBps": drain_gbs, "pcie_d2h_peak_GBps": PCIE_D2H_GBS, "pcie_util": pcie_util,
+                "host_chain_floor_s": fold_floor_s, "fold_util": fold_util,
+                "host_threads_per_rank": S * (fold_threads + 1), "fold_threads_per_session": fold_threads,
+                "host_logical_cpus": logical, "host_physical_cores": physical, "ranks_on_host": local_world,
+                "note": "limiter: pcie_drain when the ciphertext drain runs at >= 85 % of the measured pinned D2H rate; host_fold "
+                        "when a step is in flight for about as long as one AES-NI chain needs (n_ct x 13 ns); else the kernel"}
         try:
             blocks = g.bench_hash(hasher, 1 << 28, 2, device=local)
             nonfree = sum(prog.type_count[:8]) / prog.n_gates
-            need = nonfree * (AES_BLOCKS_PER_GATE_GARBLE + (1.0 if args.ct_mode == "commit" else 0.0)) * k_gates / (k_ms * 1e-3)
+            need = nonfree * (AES_BLOCKS_PER_GATE_GARBLE + (1.0 if args.ct_mode == "commit" else 0.0)) * gates_per_step / world * args.steps / (span_ms * 1e-3)
             roofline["alu"] = {"hash_blocks_per_s_peak": blocks, "hash_blocks_per_s_achieved": need,
-                               "frac": need / blocks, "note": "register-resident 2-block gate-hash micro-kernel"}
+                               "frac": need / blocks,
+                               "note": "register-resident 2-block gate-hash micro-kernel; T-table AES is bound by the "
+                                       "shared-memory pipe (160 lookups per block, one 32-lane wavefront per SM clock)"}
         except Exception as e:  # pragma: no cover
             roofline["alu"] = {"error": str(e)}
         line = {
             "metric": "garbled_gates_per_s", "value": value, "unit": "gates/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": span_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {
-                "workload": f"{args.circuit} x {B} cut-and-choose instances per GPU, garble + {commit_txt}, "
-                            f"{args.hasher} gate hasher"
+                "workload": f"{args.circuit} x {B} cut-and-choose instances per step and GPU ({S} steps in flight per GPU), "
+                            f"garble + {commit_txt}, {args.hasher} gate hasher"
                             + (" (BASELINE.json configs 2/4: Groth16 verifier, 1 public input, synthetic vk; "
                                "11.46 G gates here vs the reference's 11.17 G for its own vk)"
                                if args.circuit == "groth16_verify_compressed" else ""),
                 "kernel": kernel_name, "plan_s": round(t_plan, 1),
                 "gates_per_instance": prog.n_gates, "ciphertexts_per_instance": prog.n_ciphertexts,
-                "instances_per_gpu": B, "l2": "inputs larger than L2 (label + ciphertext state >> 126 MB)",
+                "instances_per_step": B, "steps_in_flight": S, "instances_in_flight_per_gpu": B * min(S, args.steps),
+                "seeds": "ChaCha20Rng::seed_from_u64(1234) u64 draws (garbler.rs:201-203)",
+                "l2": "inputs larger than L2 (label + ciphertext state >> 126 MB)",
                 "parallelism": f"instances sharded over {world} GPU(s); NCCL all-gather of commitments only",
             },
-            "phases_ms_per_step": {"seed_expand": seed_ms / args.steps, "garble": garble_ms / args.steps,
-                                   "commit_tail_after_kernel": commit_ms / args.steps},
+            "phases_ms_per_step": {"seed_expand": seed_ms / args.steps, "garble_kernel": garble_ms / args.steps,
+                                   "commit_tail_after_kernel": commit_ms / args.steps, "step_in_flight": step_ms / args.steps},
             "e2e": {"value": e2e, "unit": "gates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,
         }
-        if world == 1 and args.ct_mode == "commit_host" and not args.no_unthrottled:
-            # The committed step is paced by the host fold (one dependent AES-NI chain per instance) through
-            # ring back-pressure, so its kernel time understates the kernel.  One extra, untimed-for-`value`
-            # step with the ciphertexts dropped shows the garbling kernel on its own.
+        for s in sessions:
+            s.close()
+        sessions.clear()
+        if world == 1 and args.extras and not lane:
+            # the same kernel, ciphertexts dropped, whole GPU: not paced by the host fold / PCIe drain
             try:
-                sess.close()
-                s2 = g.Session(prog, B, device=local, group=args.group, worker_threads=args.worker_threads,
+                s2 = g.Session(prog, 2 * B, device=local, group=args.group, worker_threads=args.worker_threads,
                                ct_mode=g.CT_NONE, exec_mode=args.exec_mode)
-                r2 = s2.garble(seeds_for(10_000), hasher, want_inputs=False, want_outputs=False)
+                r2 = s2.garble(all_seeds[:2 * B], hasher, want_inputs=False, want_outputs=False)
                 s2.close()
-                rate2 = prog.n_gates * B / (r2.ms_garble * 1e-3)
+                rate2 = prog.n_gates * 2 * B / (r2.ms_garble * 1e-3)
                 roofline["kernel_without_commitment"] = {
-                    "kernel_ms": r2.ms_garble, "gates_per_s": rate2,
+                    "instances": 2 * B, "kernel_ms": r2.ms_garble, "gates_per_s": rate2,
                     "achieved_GBps": rate2 * ALGO_BYTES_PER_GATE / 1e9, "frac": rate2 * ALGO_BYTES_PER_GATE / 1e9 / peak,
-                    "us_per_critical_level": 1e3 * r2.ms_garble / max(prog.critical_path_levels, 1),
-                    "note": "same kernel, ciphertexts dropped: not paced by the host fold / PCIe drain"}
+                    "us_per_critical_level": 1e3 * r2.ms_garble / max(prog.critical_path_levels, 1)}
             except Exception as e:  # pragma: no cover
                 roofline["kernel_without_commitment"] = {"error": str(e)}
-        if world == 1 and args.workload == "verifier" and args.ct_mode == "commit_host" and not args.no_unthrottled:
-            # The all-GPU counterpart in the same run: the large-batch regime (Fq12 mul x 6144 instances, lane
-            # kernel, chain commitment fused on the GPU), 1 warm-up + 2 timed steps.  Not part of `value`.
-            try:
-                p2 = g.Program("fq12_mul")
-                s3 = g.Session(p2, 6144, device=local, ct_mode=g.CT_COMMIT, exec_mode=2)
-                sd = lambda i: (np.arange(6144, dtype=np.uint64) + np.uint64(i * 6144)) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(7)
-                s3.garble(sd(0), hasher, want_inputs=False, want_outputs=False)
-                ms = [s3.garble(sd(1 + i), hasher, want_inputs=False, want_outputs=False).ms_total for i in range(2)]
-                s3.close()
-                rate3 = p2.n_gates * 6144 * len(ms) / (sum(ms) * 1e-3)
-                line["gpu_fused_commit_batch"] = {
-                    "workload": "fq12_mul x 6144 instances, k_lane, AES chain commitment folded by chain CTAs on the GPU",
-                    "value": rate3, "unit": "gates/s", "ms_per_step": sum(ms) / len(ms),
-                    "roofline_frac_hbm": rate3 * ALGO_BYTES_PER_GATE / 1e9 / peak}
-            except Exception as e:  # pragma: no cover
-                line["gpu_fused_commit_batch"] = {"error": str(e)}
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
             try:
-                rate, dt, _, aesni, what = cpu_garble_rate(args.cpu_circuit, args.cpu_baseline_instances, cores, prog=prog)
+                cs = CpuSampler(args.circuit)
+                rate, dt = cs.step(logical)
                 line["cpu_baseline"] = {
-                    "value": rate, "unit": "gates/s", "cores": cores, "kind": "port",
-                    "sample": f"{what} on {cores} threads ({dt:.1f} s), garble + chain commitment, "
-                              f"{'AES-NI' if aesni else 'portable AES'} oracle",
+                    "value": rate, "unit": "gates/s", "cores": physical, "threads": logical, "kind": "port",
+                    "sample": f"{cs.describe()}, one instance per thread on {logical} threads ({dt:.1f} s), garble + chain "
+                              f"commitment, {'AES-NI' if cs.aesni else 'portable AES'} oracle",
                 }
             except Exception as e:  # pragma: no cover -- never lose the measured line to the baseline leg
-                line["cpu_baseline"] = {"value": None, "unit": "gates/s", "cores": cores, "kind": "port",
+                line["cpu_baseline"] = {"value": None, "unit": "gates/s", "cores": physical, "kind": "port",
                                         "sample": f"failed: {e}"}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,6 +1,8 @@
 // circuit.cpp -- two-pass (credits, execution) circuit recorder.  See circuit.h.
 #include "circuit.h"
 
+#include <cstring>
+
 #include <algorithm>
 #include <cassert>
 #include <stdexcept>
@@ -389,6 +391,39 @@ FlatStream flatten(const Builder& b, uint32_t root, uint64_t max_gates) {
   fs.outputs = f.expand(root, ins);
   fs.n_wires = f.next_id;
   return fs;
+}
+
+// The memoised template DAG as flat arrays (layout documented at gsv_program_export_templates).
+bool export_templates(const Builder& b, uint64_t sizes[6], uint32_t* tmpl, uint32_t* gates, uint32_t* calls,
+                      uint32_t* items, uint32_t* call_wires, uint32_t* outs) {
+  uint64_t ng = 0, nc = 0, ni = 0, nw = 0, no = 0;
+  for (size_t t = 0; t < b.n_templates(); t++) {
+    const Template& T = b.tmpl((uint32_t)t);
+    if (tmpl) {
+      uint32_t* r = tmpl + 12 * t;
+      r[0] = T.n_in; r[1] = T.n_wires; r[2] = (uint32_t)ng; r[3] = (uint32_t)T.gates.size();
+      r[4] = (uint32_t)nc; r[5] = (uint32_t)T.calls.size(); r[6] = (uint32_t)ni; r[7] = (uint32_t)T.items.size();
+      r[8] = (uint32_t)nw; r[9] = (uint32_t)T.call_wires.size(); r[10] = (uint32_t)no; r[11] = (uint32_t)T.outs.size();
+    }
+    if (gates)
+      for (size_t k = 0; k < T.gates.size(); k++) {
+        uint32_t* g = gates + 4 * (ng + k);
+        g[0] = T.gates[k].a; g[1] = T.gates[k].b; g[2] = T.gates[k].c; g[3] = T.gates[k].type;
+      }
+    if (calls)
+      for (size_t k = 0; k < T.calls.size(); k++) {
+        uint32_t* c = calls + 3 * (nc + k);
+        c[0] = T.calls[k].tmpl; c[1] = T.calls[k].in_off; c[2] = T.calls[k].out_off;
+      }
+    if (items)
+      for (size_t k = 0; k < T.items.size(); k++) items[ni + k] = (T.items[k].is_call ? 0x80000000u : 0u) | T.items[k].idx;
+    if (call_wires && !T.call_wires.empty()) memcpy(call_wires + nw, T.call_wires.data(), T.call_wires.size() * 4);
+    if (outs && !T.outs.empty()) memcpy(outs + no, T.outs.data(), T.outs.size() * 4);
+    ng += T.gates.size(); nc += T.calls.size(); ni += T.items.size(); nw += T.call_wires.size(); no += T.outs.size();
+  }
+  if (ng >= (1ull << 32) || nw >= (1ull << 32) || ni >= (1ull << 32)) return false;
+  sizes[0] = 12 * b.n_templates(); sizes[1] = 4 * ng; sizes[2] = 3 * nc; sizes[3] = ni; sizes[4] = nw; sizes[5] = no;
+  return true;
 }
 
 }  // namespace gsv

@@ -144,6 +144,11 @@ std::vector<uint8_t> execute(const Builder& b, uint32_t root, const std::vector<
                              uint64_t* gates_executed = nullptr);
 
 
+// The memoised template DAG as flat arrays (layout: gsv_program_export_templates in gsv_cuda.h).  Pass null
+// arrays to query the six sizes (in words).  false when an array would exceed 2^32 words.
+bool export_templates(const Builder& b, uint64_t sizes[6], uint32_t* tmpl, uint32_t* gates, uint32_t* calls,
+                      uint32_t* items, uint32_t* call_wires, uint32_t* outs);
+
 // Gate-level dependency depth of the circuit outputs: counting every live gate, and counting only the
 // non-free (AND-family, one dependent hash each) gates -- the floor of any schedule's critical path.
 void circuit_depth(const Builder& b, uint32_t root, uint64_t* depth_all, uint64_t* depth_nonfree);

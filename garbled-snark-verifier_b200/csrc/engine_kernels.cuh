@@ -116,6 +116,23 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// shared memory through 32-bit shared-window addresses
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 __device__ __forceinline__ void named_bar(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -413,8 +430,13 @@ __device__ __forceinline__ void publish_warp(const EngineParams& p) {
 }
 
 // MODE 0 = garble (labels are label0, ciphertexts produced), MODE 1 = evaluate.
+// At most ENGINE_MAX_THREADS threads per CTA: 128 registers per thread are available, which lets ptxas keep
+// a round's table lookups in flight together (with the 64 registers of a 1024-thread CTA every lookup was
+// consumed ~8 instructions after its issue and a worker alone on its scheduler paid the shared-memory
+// latency ~16 times per AES round; profiles/r02_level_loop.md).
+constexpr uint32_t ENGINE_MAX_THREADS = 512;
 template <int G, int HASH, int MODE>
-__global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
+__global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EngineParams p) {
   extern __shared__ uint4 smem[];
   uint32_t* te = reinterpret_cast<uint32_t*>(smem);  // 64 KB table block
   constexpr uint32_t TE_Q = AES_TABLE_BYTES / 16;    // in uint4 units
@@ -538,11 +560,15 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
     if (prof) wprof[PROF_N_ITEMS]++;
 
     // ---- level loop.  A level = its non-free gates (first), then its free gates; the header in the
-    // level's first record gives both counts.  What does not depend on the previous level -- the header
-    // and each thread's first gate records of the NEXT level -- is read from the record ring BEFORE the
-    // level barrier, so the dependent path after a barrier is: label loads, hash / XOR, label store.
+    // level's first record gives both counts.  Everything that does not depend on the previous level's
+    // labels is software-pipelined out of the dependent path: at the start of level L a thread issues the
+    // loads of its first gate records of level L + 1 and of the header of level L + 2 (their ring
+    // positions follow from headers it already holds), then does level L from registers.  Between two
+    // barriers the dependent chain is: label loads -> hash / XOR -> label store.
     // Ring invariant at a level start (pos in chunk c): chunks <= c + 2 are visible, chunk c + 3 is
-    // requested.  A level spans at most two chunks, so the prefetch only touches visible records.
+    // requested; levels are at most one chunk wide, so L + 1's records and L + 2's header are visible.
+    // All shared-memory traffic of the loop uses 32-bit shared-window addresses (ld/st.shared): with
+    // generic pointers the compiler re-derived the window base (S2UR SR_CgaCtaId) at every use.
     //   garbling  : AES gates on lane pairs (lane, lane ^ G): the two hashes of a half-gate, H(A_sel) and
     //               H(A_sel ^ delta), run one per lane and the odd lane fetches the other by shuffle
     //               (it forms the ciphertext, the even lane the output label); free gates one thread
@@ -550,36 +576,52 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
     //   evaluating: one thread per (gate, instance) for both kinds.
     constexpr uint32_t RMASK = GATE_RING - 1;
     constexpr uint32_t FULL = 0xFFFFFFFFu;
+    constexpr uint32_t SLOT_B = 16u * G;                      // bytes per label slot (G instances)
+    const uint32_t lab_s = (uint32_t)__cvta_generic_to_shared(lab) + inst * 16u;
+    const uint32_t sval_s = (uint32_t)__cvta_generic_to_shared(sval) + inst;
     const uint32_t f_idx = wt / G;                            // gate index inside a free pass
     const uint32_t f_per_pass = NT / G;
     const uint32_t a_idx = MODE == 0 ? wt / (2 * G) : f_idx;  // gate index inside an AES pass
     const uint32_t a_per_pass = MODE == 0 ? NT / (2 * G) : f_per_pass;
     const uint32_t half = (wt / G) & 1u;                      // garbling: which of the two hashes
+    auto rec_at = [&](uint32_t idx) { return lds128(ring_s + ((idx & RMASK) << 4)); };
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
     uint32_t pos = 0, chunk = 0;
-    uint32_t n_tot, n_nf;
-    uint4 rec_a = make_uint4(0, 0, 0, 0), rec_f = rec_a;
-    {
-      const uint4 h = ring[0];
+    uint32_t n_tot = 0, n_nf = 0, n_tot1 = 0, n_nf1 = 0;      // headers of the current and the next level
+    uint4 rec_a = zero4, rec_f = zero4;                       // this thread's first AES / free record of the level
+    if (task.n_levels) {
+      const uint4 h = rec_at(0);
       n_tot = ((h.y >> 25) & 0x7Fu) + 1u;
       n_nf = h.w >> 24;
-      if (a_idx < n_nf) rec_a = ring[a_idx];
-      if (n_nf + f_idx < n_tot) rec_f = ring[n_nf + f_idx];
+      if (a_idx < n_nf) rec_a = rec_at(a_idx);
+      if (n_nf + f_idx < n_tot) rec_f = rec_at(n_nf + f_idx);
+      if (task.n_levels > 1) {
+        const uint4 h1 = rec_at(n_tot);
+        n_tot1 = ((h1.y >> 25) & 0x7Fu) + 1u;
+        n_nf1 = h1.w >> 24;
+      }
     }
     for (uint32_t lvl = 0; lvl < task.n_levels; ++lvl) {
+      // ---- prefetch: first records of level lvl + 1, header of level lvl + 2
+      const uint32_t pos1 = pos + n_tot, pos2 = pos1 + n_tot1;
+      uint4 rec_a1 = zero4, rec_f1 = zero4;
+      if (a_idx < n_nf1) rec_a1 = rec_at(pos1 + a_idx);
+      if (n_nf1 + f_idx < n_tot1) rec_f1 = rec_at(pos1 + n_nf1 + f_idx);
+      const uint4 h2 = rec_at(pos2);
       // ---- non-free gates
       for (uint32_t g0 = 0; g0 < n_nf; g0 += a_per_pass) {  // uniform trip count: shuffles are full-warp
         const uint32_t gi = g0 + a_idx;
         const bool act = gi < n_nf;
         uint4 r = rec_a;
-        if (g0 != 0 && act) r = ring[(pos + gi) & RMASK];
+        if (g0 != 0 && act) r = rec_at(pos + gi);
         const uint32_t sa = r.x & 0xFFFFu, sb = r.x >> 16, sc = r.y & 0xFFFFu;
         const uint32_t type = (r.y >> 16) & 0xFFu;
         const unsigned long long gid = call.gid_base + r.z;
         if (MODE == 0) {
-          uint4 hs = make_uint4(0, 0, 0, 0);
+          uint4 hs = zero4;
           if (act) {
-            uint4 x = xor4(lab[sa * G + inst], and4(delta, 0u - ((type >> 2) & 1u)));  // selected label
-            if (half) x = xor4(x, delta);                                             // the other one
+            uint4 x = xor4(lds128(lab_s + sa * SLOT_B), and4(delta, 0u - ((type >> 2) & 1u)));  // selected label
+            if (half) x = xor4(x, delta);                                                      // the other one
             hs = hash1<HASH>(te, x, gid);
           }
           uint4 ho;
@@ -590,24 +632,24 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
           if (act) {
             if (half) {
               if (p.write_ct) {
-                const uint4 ct = xor4(xor4(hs, ho), xor4(lab[sb * G + inst], and4(delta, 0u - ((type >> 1) & 1u))));
+                const uint4 ct = xor4(xor4(hs, ho), xor4(lds128(lab_s + sb * SLOT_B), and4(delta, 0u - ((type >> 1) & 1u))));
                 unsigned long long cpos = ct_pos0 + (r.w & 0xFFFFFFu);
                 if (p.ct_ring && cpos >= p.ct_ring) cpos -= p.ct_ring;
                 __stcg(ct_out + (size_t)cpos * p.ct_pos_stride, ct);
               }
             } else {
-              lab[sc * G + inst] = xor4(hs, and4(delta, 0u - (type & 1u)));
+              sts128(lab_s + sc * SLOT_B, xor4(hs, and4(delta, 0u - (type & 1u))));
             }
           }
         } else if (act) {
-          const uint4 la = lab[sa * G + inst], lb = lab[sb * G + inst];
-          const uint32_t va = sval[sa * G + inst], vb = sval[sb * G + inst];
+          const uint4 la = lds128(lab_s + sa * SLOT_B), lb = lds128(lab_s + sb * SLOT_B);
+          const uint32_t va = lds8(sval_s + sa * G), vb = lds8(sval_s + sb * G);
           const unsigned long long cti = call.ct_base + (r.w & 0xFFFFFFu);
-          uint4 ct = make_uint4(0, 0, 0, 0);
+          uint4 ct = zero4;
           if (cti < p.ct_capacity) ct = __ldcs(p.ct + (size_t)cti * p.B + grp * G + inst);
           else *p.error_flag = 1u;
-          lab[sc * G + inst] = degarble_nonfree<HASH>(te, type, ct, la, va, lb, gid);
-          sval[sc * G + inst] = (uint8_t)gate_value(type, va, vb);
+          sts128(lab_s + sc * SLOT_B, degarble_nonfree<HASH>(te, type, ct, la, va, lb, gid));
+          sts8(sval_s + sc * G, gate_value(type, va, vb));
         }
       }
       // ---- free gates
@@ -615,33 +657,23 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
         const uint32_t gi = g0 + f_idx;
         if (gi < n_tot) {
           uint4 r = rec_f;
-          if (g0 != n_nf) r = ring[(pos + gi) & RMASK];
+          if (g0 != n_nf) r = rec_at(pos + gi);
           const uint32_t sa = r.x & 0xFFFFu, sb = r.x >> 16, sc = r.y & 0xFFFFu;
           const uint32_t type = (r.y >> 16) & 0xFFu;
-          const uint4 la = lab[sa * G + inst], lb = lab[sb * G + inst];
+          const uint4 la = lds128(lab_s + sa * SLOT_B), lb = lds128(lab_s + sb * SLOT_B);
           uint4 lc = (type == 10) ? la : xor4(la, lb);
           if (MODE == 0) {
             if (type != 8) lc = xor4(lc, delta);  // Xnor / Not flip the zero label
           } else {
-            sval[sc * G + inst] = (uint8_t)gate_value(type, sval[sa * G + inst], sval[sb * G + inst]);
+            sts8(sval_s + sc * G, gate_value(type, lds8(sval_s + sa * G), lds8(sval_s + sb * G)));
           }
-          lab[sc * G + inst] = lc;
+          sts128(lab_s + sc * SLOT_B, lc);
         }
       }
-      // ---- next level's header and first records (independent of this level's results)
-      const uint32_t pos_n = pos + n_tot;
-      uint32_t n_tot_n = 0, n_nf_n = 0;
-      if (lvl + 1 < task.n_levels) {
-        const uint4 h = ring[pos_n & RMASK];
-        n_tot_n = ((h.y >> 25) & 0x7Fu) + 1u;
-        n_nf_n = h.w >> 24;
-        if (a_idx < n_nf_n) rec_a = ring[(pos_n + a_idx) & RMASK];
-        if (n_nf_n + f_idx < n_tot_n) rec_f = ring[(pos_n + n_nf_n + f_idx) & RMASK];
-      }
-      const bool cross = pos_n / GATE_CHUNK != chunk;  // uniform over the worker; at most one chunk per level
-      if (cross) cp_async_wait<0>();                   // chunk c + 3, requested one crossing ago
+      const bool cross = pos1 / GATE_CHUNK != chunk;  // uniform over the worker; at most one chunk per level
+      if (cross) cp_async_wait<0>();                  // chunk c + 3, requested one crossing ago
       named_bar(bar_id, NT);
-      if (cross) {                                     // the chunk left behind is free: request chunk c + 4
+      if (cross) {                                    // the chunk left behind is free: request chunk c + 4
         issue_chunk();
         chunk++;
       }
@@ -650,9 +682,16 @@ __global__ void __launch_bounds__(1024, 1) k_engine(const EngineParams p) {
         wprof[n_nf ? PROF_N_AES_LEVELS : PROF_N_FREE_LEVELS]++;
         wprof[PROF_N_PASSES] += (n_nf + a_per_pass - 1) / a_per_pass;
       }
-      pos = pos_n;
-      n_tot = n_tot_n;
-      n_nf = n_nf_n;
+      pos = pos1;
+      n_tot = n_tot1;
+      n_nf = n_nf1;
+      rec_a = rec_a1;
+      rec_f = rec_f1;
+      n_tot1 = n_nf1 = 0;
+      if (lvl + 2 < task.n_levels) {
+        n_tot1 = ((h2.y >> 25) & 0x7Fu) + 1u;
+        n_nf1 = h2.w >> 24;
+      }
     }
     cp_async_wait<0>();
 

@@ -304,34 +304,8 @@ int gsv_program_export_templates(const gsv_program* p, uint64_t sizes[6], uint32
                                  uint32_t* gates, uint32_t* calls, uint32_t* items, uint32_t* call_wires,
                                  uint32_t* outs) {
   if (!p || !sizes) return fail(GSV_ERR_INVALID, "null argument");
-  const gsv::Builder& b = *p->builder;
-  uint64_t ng = 0, nc = 0, ni = 0, nw = 0, no = 0;
-  for (size_t t = 0; t < b.n_templates(); t++) {
-    const gsv::Template& T = b.tmpl((uint32_t)t);
-    if (tmpl) {
-      uint32_t* r = tmpl + 12 * t;
-      r[0] = T.n_in; r[1] = T.n_wires; r[2] = (uint32_t)ng; r[3] = (uint32_t)T.gates.size();
-      r[4] = (uint32_t)nc; r[5] = (uint32_t)T.calls.size(); r[6] = (uint32_t)ni; r[7] = (uint32_t)T.items.size();
-      r[8] = (uint32_t)nw; r[9] = (uint32_t)T.call_wires.size(); r[10] = (uint32_t)no; r[11] = (uint32_t)T.outs.size();
-    }
-    if (gates)
-      for (size_t k = 0; k < T.gates.size(); k++) {
-        uint32_t* g = gates + 4 * (ng + k);
-        g[0] = T.gates[k].a; g[1] = T.gates[k].b; g[2] = T.gates[k].c; g[3] = T.gates[k].type;
-      }
-    if (calls)
-      for (size_t k = 0; k < T.calls.size(); k++) {
-        uint32_t* c = calls + 3 * (nc + k);
-        c[0] = T.calls[k].tmpl; c[1] = T.calls[k].in_off; c[2] = T.calls[k].out_off;
-      }
-    if (items)
-      for (size_t k = 0; k < T.items.size(); k++) items[ni + k] = (T.items[k].is_call ? 0x80000000u : 0u) | T.items[k].idx;
-    if (call_wires && !T.call_wires.empty()) memcpy(call_wires + nw, T.call_wires.data(), T.call_wires.size() * 4);
-    if (outs && !T.outs.empty()) memcpy(outs + no, T.outs.data(), T.outs.size() * 4);
-    ng += T.gates.size(); nc += T.calls.size(); ni += T.items.size(); nw += T.call_wires.size(); no += T.outs.size();
-  }
-  if (ng >= (1ull << 32) || nw >= (1ull << 32) || ni >= (1ull << 32)) return fail(GSV_ERR_INVALID, "template DAG too large to export");
-  sizes[0] = 12 * b.n_templates(); sizes[1] = 4 * ng; sizes[2] = 3 * nc; sizes[3] = ni; sizes[4] = nw; sizes[5] = no;
+  if (!gsv::export_templates(*p->builder, sizes, tmpl, gates, calls, items, call_wires, outs))
+    return fail(GSV_ERR_INVALID, "template DAG too large to export");
   if (root) *root = p->root;
   return GSV_OK;
 }
@@ -918,16 +892,17 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
     slots = (slots + 3) & ~3u;
     s->slots_per_worker = slots;
     s->NT = opt->worker_threads ? opt->worker_threads : 256;
-    if (s->NT != 64 && s->NT != 128 && s->NT != 256 && s->NT != 512 && s->NT != 1024)
-      throw std::runtime_error("worker_threads must be 64/128/256/512/1024");
+    if (s->NT != 64 && s->NT != 128 && s->NT != 256 && s->NT != 512)
+      throw std::runtime_error("worker_threads must be 64/128/256/512");
     // commitment consumers: one chain warp per CHAIN_INST instances, packed a few warps per SMSP
     // onto dedicated trailing CTAs (SMs) of the persistent grid
     const uint32_t chain_warps_total = (s->ct_mode == GSV_CT_COMMIT || s->ct_mode == GSV_CT_KEEP) ? (s->B + CHAIN_INST - 1) / CHAIN_INST : 0;
     uint32_t n_chain = 0;  // chain warps per chain CTA
     s->n_chain_ctas = 0;
     if (chain_warps_total) {
-      uint32_t per_cta = 16;
-      if (const char* e = getenv("GSV_CHAIN_WARPS_PER_SM")) per_cta = std::max(1, std::min(31, atoi(e)));  // warp 31: governor
+      // the lane kernel runs 1024-thread CTAs (16 chain warps + the governor warp), the levelised kernel 512
+      uint32_t per_cta = 15;
+      if (const char* e = getenv("GSV_CHAIN_WARPS_PER_SM")) per_cta = std::max(1, std::min(15, atoi(e)));  // + 1 governor warp
       n_chain = std::min(per_cta, chain_warps_total);
       s->n_chain_ctas = (chain_warps_total + n_chain - 1) / n_chain;
       if (s->n_chain_ctas * 2 > (uint32_t)s->sm_count)
@@ -944,7 +919,7 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
       s->host_threads = opt->host_threads ? opt->host_threads : std::max(1u, hw / 2);
       if (const char* e = getenv("GSV_HOST_CHAIN_THREADS")) s->host_threads = std::max(1, atoi(e));
     }
-    uint32_t n_workers = std::min<uint32_t>(1024 / s->NT, 15);  // worker w syncs on named barrier w + 1 (ids 1..15)
+    uint32_t n_workers = std::min<uint32_t>(ENGINE_MAX_THREADS / s->NT, 15);  // worker w syncs on named barrier w + 1 (ids 1..15)
     if (n_workers == 0) throw std::runtime_error("worker_threads too large");
     // largest G (power of two dividing B, <= 8) whose label working set fits next to the tables
     auto smem_for = [&](uint32_t G, uint32_t nw, bool eval) {

@@ -177,7 +177,7 @@ typedef struct {
   int device;             /* CUDA device ordinal */
   uint32_t n_instances;   /* batch size B (cut-and-choose instances on this GPU) */
   uint32_t group;         /* instances per work item: 1,2,4,8; 0 = auto */
-  uint32_t worker_threads;/* threads per worker: 64/128/256/512/1024; 0 = auto (256) */
+  uint32_t worker_threads;/* threads per worker: 64/128/256/512; 0 = auto (256) */
   uint32_t ct_mode;       /* enum gsv_ct_mode */
   uint32_t ct_ring_log2;  /* GSV_CT_COMMIT: cap the ciphertext ring at 2^n entries per instance; 0 = auto */
   uint32_t exec_mode;     /* 0 = auto, 1 = levelised (labels in shared memory, small batches),

@@ -266,3 +266,61 @@ class TemplateDag:
         return {"delta": bytes(sm.delta), "false_label0": bytes(sm.false_label0), "true_label0": bytes(sm.true_label0),
                 "ct_commit": bytes(sm.ct_commit), "n_ct": int(sm.n_ct), "n_gates": int(sm.n_gates),
                 "input_label0": inl, "output_label0": outl}
+
+
+GEN_LIB_PATH = os.path.join(_HERE, "libgsv_circuitgen.so")
+_gen = None
+
+
+def _genlib() -> C.CDLL:
+    global _gen
+    if _gen is None:
+        if not os.path.exists(GEN_LIB_PATH):
+            build()
+        L = C.CDLL(GEN_LIB_PATH)
+        L.gsvgen_build.restype = C.c_void_p
+        L.gsvgen_build.argtypes = [C.c_char_p]
+        L.gsvgen_destroy.argtypes = [C.c_void_p]
+        L.gsvgen_last_error.restype = C.c_char_p
+        L.gsvgen_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_void_p] * 6
+        L.gsvgen_totals.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _gen = L
+    return _gen
+
+
+class CircuitGen:
+    """A named workload circuit recorded by the host-only generator library (oracle/circuitgen.cpp): the
+    template DAG the oracle walks, without loading the CUDA engine (bench.py --impl reference)."""
+
+    def __init__(self, circuit: str):
+        L = _genlib()
+        h = L.gsvgen_build(circuit.encode())
+        if not h:
+            raise RuntimeError(f"circuit generator: {L.gsvgen_last_error().decode()}")
+        try:
+            sizes = (C.c_uint64 * 6)()
+            root = C.c_uint32(0)
+            assert L.gsvgen_export(h, sizes, C.byref(root), None, None, None, None, None, None) == 0
+            self.arrays = [np.zeros(max(int(n), 1), np.uint32) for n in sizes]
+            assert L.gsvgen_export(h, sizes, C.byref(root), *[a.ctypes.data for a in self.arrays]) == 0
+            self.arrays = [a[: int(n)] for a, n in zip(self.arrays, sizes)]
+            self.root = int(root.value)
+            self.n_templates = self.arrays[0].shape[0] // 12
+            self.total_gates = np.zeros(self.n_templates, np.uint64)
+            self.total_ct = np.zeros(self.n_templates, np.uint64)
+            assert L.gsvgen_totals(h, self.total_gates.ctypes.data, self.total_ct.ctypes.data) == 0
+        finally:
+            L.gsvgen_destroy(h)
+        self.circuit = circuit
+        self.n_gates = int(self.total_gates[self.root])
+        self.n_ciphertexts = int(self.total_ct[self.root])
+
+    def dag(self, root: int | None = None) -> "TemplateDag":
+        return TemplateDag(self.root if root is None else root, *self.arrays)
+
+    def children(self, tmpl: int | None = None):
+        """Callee template index of every call of `tmpl` (default: the circuit's root), in emission order."""
+        t = self.root if tmpl is None else tmpl
+        r = self.arrays[0][12 * t:12 * t + 12]
+        calls = self.arrays[2][3 * int(r[4]):3 * (int(r[4]) + int(r[5]))].reshape(-1, 3)
+        return [int(c[0]) for c in calls]

@@ -1,13 +1,13 @@
 """Round-2 exploration probe (not the bench): PCIe copy rates and per-phase worker cycles (GSV_PROFILE)
 of the levelised kernel on circuits that resemble the verifier's critical path.
 
-usage: probe_r02.py [pcie] [small] [verifier] [verifier_shapes=4x256,2x256]
+usage: probe_r02.py [pcie] [latency] [small] [verifier] [verifier_shapes=4x256,2x256] [circuits=a,b]
+Set GSV_PROFILE=1 to get the per-phase cycle split (costs a few percent).
 """
 import os
 import sys
 import time
 
-os.environ.setdefault("GSV_PROFILE", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gsv_b200 as g
 
@@ -64,8 +64,13 @@ if "pcie" in what:
     print(f"pcie D2H + H2D concurrently: {n / dt / 1e9:.1f} GB/s each direction", flush=True)
     del d, h, h2, d2
 
+if "latency" in what:
+    for w in (1, 2, 4, 8, 16):
+        print(f"dependent gate hash, {w} warp(s) per SM: AES {g.bench_hash_latency(g.HASH_AES, w):.0f} cycles, "
+              f"BLAKE3 {g.bench_hash_latency(g.HASH_BLAKE3, w):.0f} cycles", flush=True)
+
 if "small" in what:
-    for circ in ("fq12_mul", "fq12_inverse"):
+    for circ in kv.get("circuits", "fq12_mul,fq12_inverse").split(","):
         p = g.Program(circ)
         print(f"{circ}: gates {p.n_gates} calls {p.n_calls} critical path {p.critical_path_levels} levels, "
               f"sum of call levels {p.sum_call_levels}", flush=True)

@@ -12,7 +12,7 @@ def _run(env_extra=None):
     env = dict(os.environ)
     env.update(env_extra or {})
     return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "batch",
-                           "--circuit", "fq_mul", "--steps", "1", "--warmup", "0", "--ref-instances-per-core", "2"],
+                           "--circuit", "fq_mul", "--steps", "1", "--warmup", "0"],
                           capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
 
 
@@ -28,6 +28,8 @@ def test_reference_arm_prints_one_json_line(built):
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+    # the reference arm runs the CPU oracle and the host-only circuit generator, never the CUDA engine
+    assert d["native_libs"] == ["oracle/libgsv_circuitgen.so", "oracle/libgsv_oracle.so"]
 
 
 def test_reference_arm_is_silent_on_other_ranks(built):
