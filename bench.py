@@ -426,17 +426,28 @@ def main():
             drain_gbs = d2h * args.steps / wall / 1e9
             fold_floor_s = prog.n_ciphertexts * 13e-9      # one dependent AES-NI block per ~13 ns (10 aesenc)
             pcie_util = drain_gbs / PCIE_D2H_GBS
-            fold_util = fold_floor_s / wave_s
-            limiter = "pcie_drain" if pcie_util >= 0.85 and pcie_util >= fold_util else ("host_fold" if fold_util >= 0.85 else "kernel")
+            fold_busy = max(r.host_fold_busy for r in results)               # busiest fold thread, share of its step
+            wait_kernel = sum(r.host_drain_wait_kernel for r in results) / len(results)
+            wait_fold = sum(r.host_drain_wait_fold for r in results) / len(results)
+            if fold_busy >= 0.85 or wait_fold >= 0.25:
+                limiter = "host_fold"
+            elif pcie_util >= 0.85:
+                limiter = "pcie_drain"
+            elif wait_kernel >= 0.5:
+                limiter = "kernel"
+            else:
+                limiter = "pcie_drain" if pcie_util >= 0.6 else "kernel"
             roofline["gpu_chain_floor_s"] = prog.n_ciphertexts * 0.46e-6  # measured dependent-AES step on the GPU
             roofline["pipeline"] = {
                 "limiter": limiter, "steps_in_flight": conc, "step_in_flight_s": wave_s,
                 "d2h_drain_GBps": drain_gbs, "pcie_d2h_peak_GBps": PCIE_D2H_GBS, "pcie_util": pcie_util,
-                "host_chain_floor_s": fold_floor_s, "fold_util": fold_util,
+                "host_chain_floor_s": fold_floor_s, "fold_thread_busy": fold_busy,
+                "drain_wait_for_kernel": wait_kernel, "drain_wait_for_fold": wait_fold,
                 "host_threads_per_rank": S * (fold_threads + 1), "fold_threads_per_session": fold_threads,
                 "host_logical_cpus": logical, "host_physical_cores": physical, "ranks_on_host": local_world,
-                "note": "limiter: pcie_drain when the ciphertext drain runs at >= 85 % of the measured pinned D2H rate; host_fold "
-                        "when a step is in flight for about as long as one AES-NI chain needs (n_ct x 13 ns); else the kernel"}
+                "note": "rank 0's view.  host_fold: the busiest AES-NI fold thread is busy >= 85 % of its step (or the drain waits for "
+                        "fold buffers); pcie_drain: the ciphertext drain runs at >= 85 % of the measured pinned D2H rate (GPUs that "
+                        "share a PCIe switch divide it); kernel: the drain mostly waits for the kernel to publish ciphertexts"}
         try:
             blocks = g.bench_hash(hasher, 1 << 28, 2, device=local)
             nonfree = sum(prog.type_count[:8]) / prog.n_gates

@@ -93,6 +93,10 @@ class _GarbleResult(C.Structure):
         ("ms_total", C.c_float),
         ("n_launches", C.c_uint32),
         ("reserved", C.c_uint32),
+        ("host_fold_busy", C.c_float),
+        ("host_drain_wait_kernel", C.c_float),
+        ("host_drain_wait_fold", C.c_float),
+        ("reserved2", C.c_float),
     ]
 
 
@@ -269,6 +273,9 @@ class GarbleResult:
     ms_commit: float
     ms_total: float
     n_launches: int
+    host_fold_busy: float = 0.0          # CT_COMMIT_HOST: busiest fold thread's share of the call inside the fold
+    host_drain_wait_kernel: float = 0.0  # drain loop waiting for the kernel
+    host_drain_wait_fold: float = 0.0    # drain loop waiting for the fold threads
 
     @property
     def true_label1(self) -> np.ndarray:
@@ -330,7 +337,8 @@ class Session:
         r.input_label0, r.output_label0, r.ct_commit = _ptr(il), _ptr(ol), _ptr(cc)
         _check(lib.gsv_garble_batch(self._h, hasher, _ptr(seeds_a), C.byref(r)))
         return GarbleResult(delta, fl, tl, il, ol, cc, int(r.n_ciphertexts), r.ms_seed, r.ms_garble,
-                            r.ms_commit, r.ms_total, r.n_launches)
+                            r.ms_commit, r.ms_total, r.n_launches, r.host_fold_busy, r.host_drain_wait_kernel,
+                            r.host_drain_wait_fold)
 
     def read_ciphertexts(self, instance: int, first: int = 0, count: Optional[int] = None) -> np.ndarray:
         lib = load_library()

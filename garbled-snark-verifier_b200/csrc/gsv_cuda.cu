@@ -758,7 +758,16 @@ void launch_engine(gsv_session* s, int hasher, const EngineParams& p) {
 // n_quads rows of n * 64 contiguous bytes, and a fold step of a quad is one 64-byte load.
 // Waiting threads sleep (the drain loop and the fold threads of several sessions / ranks share the
 // host cores; spinning on yield() would take the cores the folds need).
-void run_host_chain(gsv_session* s, uint8_t* commits) {
+struct HostChainStats {
+  double fold_busy = 0;         // busiest fold thread: share of the run spent folding
+  double drain_wait_ready = 0;  // drain loop: share of the run spent waiting for the kernel to publish data
+  double drain_wait_slot = 0;   // ... waiting for a host buffer the fold threads still hold
+};
+void run_host_chain(gsv_session* s, uint8_t* commits, HostChainStats* stats) {
+  const auto t_run0 = std::chrono::steady_clock::now();
+  auto secs = [](std::chrono::steady_clock::duration d) { return std::chrono::duration<double>(d).count(); };
+  std::vector<double> busy(64, 0.0);
+  double wait_ready = 0, wait_slot = 0;
   const gsv::Program& g = s->prog->prog;
   const uint32_t B = s->B, nq = (B + 3) / 4;
   const uint64_t total = g.total_ct;
@@ -792,9 +801,12 @@ void run_host_chain(gsv_session* s, uint8_t* commits) {
         abort.store(true);
         return;
       }
-      if (q1 > q0)
+      if (q1 > q0) {
+        const auto t0 = std::chrono::steady_clock::now();
         gsv::host_chain_fold_quads(h.data() + (size_t)q0 * 64, s->hc_buf[b] + (size_t)q0 * chunk_pos * 64, chunk_pos * 64,
                                    slot_npos[b], q1 - q0);
+        busy[t % busy.size()] += secs(std::chrono::steady_clock::now() - t0);
+      }
       slot_done[b].fetch_add(1, std::memory_order_release);
     }
   };
@@ -827,12 +839,17 @@ void run_host_chain(gsv_session* s, uint8_t* commits) {
             throw std::runtime_error("garbling kernel ended before the stream was complete");
         }
         nap();
+        wait_ready += secs(std::chrono::steady_clock::now() - now);
         continue;
       }
       const int b = (int)(jobs % NB);
-      while (slot_done[b].load(std::memory_order_acquire) != (uint64_t)T * (jobs / NB)) {
-        if (abort.load()) throw std::runtime_error("host chain thread failed");
-        nap();
+      {
+        const auto t0 = std::chrono::steady_clock::now();
+        while (slot_done[b].load(std::memory_order_acquire) != (uint64_t)T * (jobs / NB)) {
+          if (abort.load()) throw std::runtime_error("host chain thread failed");
+          nap();
+        }
+        wait_slot += secs(std::chrono::steady_clock::now() - t0);
       }
       CUDA_TRY(cudaMemcpy2DAsync(s->hc_buf[b], (size_t)chunk_pos * 64, s->d_ct.p + pos * 4, (size_t)cap * 64, (size_t)n * 64, nq,
                                  cudaMemcpyDeviceToHost, s->copy_stream));
@@ -861,6 +878,12 @@ void run_host_chain(gsv_session* s, uint8_t* commits) {
     throw std::runtime_error(err);
   }
   for (uint32_t i = 0; i < B; i++) memcpy(commits + (size_t)i * 16, h.data() + (size_t)i * 16, 16);
+  if (stats) {
+    const double total_s = std::max(1e-9, secs(std::chrono::steady_clock::now() - t_run0));
+    stats->fold_busy = *std::max_element(busy.begin(), busy.end()) / total_s;
+    stats->drain_wait_ready = wait_ready / total_s;
+    stats->drain_wait_slot = wait_slot / total_s;
+  }
 }
 
 }  // namespace
@@ -1063,6 +1086,7 @@ int gsv_garble_batch(gsv_session* s, int hasher, const uint64_t* seeds, gsv_garb
     const uint32_t B = s->B;
     uint32_t launches = 0;
     s->epoch++;
+    res->host_fold_busy = res->host_drain_wait_kernel = res->host_drain_wait_fold = 0.f;
     const auto t_begin = std::chrono::steady_clock::now();
     CUDA_TRY(cudaMemcpyAsync(s->d_seeds.p, seeds, (size_t)B * 8, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaMemsetAsync(s->d_ctrl.p, 0, 16, s->stream));
@@ -1093,7 +1117,11 @@ int gsv_garble_batch(gsv_session* s, int hasher, const uint64_t* seeds, gsv_garb
     double host_ms = 0.0;
     if (s->ct_mode == GSV_CT_COMMIT_HOST) {
       host_commits.resize((size_t)B * 16);
-      run_host_chain(s, host_commits.data());  // returns when the last chain is folded
+      HostChainStats hs;
+      run_host_chain(s, host_commits.data(), &hs);  // returns when the last chain is folded
+      res->host_fold_busy = (float)hs.fold_busy;
+      res->host_drain_wait_kernel = (float)hs.drain_wait_ready;
+      res->host_drain_wait_fold = (float)hs.drain_wait_slot;
       host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     }
     // the chain commitment is folded inside k_engine by the chain warps (no separate launch)

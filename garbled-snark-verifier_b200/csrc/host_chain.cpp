@@ -177,6 +177,10 @@ void host_chain_fold_quads(uint8_t* h, const uint8_t* base, size_t quad_bytes, s
   uint32_t q = 0;
   if (have_vaes()) {
     for (; q + 4 <= n_quads; q += 4) fold_quads_vaes<4>(h + 64 * q, base + quad_bytes * q, quad_bytes, n_pos, rk);
+    if (q + 3 <= n_quads) {
+      fold_quads_vaes<3>(h + 64 * q, base + quad_bytes * q, quad_bytes, n_pos, rk);
+      q += 3;
+    }
     if (q + 2 <= n_quads) {
       fold_quads_vaes<2>(h + 64 * q, base + quad_bytes * q, quad_bytes, n_pos, rk);
       q += 2;

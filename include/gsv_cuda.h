@@ -209,6 +209,11 @@ typedef struct {
   float ms_total;         /* first launch -> last kernel done                            */
   uint32_t n_launches;    /* kernels launched by this call                               */
   uint32_t reserved;
+  /* GSV_CT_COMMIT_HOST: where the step's time went on the host side (shares of the call's duration) */
+  float host_fold_busy;         /* busiest fold thread: time inside the AES-NI fold                 */
+  float host_drain_wait_kernel; /* drain loop waiting for the kernel to publish more ciphertexts    */
+  float host_drain_wait_fold;   /* drain loop waiting for a host buffer the fold threads still hold */
+  float reserved2;
 } gsv_garble_result;
 
 /* The recorded circuit as its memoised template DAG (what gsv_program_flat_stream expands), for checkers
