@@ -223,6 +223,91 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------- config 3
+NVLINK_PEER_GBS = 770.0      # measured peer copy per direction on this pool (B200_PROFILING.md)
+
+
+def run_mpc(args):
+    """BASELINE.json config 3: the garbler (GPU 0) regarbles the verifier and streams every ciphertext into a ring in
+    the evaluator's memory (GPU 1) with peer stores over NVLink; the evaluator (GPU 1) consumes the ring, and hashes
+    what it received on host AES-NI threads like the reference's evaluator does (examples/groth16_garble.rs:170-267).
+    One process drives both GPUs (`--gpus 2`; on one GPU the two persistent grids split the SMs)."""
+    import numpy as np
+    import torch
+
+    import gsv_b200 as g
+    from gsv_b200 import cut_and_choose as cc
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    two = torch.cuda.device_count() >= 2 and args.gpus >= 2
+    hasher = g.HASH_AES if args.hasher == "aes" else g.HASH_BLAKE3
+    t_plan = time.perf_counter()
+    prog = g.Program(args.circuit)
+    t_plan = time.perf_counter() - t_plan
+    B = args.instances
+    logical, physical = host_cpus()
+    fold_threads = args.host_threads or max(1, min((B + 3) // 4, logical - 2))
+    sm_limit = 0 if two else (torch.cuda.get_device_properties(0).multi_processor_count - SM_RESERVE) // 2
+    gs = g.Session(prog, B, device=0, group=args.group, worker_threads=args.worker_threads, ct_mode=g.CT_NONE,
+                   exec_mode=args.exec_mode, sm_limit=sm_limit)
+    es = g.Session(prog, B, device=1 if two else 0, group=args.group, worker_threads=args.worker_threads, ct_mode=g.CT_NONE,
+                   exec_mode=args.exec_mode, sm_limit=sm_limit, host_threads=fold_threads)
+    g.link_sessions(gs, es)
+    compressed = args.circuit == "groth16_verify_compressed"
+    if args.circuit.startswith("groth16"):
+        bits1 = g.groth16_synthetic_inputs(compressed=compressed)
+    else:
+        bits1 = np.random.default_rng(3).integers(0, 2, prog.n_inputs, dtype=np.uint8)
+    bits = np.broadcast_to(bits1, (B, prog.n_inputs)).copy()
+    seeds = np.asarray(cc.instance_seeds(1234, (args.warmup + args.steps) * B), dtype=np.uint64)
+    for i in range(args.warmup):
+        g.stream_garble_evaluate(gs, es, seeds[i * B:(i + 1) * B], hasher, bits)
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ok, ms_eval, ms_garble, launches = True, 0.0, 0.0, 0
+    for i in range(args.warmup, args.warmup + args.steps):
+        gres, ev = g.stream_garble_evaluate(gs, es, seeds[i * B:(i + 1) * B], hasher, bits)
+        ms_eval += ev.ms_evaluate
+        ms_garble += gres.ms_garble
+        launches += gres.n_launches + ev.n_launches
+        if args.circuit.startswith("groth16"):
+            ok = ok and bool((ev.output_bits == 1).all())   # the synthetic proof verifies
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    gates = prog.n_gates * B * args.steps
+    ct_bytes = prog.n_ciphertexts * 16 * B * args.steps
+    value = gates / wall
+    nv = ct_bytes / wall / 1e9
+    peak, peak_src = measured_peaks()
+    line = {
+        "metric": "garbled_gates_per_s", "value": value, "unit": "gates/s", "n_gpus": 2 if two else 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {
+            "workload": f"{args.circuit} x {B} instances garbled on GPU 0 and evaluated on GPU {1 if two else 0} at the same time "
+                        f"(BASELINE.json config 3): ciphertexts streamed through a ring in the evaluator's memory"
+                        + (" by peer stores over NVLink" if two else " (one GPU: the two grids split the SMs)")
+                        + ", evaluator hashes the received stream on host AES-NI threads",
+            "kernel": "k_engine (garble) + k_engine (evaluate)", "plan_s": round(t_plan, 1), "instances": B,
+            "gates_per_instance": prog.n_gates, "ciphertexts_per_instance": prog.n_ciphertexts,
+            "verify_bits_all_one": ok,
+        },
+        "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": B * (8 + 16 * (2 + prog.n_inputs) + prog.n_inputs),
+                "d2h_bytes_per_step": B * 16 * (3 + prog.n_inputs + 2 * prog.n_outputs) + B * 16 * prog.n_ciphertexts},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "nvlink" if two else "hbm", "achieved": nv, "peak": NVLINK_PEER_GBS if two else peak, "unit": "GB/s",
+                     "frac": nv / (NVLINK_PEER_GBS if two else peak), "traffic": None, "kernel": "k_engine",
+                     "kernel_ms": ms_garble / args.steps, "evaluate_kernel_ms": ms_eval / args.steps,
+                     "note": "achieved = ciphertext bytes crossing from the garbler to the evaluator per second (16 B x ciphertexts); "
+                             "the stream is paced by the evaluator-side hash (one AES-NI chain per instance, fed over PCIe), "
+                             "not by the link"},
+    }
+    print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -230,7 +315,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gsv", choices=["gsv", "reference"])
-    ap.add_argument("--workload", default="verifier", choices=["verifier", "batch"])
+    ap.add_argument("--workload", default="verifier", choices=["verifier", "batch", "mpc"])
     ap.add_argument("--circuit", default=None, help="override the workload's circuit")
     ap.add_argument("--instances", type=int, default=None, help="cut-and-choose instances per step and GPU")
     ap.add_argument("--sessions", type=int, default=None, help="steps in flight per GPU (software pipelining)")
@@ -248,6 +333,8 @@ def main():
     # workload presets (explicit flags win)
     preset = {"verifier": dict(circuit="groth16_verify_compressed", instances=16, sessions=3, exec_mode=1, group=4,
                                ct_mode="commit_host", steps=6),
+              "mpc": dict(circuit="groth16_verify_compressed", instances=16, sessions=1, exec_mode=1, group=4,
+                          ct_mode="none", steps=2),
               "batch": dict(circuit="fq12_mul", instances=6144, sessions=1, exec_mode=2, group=0, ct_mode="commit",
                             steps=3)}[args.workload]
     for k, v in preset.items():
@@ -258,6 +345,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload == "mpc":
+        run_mpc(args)
         return
 
     import numpy as np

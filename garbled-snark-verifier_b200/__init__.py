@@ -304,6 +304,7 @@ class Session:
         self.n_instances = n_instances
         self.device = device
         self.ct_mode = ct_mode
+        self.group = group
         opt = _SessionOptions(device, n_instances, group, worker_threads, ct_mode, ct_ring_log2, exec_mode,
                               sm_limit, ct_buffer_bytes, host_threads, 0)
         self._h = lib.gsv_session_create(program._h, C.byref(opt))
@@ -340,6 +341,41 @@ class Session:
                             r.ms_commit, r.ms_total, r.n_launches, r.host_fold_busy, r.host_drain_wait_kernel,
                             r.host_drain_wait_fold)
 
+    def set_ciphertext_files(self, paths: Optional[Sequence[Optional[str]]]) -> None:
+        """gc_{i}.bin writers (ciphertext_repository.rs:94-106) for the next garbling runs of a CT_COMMIT_HOST
+        session (or the runs a linked evaluator receives): instance i's stream goes to paths[i] (None = skip).
+        Pass None to close the files and clear the sink."""
+        lib = load_library()
+        lib.gsv_session_set_ciphertext_files.argtypes = [C.c_void_p, C.c_void_p]
+        for fd in getattr(self, "_ct_fds", []):
+            if fd >= 0:
+                os.close(fd)
+        self._ct_fds = []
+        if paths is None:
+            _check(lib.gsv_session_set_ciphertext_files(self._h, None))
+            return
+        if len(paths) != self.n_instances:
+            raise ValueError("need one path (or None) per instance")
+        self._ct_fds = [os.open(p, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644) if p else -1 for p in paths]
+        arr = (C.c_int * len(paths))(*self._ct_fds)
+        _check(lib.gsv_session_set_ciphertext_files(self._h, arr))
+
+    def expand_seeds(self, seeds: Sequence[int]) -> GarbleResult:
+        """Delta, constants and input label0s of `seeds` (the seed expansion alone, no garbling)."""
+        lib = load_library()
+        B, p = self.n_instances, self.program
+        seeds_a = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
+        if seeds_a.shape != (B,):
+            raise ValueError("need one seed per instance")
+        delta, fl, tl = (np.zeros((B, 16), np.uint8) for _ in range(3))
+        il = np.zeros((B, p.n_inputs, 16), np.uint8)
+        r = _GarbleResult()
+        r.delta, r.false_label0, r.true_label0, r.input_label0 = _ptr(delta), _ptr(fl), _ptr(tl), _ptr(il)
+        lib.gsv_session_expand_seeds.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_GarbleResult)]
+        _check(lib.gsv_session_expand_seeds(self._h, _ptr(seeds_a), C.byref(r)))
+        return GarbleResult(delta, fl, tl, il, None, np.zeros((B, 16), np.uint8), int(r.n_ciphertexts), 0.0, 0.0, 0.0, 0.0,
+                            r.n_launches)
+
     def read_ciphertexts(self, instance: int, first: int = 0, count: Optional[int] = None) -> np.ndarray:
         lib = load_library()
         if count is None:
@@ -374,6 +410,46 @@ class Session:
         io.output_active, io.output_bits, io.ct_commit = _ptr(oa), _ptr(ob), _ptr(cc if want_commit else None)
         _check(lib.gsv_evaluate_batch(self._h, hasher, C.byref(io)))
         return EvalResult(oa, ob, cc, io.ms_evaluate, io.ms_commit, io.ms_total, io.n_launches)
+
+
+def link_sessions(garbler: "Session", evaluator: "Session", ring_bytes: int = 0) -> None:
+    """Garbler -> evaluator streaming (gsv_session_link): afterwards call garbler.garble(..) and
+    evaluator.evaluate(.., ct_streams=None) concurrently from two threads (see `stream_garble_evaluate`)."""
+    lib = load_library()
+    lib.gsv_session_link.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    _check(lib.gsv_session_link(garbler._h, evaluator._h, ring_bytes))
+    garbler._linked = evaluator._linked = True
+
+
+def stream_garble_evaluate(garbler: "Session", evaluator: "Session", seeds, hasher: int, input_bits: np.ndarray):
+    """One run over a linked pair (examples/groth16_garble.rs:170-267): the garbler regarbles from `seeds`
+    while the evaluator consumes the ciphertext ring.  The evaluator's inputs are built like the reference's
+    G2EMsg::Commit: active input labels = select(bit), constants = (true.label1, false.label0), all pure
+    functions of the seed.  Returns (GarbleResult, EvalResult)."""
+    import threading
+
+    p = garbler.program
+    B = garbler.n_instances
+    bits = np.ascontiguousarray(input_bits, np.uint8).reshape(B, p.n_inputs)
+    lab = garbler.expand_seeds(seeds)
+    active = lab.input_label0 ^ (lab.delta[:, None, :] * bits[:, :, None])
+    out = {}
+
+    def run_g():
+        try:
+            out["g"] = garbler.garble(seeds, hasher)
+        except Exception as e:  # pragma: no cover
+            out["g_err"] = e
+
+    tg = threading.Thread(target=run_g)
+    tg.start()
+    try:
+        ev = evaluator.evaluate(hasher, lab.true_label0 ^ lab.delta, lab.false_label0, active, bits)
+    finally:
+        tg.join()
+    if "g_err" in out:
+        raise out["g_err"]
+    return out["g"], ev
 
 
 def host_chain_fold(h: np.ndarray, blocks: np.ndarray, instance_major: bool = False) -> np.ndarray:

@@ -70,6 +70,16 @@ struct EngineParams {
   unsigned long long park_q;        // bucket width in ciphertexts
   uint32_t n_buckets;
   uint32_t n_progress;              // consumer progress counters to take the minimum of
+  // Flow control of the ciphertext ring (the governor publishes sched_limit = min(progress words) + limit_add):
+  //   garbling into a ring   : progress = what the consumers (chain warps / host drain / a linked evaluator)
+  //                            have released, limit_add = ring capacity, free_until = ring capacity (first lap);
+  //   evaluating from a ring : progress = what the producer has made available, limit_add = free_until = 0.
+  uint32_t flow_control;            // items are admitted against sched_limit (else: everything is resident)
+  unsigned long long limit_add, free_until;
+  unsigned long long flow_total;    // ciphertexts in the whole stream
+  const unsigned long long* ext_progress;  // optional progress word in mapped host memory (another device / the host
+                                           // writes it): read at system scope
+  uint32_t ct_sys;                  // the ciphertext ring is written to / read by another device: system-scope fences
   uint32_t* error_flag;       // evaluate: set to 1 on ciphertext exhaustion
   unsigned long long* chain_progress;  // [chain warp] ciphertexts folded so far
   uint4* commit;        // [B] chain result
@@ -153,6 +163,13 @@ __device__ __forceinline__ unsigned long long ld_acquire64(const unsigned long l
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+// words another device or the host writes (mapped host memory): system scope
+__device__ __forceinline__ unsigned long long ld_sys64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ void st_release64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -306,8 +323,10 @@ __device__ __forceinline__ void sched_park(const EngineParams& p, uint32_t item,
 // true when the item may start now; otherwise it has been parked
 __device__ __forceinline__ bool sched_ring_admit(const EngineParams& p, uint32_t item) {
   const uint32_t ci = item / p.n_groups;
-  const unsigned long long need = p.calls[ci].ct_base + p.tasks[p.calls[ci].task].n_ct;
-  if (need <= p.ct_ring || need <= ld_acquire64(p.sched_limit)) return true;
+  const uint32_t n_ct = p.tasks[p.calls[ci].task].n_ct;
+  if (n_ct == 0) return true;  // touches no ring position
+  const unsigned long long need = p.calls[ci].ct_base + n_ct;
+  if (need <= p.free_until || need <= ld_acquire64(p.sched_limit)) return true;
   sched_park(p, item, need);
   return false;
 }
@@ -320,11 +339,17 @@ __device__ __forceinline__ void governor_warp(const EngineParams& p) {
     const bool done = ld_acquire(p.sched + 2) >= n_items;
     unsigned long long m = ~0ull;
     for (uint32_t i = lane; i < p.n_progress; i += 32) m = min(m, ld_acquire64(p.chain_progress + i));
+    if (p.ext_progress && lane == 0) {
+      m = min(m, ld_sys64(p.ext_progress));
+      fence_sys();  // what the other side wrote before advancing the word is visible from here on
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(FULL, m, o));
-    const unsigned long long limit = m + p.ct_ring;
+    const unsigned long long limit = m + p.limit_add;
     if (lane == 0) st_release64(p.sched_limit, limit);
-    const uint32_t nb = (uint32_t)min((unsigned long long)p.n_buckets, limit / p.park_q);  // fully covered
+    // buckets the limit covers entirely; everything once the whole stream is covered (when evaluating, the
+    // limit ends exactly at the stream's length, inside the last bucket)
+    const uint32_t nb = limit >= p.flow_total ? p.n_buckets : (uint32_t)min((unsigned long long)p.n_buckets, limit / p.park_q);
     if (nb > released) {
       if (lane == 0) st_release(p.sched + 3, nb);
       __threadfence();
@@ -392,7 +417,7 @@ __device__ __forceinline__ uint32_t sched_complete_warp(const EngineParams& p, u
 // pending[item] = number of dependencies; items without any are pushed right away
 __global__ void k_sched_init(const EngineParams p) {
   const uint32_t n_items = p.n_calls * p.n_groups;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *p.sched_limit = p.ct_ring;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.sched_limit = p.free_until;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
     const uint32_t nd = p.calls[i / p.n_groups].n_deps;
     p.pending[i] = nd;
@@ -445,15 +470,16 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
   load_tables(te, threadIdx.x, blockDim.x);
   __syncthreads();
 
-  if (MODE == 0 && blockIdx.x >= gridDim.x - p.n_chain_ctas) {
+  if (blockIdx.x >= gridDim.x - p.n_chain_ctas) {
     // ---- chain CTA: the last n_chain_ctas SMs only run commitment consumers, a few warps per
-    // SMSP, so the latency-bound chain never competes with garbling warps for issue slots
+    // SMSP, so the latency-bound chain never competes with garbling warps for issue slots (evaluating
+    // from a ring: one such CTA with the governor and the publisher of the consumed frontier)
     const uint32_t warp = threadIdx.x >> 5;
-    if (p.ct_ring && blockIdx.x == gridDim.x - p.n_chain_ctas && warp == (blockDim.x >> 5) - 1) {
+    if (p.flow_control && blockIdx.x == gridDim.x - p.n_chain_ctas && warp == (blockDim.x >> 5) - 1) {
       governor_warp(p);
     } else if (p.host_chain) {
       if (warp == 0) publish_warp(p);
-    } else if (warp < p.n_chain_warps) {
+    } else if (MODE == 0 && warp < p.n_chain_warps) {
       chain_warp(p, te, (blockIdx.x - (gridDim.x - p.n_chain_ctas)) * p.n_chain_warps + warp);
     }
     return;
@@ -502,7 +528,7 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
       *keep = SCHED_NONE;
       for (;;) {
         if (it == SCHED_NONE) it = sched_pop(p, n_items);
-        if (it == SCHED_DONE || MODE != 0 || !p.ct_ring || sched_ring_admit(p, it)) break;
+        if (it == SCHED_DONE || !p.flow_control || sched_ring_admit(p, it)) break;
         it = SCHED_NONE;  // parked until the ring has room
       }
       *ctrl = it;
@@ -534,12 +560,10 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
     // ---- gather inputs (and the two constant wires) into shared memory
     const size_t gbase = (size_t)grp * p.n_global_slots;
     uint4 delta = make_uint4(0, 0, 0, 0);
-    uint4* ct_out = nullptr;  // garbling: this thread's instance column of the ciphertext buffer
-    if (MODE == 0) {
-      delta = p.delta[grp * G + inst];
-      const uint32_t gi = grp * G + inst;
-      ct_out = p.ct + (size_t)(gi >> p.ct_qshift) * p.ct_quad_stride + (gi & ((1u << p.ct_qshift) - 1u));
-    }
+    if (MODE == 0) delta = p.delta[grp * G + inst];
+    // this thread's instance column of the ciphertext buffer (written when garbling, read when evaluating)
+    const uint32_t ginst = grp * G + inst;
+    uint4* const ct_out = p.ct + (size_t)(ginst >> p.ct_qshift) * p.ct_quad_stride + (ginst & ((1u << p.ct_qshift) - 1u));
     if (wt < 2 * G) {
       const uint32_t s = wt / G;
       lab[s * G + inst] = __ldcg(p.labels + (gbase + s) * G + inst);
@@ -646,8 +670,13 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
           const uint32_t va = lds8(sval_s + sa * G), vb = lds8(sval_s + sb * G);
           const unsigned long long cti = call.ct_base + (r.w & 0xFFFFFFu);
           uint4 ct = zero4;
-          if (cti < p.ct_capacity) ct = __ldcs(p.ct + (size_t)cti * p.B + grp * G + inst);
-          else *p.error_flag = 1u;
+          if (cti < p.ct_capacity) {
+            unsigned long long cpos = ct_pos0 + (r.w & 0xFFFFFFu);
+            if (p.ct_ring && cpos >= p.ct_ring) cpos -= p.ct_ring;
+            ct = __ldcg(ct_out + (size_t)cpos * p.ct_pos_stride);  // L2 only: ring positions are rewritten
+          } else {
+            *p.error_flag = 1u;
+          }
           sts128(lab_s + sc * SLOT_B, degarble_nonfree<HASH>(te, type, ct, la, va, lb, gid));
           sts8(sval_s + sc * G, gate_value(type, va, vb));
         }
@@ -703,7 +732,8 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
       p.labels[gi] = lab[s * G + inst];
       if (MODE == 1) p.vals[gi] = sval[s * G + inst];
     }
-    __threadfence();
+    if (p.ct_sys) __threadfence_system();  // ciphertexts stored to a peer's ring are ordered before the flags
+    else __threadfence();
     named_bar(bar_id, NT);
     lap(PROF_SCATTER);
     sched_complete_cta(p, call_i, grp, wt, NT, keep);
@@ -724,20 +754,25 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
 // small) whose slots are recycled by emission-order liveness.  This is the throughput mode for
 // cut-and-choose batches of hundreds to thousands of instances; k_engine (levelised, labels in
 // shared memory) is the latency mode for small batches.
+// 512 threads per CTA (16 worker warps, 128 registers per thread): with 1024 threads the 64-register budget
+// spilled 200+ bytes per thread, and kernels with local memory make a first launch resize the context's
+// local-memory pool, which synchronises the device -- a dead-lock when another session's persistent
+// kernel on the same GPU is waiting for this one (linked garbler / evaluator).
+constexpr uint32_t LANE_WARPS = 16;
 template <int HASH, int MODE>
-__global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
+__global__ void __launch_bounds__(32 * LANE_WARPS, 1) k_lane(const EngineParams p) {
   extern __shared__ uint4 smem[];
   uint32_t* te = reinterpret_cast<uint32_t*>(smem);
   load_tables(te, threadIdx.x, blockDim.x);
   __syncthreads();
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-  if (MODE == 0 && blockIdx.x >= gridDim.x - p.n_chain_ctas) {
+  if (blockIdx.x >= gridDim.x - p.n_chain_ctas) {
     // chain CTA (see k_engine): dedicated SMs for the serial commitment
-    if (p.ct_ring && blockIdx.x == gridDim.x - p.n_chain_ctas && warp == (blockDim.x >> 5) - 1) {
+    if (p.flow_control && blockIdx.x == gridDim.x - p.n_chain_ctas && warp == (blockDim.x >> 5) - 1) {
       governor_warp(p);
     } else if (p.host_chain) {
       if (warp == 0) publish_warp(p);
-    } else if (warp < p.n_chain_warps) {
+    } else if (MODE == 0 && warp < p.n_chain_warps) {
       chain_warp(p, te, (blockIdx.x - (gridDim.x - p.n_chain_ctas)) * p.n_chain_warps + warp);
     }
     return;
@@ -758,7 +793,7 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
         if (lane == 0) item = sched_pop(p, n_items);
         item = __shfl_sync(FULL, item, 0);
       }
-      if (item == SCHED_DONE || MODE != 0 || !p.ct_ring) break;
+      if (item == SCHED_DONE || !p.flow_control) break;
       uint32_t ok = 0;
       if (lane == 0) ok = sched_ring_admit(p, item) ? 1u : 0u;
       if (__shfl_sync(FULL, ok, 0)) break;
@@ -851,7 +886,9 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
             const unsigned long long cti = call.ct_base + __shfl_sync(FULL, rec.w, j);
             uint4 ct = make_uint4(0, 0, 0, 0);
             if (cti < p.ct_capacity) {
-              if (act) ct = __ldcs(p.ct + (size_t)cti * p.B + instance);
+              unsigned long long pos = ct_pos0 + __shfl_sync(FULL, rec.w, j);
+              if (p.ct_ring && pos >= p.ct_ring) pos -= p.ct_ring;
+              if (act) ct = __ldcg(ct_out + (size_t)pos * p.ct_pos_stride);
             } else if (lane == 0) {
               *p.error_flag = 1u;
             }
@@ -879,7 +916,8 @@ __global__ void __launch_bounds__(1024, 1) k_lane(const EngineParams p) {
         if (MODE == 1) wval[(size_t)gs * 32u] = myv[s * 32u];
       }
     }
-    __threadfence();
+    if (p.ct_sys) __threadfence_system();
+    else __threadfence();
     __syncwarp();
     kept = sched_complete_warp(p, call_i, grp, lane);
   }

@@ -3,11 +3,13 @@
 #include "gsv_cuda.h"
 
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <chrono>
 #include <thread>
 #include <atomic>
@@ -85,6 +87,50 @@ struct AesTables {
   }
 };
 
+// CUDA loads kernels lazily, and loading one may synchronise the context.  Sessions that share a GPU run
+// persistent kernels which wait for each other's progress (linked garbler / evaluator), so a first-use load
+// behind a running kernel can dead-lock: every kernel of the library is loaded when a device is first used.
+int g_smem_optin = 0;  // the device's opt-in shared memory per block
+template <typename K>
+void preload(K kernel) {
+  cudaFuncAttributes a;
+  CUDA_TRY(cudaFuncGetAttributes(&a, kernel));
+  // the dynamic shared-memory opt-in is set here, once, for the same reason: changing a function's
+  // attributes can reconfigure the SMs' shared-memory carve-out, which waits for running kernels
+  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin - (int)a.sharedSizeBytes));
+}
+template <int G>
+void preload_engine() {
+  preload(k_engine<G, HASH_AES, 0>);
+  preload(k_engine<G, HASH_AES, 1>);
+  preload(k_engine<G, HASH_BLAKE3, 0>);
+  preload(k_engine<G, HASH_BLAKE3, 1>);
+}
+void preload_kernels() {
+  preload_engine<1>();
+  preload_engine<2>();
+  preload_engine<4>();
+  preload_engine<8>();
+  preload(k_lane<HASH_AES, 0>);
+  preload(k_lane<HASH_AES, 1>);
+  preload(k_lane<HASH_BLAKE3, 0>);
+  preload(k_lane<HASH_BLAKE3, 1>);
+  preload(k_sched_init);
+  preload(k_seed_expand<0>);
+  preload(k_chain<0>);
+  preload(k_gather_slots<0>);
+  preload(k_scatter_inputs<0>);
+  preload(k_ct_extract<0>);
+  preload(k_ct_insert<0>);
+  preload(k_commit_labels<0>);
+  preload(k_hash_blocks<HASH_AES>);
+  preload(k_hash_blocks<HASH_BLAKE3>);
+  preload(k_bench_hash<HASH_AES>);
+  preload(k_bench_hash<HASH_BLAKE3>);
+  preload(k_hash_latency<HASH_AES>);
+  preload(k_hash_latency<HASH_BLAKE3>);
+}
+
 bool g_tables_loaded[64] = {false};
 void ensure_device(int device) {
   int n = 0;
@@ -96,6 +142,8 @@ void ensure_device(int device) {
     static const AesTables T;
     CUDA_TRY(cudaMemcpyToSymbol(c_te0, T.te0, sizeof(T.te0)));
     CUDA_TRY(cudaMemcpyToSymbol(c_rk, T.rk, sizeof(T.rk)));
+    CUDA_TRY(cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    preload_kernels();
     g_tables_loaded[device] = true;
   }
 }
@@ -498,6 +546,31 @@ int64_t gsv_program_flat_stream(const gsv_program* p, uint8_t* type, uint32_t* a
 }  // extern "C"
 
 // =============================================================================== session
+// Garbler -> evaluator streaming (gsv_session_link): a ciphertext ring in the evaluator's device memory that the
+// garbler's kernel fills (peer stores over NVLink when the sessions sit on two GPUs) and three progress words in
+// mapped host memory, each in its own cache line.
+struct gsv_link {
+  int dev_g = 0, dev_e = 0;
+  uint4* ring = nullptr;            // on dev_e, layout [instance quad][position][4]
+  uint64_t ring_positions = 0;      // 0: the whole stream fits (no wrap)
+  uint64_t cap = 0;                 // positions per instance in the buffer
+  unsigned long long* words = nullptr;  // mapped + portable host memory, 4 x 64 bytes:
+  //   words[0]  stream positions the garbler has completed        (garbler's publisher warp writes)
+  //   words[8]  stream positions the evaluate kernel has consumed (evaluator's publisher warp writes)
+  //   words[16] stream positions the garbler may overwrite        (evaluator's host thread writes)
+  unsigned long long *ready_g = nullptr, *release_g = nullptr;   // device views for the garbler's GPU
+  unsigned long long *ready_e = nullptr, *done_e = nullptr;      // device views for the evaluator's GPU
+  std::atomic<uint64_t> runs_started{0}, runs_consumed{0};
+  std::atomic<bool> failed{false};
+  ~gsv_link() {
+    if (ring) {
+      cudaSetDevice(dev_e);
+      cudaFree(ring);
+    }
+    if (words) cudaFreeHost(words);
+  }
+};
+
 struct gsv_session {
   const gsv_program* prog = nullptr;
   int device = 0;
@@ -522,6 +595,11 @@ struct gsv_session {
   // instance state
   DevBuf<uint4> d_labels, d_delta, d_ct, d_commit, d_io, d_stage;
   DevBuf<uint8_t> d_vals, d_io_bits;
+  // result / input staging, allocated once: cudaMalloc / cudaFree in a call would synchronise the device,
+  // i.e. wait for the persistent kernels of the other sessions sharing the GPU
+  DevBuf<uint32_t> d_gather_slots;   // 0, 1, 2 .. 2 + n_inputs (constants, inputs)
+  DevBuf<uint4> d_ev_true, d_ev_false, d_ev_in;
+  DevBuf<uint8_t> d_ev_bits;
   DevBuf<uint32_t> d_flags, d_ctrl;  // d_ctrl[1] = error flag, [4..6] = scheduler head / tail / completed
   DevBuf<uint32_t> d_succ_off, d_succ, d_pending;
   DevBuf<unsigned long long> d_queue, d_limit;
@@ -539,6 +617,9 @@ struct gsv_session {
   DevBuf<uint16_t> d_seq_in_slot, d_seq_out_slot;
   DevBuf<uint8_t> d_scratch_vals;
   bool ct_valid = false;
+  std::vector<int> ct_sink_fds;    // gsv_session_set_ciphertext_files: gc_{i}.bin writers fed by the host drain
+  std::shared_ptr<gsv_link> link;  // gsv_session_link: this session is one end of a garbler -> evaluator stream
+  bool link_garbler = false;
   // GSV_CT_COMMIT_HOST: ring drained to pinned host buffers, chains folded by AES-NI threads
   static constexpr int HC_BUFS = 4;
   cudaStream_t copy_stream = nullptr;
@@ -642,6 +723,35 @@ void upload_program(gsv_session* s) {
   s->d_output_slots.upload(os);
 }
 
+// everything gsv_evaluate_batch needs on the device besides the ciphertexts
+void ensure_eval_buffers(gsv_session* s) {
+  const gsv::Program& g = s->prog->prog;
+  const size_t B = s->B, n_in = g.n_inputs, n_out = g.output_slots.size();
+  if (s->d_vals.n < (size_t)s->B_pad * g.n_global_slots) s->d_vals.alloc((size_t)s->B_pad * g.n_global_slots);
+  if (s->d_ev_true.n < B) {
+    s->d_ev_true.alloc(B);
+    s->d_ev_false.alloc(B);
+    s->d_ev_in.alloc(std::max<size_t>(B * n_in, 1));
+    s->d_ev_bits.alloc(std::max<size_t>(B * n_in, 1));
+  }
+  if (s->d_io_bits.n < B * std::max<size_t>(n_out, 1)) s->d_io_bits.alloc(B * std::max<size_t>(n_out, 1));
+}
+
+// pinned drain buffers, copy stream and the mapped progress word of the host-folded chain
+void ensure_host_chain_resources(gsv_session* s) {
+  if (s->copy_stream) return;
+  CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  s->hc_buf_bytes = 64u << 20;
+  if (const char* e = getenv("GSV_HOST_CHAIN_BUF_MB")) s->hc_buf_bytes = (size_t)std::max(1, atoi(e)) << 20;
+  for (int b = 0; b < gsv_session::HC_BUFS; b++) {
+    CUDA_TRY(cudaEventCreateWithFlags(&s->hc_ev[b], cudaEventDisableTiming));
+    CUDA_TRY(cudaHostAlloc((void**)&s->hc_buf[b], s->hc_buf_bytes, cudaHostAllocDefault));
+  }
+  CUDA_TRY(cudaHostAlloc((void**)&s->hc_ready, 64, cudaHostAllocMapped));
+  CUDA_TRY(cudaHostGetDevicePointer((void**)&s->hc_ready_dev, s->hc_ready, 0));
+  CUDA_TRY(cudaHostAlloc((void**)&s->hc_consumed, 8 * gsv_session::HC_BUFS, cudaHostAllocDefault));
+}
+
 EngineParams make_params(gsv_session* s) {
   EngineParams p;
   memset(&p, 0, sizeof(p));
@@ -700,6 +810,9 @@ EngineParams make_params(gsv_session* s) {
   }
   p.host_ready = s->hc_ready_dev;
   p.prof = s->d_prof.p;
+  p.flow_control = s->ct_ring ? 1u : 0u;  // garbling into a ring: admit items against the consumers' progress
+  p.limit_add = p.free_until = s->ct_ring;
+  p.flow_total = s->prog->prog.total_ct;
   return p;
 }
 
@@ -717,10 +830,8 @@ void launch_engine(gsv_session* s, int hasher, const EngineParams& p) {
   if (s->lane_mode) {
     dim3 lgrid(s->sm_count), lblock(32 * s->n_workers);
     if (hasher == GSV_HASH_AES) {
-      CUDA_TRY(cudaFuncSetAttribute(k_lane<HASH_AES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
       k_lane<HASH_AES, MODE><<<lgrid, lblock, AES_TABLE_BYTES, s->stream>>>(p);
     } else if (hasher == GSV_HASH_BLAKE3) {
-      CUDA_TRY(cudaFuncSetAttribute(k_lane<HASH_BLAKE3, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
       k_lane<HASH_BLAKE3, MODE><<<lgrid, lblock, AES_TABLE_BYTES, s->stream>>>(p);
     } else {
       throw std::runtime_error("unknown hasher");
@@ -732,8 +843,6 @@ void launch_engine(gsv_session* s, int hasher, const EngineParams& p) {
   dim3 grid(s->sm_count), block(std::max<uint32_t>(s->n_workers * s->NT, 32 * (p.n_chain_warps + (p.n_chain_ctas ? 1 : 0))));  // + governor warp
 #define GSV_LAUNCH(GG, HH)                                                                              \
   do {                                                                                                  \
-    CUDA_TRY(cudaFuncSetAttribute(k_engine<GG, HH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                  (int)smem));                                                          \
     k_engine<GG, HH, MODE><<<grid, block, smem, s->stream>>>(p);                                        \
   } while (0)
 #define GSV_LAUNCH_G(HH)                         \
@@ -763,7 +872,21 @@ struct HostChainStats {
   double drain_wait_ready = 0;  // drain loop: share of the run spent waiting for the kernel to publish data
   double drain_wait_slot = 0;   // ... waiting for a host buffer the fold threads still hold
 };
-void run_host_chain(gsv_session* s, uint8_t* commits, HostChainStats* stats) {
+// What the drain loop works on.  Garbling with GSV_CT_COMMIT_HOST: the session's own ring, published by its
+// own kernel, ring space returned through a device word (stream-ordered copy behind each drain).  A linked
+// evaluator: the link's ring (written by the garbler's GPU), published by the garbler, ring space returned
+// through the link's release word = min(drained, consumed by the evaluate kernel).
+struct DrainSource {
+  const uint4* ring = nullptr;       // device pointer, layout [instance quad][position][4]
+  uint64_t cap = 0;                  // positions per instance in the buffer
+  uint64_t ring_positions = 0;       // 0: the whole stream is resident (no wrap)
+  const volatile unsigned long long* ready = nullptr;  // host-visible: stream positions complete
+  cudaStream_t watch = nullptr;      // a kernel whose failure (or end before `total`) aborts the drain; may be null
+  unsigned long long* dev_progress = nullptr;          // device word to advance behind every drain copy (or null)
+  std::atomic<uint64_t>* copied_done = nullptr;        // out: positions whose copy has completed (or null)
+  std::function<bool()> tick;        // called every loop iteration; return false to abort (or empty)
+};
+void run_host_chain(gsv_session* s, const DrainSource& src, uint8_t* commits, HostChainStats* stats) {
   const auto t_run0 = std::chrono::steady_clock::now();
   auto secs = [](std::chrono::steady_clock::duration d) { return std::chrono::duration<double>(d).count(); };
   std::vector<double> busy(64, 0.0);
@@ -773,13 +896,13 @@ void run_host_chain(gsv_session* s, uint8_t* commits, HostChainStats* stats) {
   const uint64_t total = g.total_ct;
   const size_t row_bytes = (size_t)nq * 64;
   const uint64_t chunk_pos = std::max<uint64_t>(1, s->hc_buf_bytes / row_bytes);
-  const uint64_t cap = s->d_ct.n / ((size_t)nq * 4);  // device ring (or whole stream) positions per instance
+  const uint64_t cap = src.cap, ring = src.ring_positions;
   constexpr int NB = gsv_session::HC_BUFS;
   const uint32_t T = std::max<uint32_t>(1, std::min(s->host_threads, nq));
   std::vector<uint8_t> h((size_t)nq * 64, 0);
   std::atomic<uint64_t> slot_job[NB];   // 1 + index of the job whose copy was enqueued into the slot
   std::atomic<uint64_t> slot_done[NB];  // hasher completions on the slot, over all jobs
-  uint64_t slot_npos[NB] = {0, 0, 0, 0};
+  uint64_t slot_npos[NB] = {0, 0, 0, 0}, slot_end[NB] = {0, 0, 0, 0};
   for (int b = 0; b < NB; b++) {
     slot_job[b].store(0);
     slot_done[b].store(0);
@@ -787,6 +910,9 @@ void run_host_chain(gsv_session* s, uint8_t* commits, HostChainStats* stats) {
   std::atomic<int64_t> n_jobs{-1};
   std::atomic<bool> abort{false};
   const auto nap = [] { std::this_thread::sleep_for(std::chrono::microseconds(50)); };
+  std::atomic<bool> sink_failed{false};
+  std::vector<uint8_t> sink_buf;  // sized before the threads start: one run of a chunk's records per fold thread
+  if (!s->ct_sink_fds.empty()) sink_buf.resize((size_t)T * chunk_pos * 16);
   auto hasher = [&](uint32_t t) {
     const uint32_t q0 = (uint32_t)((uint64_t)nq * t / T), q1 = (uint32_t)((uint64_t)nq * (t + 1) / T);
     cudaSetDevice(s->device);
@@ -801,11 +927,35 @@ void run_host_chain(gsv_session* s, uint8_t* commits, HostChainStats* stats) {
         abort.store(true);
         return;
       }
+      if (t == 0 && src.copied_done) src.copied_done->store(slot_end[b], std::memory_order_release);  // jobs are in stream order
       if (q1 > q0) {
         const auto t0 = std::chrono::steady_clock::now();
         gsv::host_chain_fold_quads(h.data() + (size_t)q0 * 64, s->hc_buf[b] + (size_t)q0 * chunk_pos * 64, chunk_pos * 64,
                                    slot_npos[b], q1 - q0);
         busy[t % busy.size()] += secs(std::chrono::steady_clock::now() - t0);
+      }
+      if (!s->ct_sink_fds.empty() && q1 > q0) {
+        // gc_{i}.bin (ciphertext_repository.rs:94-106): the drained rows are [quad][position][4 chains]; each chain's
+        // 16-byte records are gathered into a contiguous run and written at their stream offset
+        const uint64_t n = slot_npos[b], first = slot_end[b] - n;
+        uint8_t* out = sink_buf.data() + (size_t)t * chunk_pos * 16;
+        for (uint32_t q = q0; q < q1 && !abort.load(); q++)
+          for (uint32_t j = 0; j < 4 && 4 * q + j < B; j++) {
+            const int fd = s->ct_sink_fds[4 * q + j];
+            if (fd < 0) continue;
+            const uint8_t* in = s->hc_buf[b] + (size_t)q * chunk_pos * 64 + 16 * j;
+            for (uint64_t k = 0; k < n; k++) memcpy(out + 16 * k, in + 64 * k, 16);
+            size_t off = 0;
+            while (off < n * 16) {
+              const ssize_t wr = pwrite(fd, out + off, n * 16 - off, (off_t)(first * 16 + off));
+              if (wr <= 0) {
+                sink_failed.store(true);
+                abort.store(true);
+                break;
+              }
+              off += (size_t)wr;
+            }
+          }
       }
       slot_done[b].fetch_add(1, std::memory_order_release);
     }
@@ -817,25 +967,26 @@ void run_host_chain(gsv_session* s, uint8_t* commits, HostChainStats* stats) {
     uint64_t copied = 0, jobs = 0;
     auto last_query = std::chrono::steady_clock::now();
     while (copied < total) {
-      const uint64_t ready = *reinterpret_cast<volatile unsigned long long*>(s->hc_ready);
+      if (src.tick && !src.tick()) throw std::runtime_error("the linked session failed");
+      const uint64_t ready = *src.ready;
       uint64_t n = ready > copied ? std::min<uint64_t>(ready - copied, chunk_pos) : 0;
       uint64_t pos = copied;
-      if (s->ct_ring) {
-        pos = copied % s->ct_ring;
-        n = std::min<uint64_t>(n, s->ct_ring - pos);
+      if (ring) {
+        pos = copied % ring;
+        n = std::min<uint64_t>(n, ring - pos);
       }
       // small drains waste DMA launches: unless the stream or the ring ends, wait for half a buffer (or a
-      // quarter of a small ring: the kernel stalls once the ring is full, so never wait for more than it holds)
+      // quarter of a small ring: the producer stalls once the ring is full, so never wait for more than it holds)
       uint64_t thresh = chunk_pos / 2;
-      if (s->ct_ring) thresh = std::min<uint64_t>(thresh, std::max<uint64_t>(1, s->ct_ring / 4));
-      const bool worth = n > 0 && (n >= thresh || copied + n == total || (s->ct_ring && pos + n == s->ct_ring));
+      if (ring) thresh = std::min<uint64_t>(thresh, std::max<uint64_t>(1, ring / 4));
+      const bool worth = n > 0 && (n >= thresh || copied + n == total || (ring && pos + n == ring));
       if (!worth) {
         auto now = std::chrono::steady_clock::now();
-        if (now - last_query > std::chrono::milliseconds(5)) {
+        if (src.watch && now - last_query > std::chrono::milliseconds(5)) {
           last_query = now;
-          cudaError_t q = cudaStreamQuery(s->stream);
-          if (q != cudaSuccess && q != cudaErrorNotReady) throw std::runtime_error(std::string("garbling kernel failed: ") + cudaGetErrorString(q));
-          if (q == cudaSuccess && *reinterpret_cast<volatile unsigned long long*>(s->hc_ready) < total)
+          cudaError_t q = cudaStreamQuery(src.watch);
+          if (q != cudaSuccess && q != cudaErrorNotReady) throw std::runtime_error(std::string("kernel failed: ") + cudaGetErrorString(q));
+          if (q == cudaSuccess && *src.ready < total && !src.tick)
             throw std::runtime_error("garbling kernel ended before the stream was complete");
         }
         nap();
@@ -847,34 +998,47 @@ void run_host_chain(gsv_session* s, uint8_t* commits, HostChainStats* stats) {
         const auto t0 = std::chrono::steady_clock::now();
         while (slot_done[b].load(std::memory_order_acquire) != (uint64_t)T * (jobs / NB)) {
           if (abort.load()) throw std::runtime_error("host chain thread failed");
+          if (src.tick && !src.tick()) throw std::runtime_error("the linked session failed");
           nap();
         }
         wait_slot += secs(std::chrono::steady_clock::now() - t0);
       }
-      CUDA_TRY(cudaMemcpy2DAsync(s->hc_buf[b], (size_t)chunk_pos * 64, s->d_ct.p + pos * 4, (size_t)cap * 64, (size_t)n * 64, nq,
+      CUDA_TRY(cudaMemcpy2DAsync(s->hc_buf[b], (size_t)chunk_pos * 64, src.ring + pos * 4, (size_t)cap * 64, (size_t)n * 64, nq,
                                  cudaMemcpyDeviceToHost, s->copy_stream));
-      s->hc_consumed[b] = copied + n;
-      CUDA_TRY(cudaMemcpyAsync(s->d_progress.p, s->hc_consumed + b, 8, cudaMemcpyHostToDevice, s->copy_stream));
+      if (src.dev_progress) {
+        s->hc_consumed[b] = copied + n;
+        CUDA_TRY(cudaMemcpyAsync(src.dev_progress, s->hc_consumed + b, 8, cudaMemcpyHostToDevice, s->copy_stream));
+      }
       CUDA_TRY(cudaEventRecord(s->hc_ev[b], s->copy_stream));
       slot_npos[b] = n;
+      slot_end[b] = copied + n;
       slot_job[b].store(jobs + 1, std::memory_order_release);
       jobs++;
       copied += n;
     }
     n_jobs.store((int64_t)jobs, std::memory_order_release);
+    // the last copies: keep the release word moving until the fold threads have seen them
+    if (src.tick)
+      while (src.copied_done && src.copied_done->load(std::memory_order_acquire) < total && !abort.load()) {
+        if (!src.tick()) throw std::runtime_error("the linked session failed");
+        nap();
+      }
   } catch (const std::exception& e) {
     err = e.what();
     abort.store(true);
   }
   for (auto& t : threads) t.join();
+  if (err.empty() && sink_failed.load()) err = "writing a ciphertext file failed";
   if (err.empty() && abort.load()) err = "host chain thread failed";
   if (!err.empty()) {
     // unblock the persistent kernel before reporting: with a ring its workers park behind the progress
     // word nobody advances any more; "everything consumed" lets it run to completion
-    s->hc_consumed[0] = ~0ull >> 1;
-    cudaMemcpyAsync(s->d_progress.p, s->hc_consumed, 8, cudaMemcpyHostToDevice, s->copy_stream);
-    cudaStreamSynchronize(s->copy_stream);
-    cudaStreamSynchronize(s->stream);
+    if (src.dev_progress) {
+      s->hc_consumed[0] = ~0ull >> 1;
+      cudaMemcpyAsync(src.dev_progress, s->hc_consumed, 8, cudaMemcpyHostToDevice, s->copy_stream);
+      cudaStreamSynchronize(s->copy_stream);
+      cudaStreamSynchronize(s->stream);
+    }
     throw std::runtime_error(err);
   }
   for (uint32_t i = 0; i < B; i++) memcpy(commits + (size_t)i * 16, h.data() + (size_t)i * 16, 16);
@@ -923,7 +1087,7 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
     uint32_t n_chain = 0;  // chain warps per chain CTA
     s->n_chain_ctas = 0;
     if (chain_warps_total) {
-      // the lane kernel runs 1024-thread CTAs (16 chain warps + the governor warp), the levelised kernel 512
+      // both persistent kernels run 512-thread CTAs: at most 15 chain warps + the governor warp
       uint32_t per_cta = 15;
       if (const char* e = getenv("GSV_CHAIN_WARPS_PER_SM")) per_cta = std::max(1, std::min(15, atoi(e)));  // + 1 governor warp
       n_chain = std::min(per_cta, chain_warps_total);
@@ -935,8 +1099,10 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
       if (!gsv::host_chain_available()) throw std::runtime_error("GSV_CT_COMMIT_HOST needs a host CPU with AES-NI");
       n_chain = 1;  // one publisher warp on one trailing CTA
       s->n_chain_ctas = 1;
-      // fold threads: one per quad of chains up to half the hardware threads (the SMT siblings share the
-      // AES units); callers that run several sessions or ranks per host pass their share explicitly
+    }
+    {
+      // host fold threads (GSV_CT_COMMIT_HOST, linked evaluators): one per quad of chains up to half the hardware
+      // threads; callers that run several sessions or ranks per host pass their share explicitly
       unsigned hw = std::thread::hardware_concurrency();
       if (hw == 0) hw = 4;
       s->host_threads = opt->host_threads ? opt->host_threads : std::max(1u, hw / 2);
@@ -962,7 +1128,7 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
     if (s->lane_mode) {
       G = 32;
       s->NT = 32;
-      n_workers = 32;
+      n_workers = LANE_WARPS;
       s->B_pad = (s->B + 31) / 32 * 32;
       s->n_groups = s->B_pad / 32;
       s->scratch_stride = std::max<uint32_t>(g.max_task_seq_slots, 4);
@@ -986,18 +1152,7 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
     s->n_chain_warps = n_chain;
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto& e : s->ev) CUDA_TRY(cudaEventCreate(&e));
-    if (s->ct_mode == GSV_CT_COMMIT_HOST) {
-      CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-      s->hc_buf_bytes = 64u << 20;
-      if (const char* e = getenv("GSV_HOST_CHAIN_BUF_MB")) s->hc_buf_bytes = (size_t)std::max(1, atoi(e)) << 20;
-      for (int b = 0; b < gsv_session::HC_BUFS; b++) {
-        CUDA_TRY(cudaEventCreateWithFlags(&s->hc_ev[b], cudaEventDisableTiming));
-        CUDA_TRY(cudaHostAlloc((void**)&s->hc_buf[b], s->hc_buf_bytes, cudaHostAllocDefault));
-      }
-      CUDA_TRY(cudaHostAlloc((void**)&s->hc_ready, 64, cudaHostAllocMapped));
-      CUDA_TRY(cudaHostGetDevicePointer((void**)&s->hc_ready_dev, s->hc_ready, 0));
-      CUDA_TRY(cudaHostAlloc((void**)&s->hc_consumed, 8 * gsv_session::HC_BUFS, cudaHostAllocDefault));
-    }
+    if (s->ct_mode == GSV_CT_COMMIT_HOST) ensure_host_chain_resources(s.get());
     upload_program(s.get());
     s->d_labels.alloc((size_t)s->B_pad * g.n_global_slots);
     s->d_delta.alloc(s->B_pad);
@@ -1009,6 +1164,12 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
     }
     s->d_commit.alloc(s->B);
     s->d_seeds.alloc(s->B);
+    {
+      std::vector<uint32_t> gs(2 + g.n_inputs);
+      for (size_t i = 0; i < gs.size(); i++) gs[i] = (uint32_t)i;
+      s->d_gather_slots.upload(gs);
+      s->d_io.alloc((size_t)s->B * std::max<size_t>({(size_t)g.n_inputs, g.output_slots.size(), (size_t)1}));
+    }
     s->d_flags.alloc((size_t)g.calls.size() * s->n_groups + 1);
     CUDA_TRY(cudaMemset(s->d_flags.p, 0, s->d_flags.n * 4));
     s->d_ctrl.alloc(8);
@@ -1073,6 +1234,74 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
   }
 }
 
+int gsv_session_link(gsv_session* garbler, gsv_session* evaluator, uint64_t ring_bytes) {
+  if (!garbler || !evaluator || garbler == evaluator) return fail(GSV_ERR_INVALID, "need two distinct sessions");
+  if (garbler->prog != evaluator->prog || garbler->B != evaluator->B)
+    return fail(GSV_ERR_INVALID, "linked sessions must share the program and the batch size");
+  if (garbler->link || evaluator->link) return fail(GSV_ERR_INVALID, "session already linked");
+  if (!gsv::host_chain_available()) return fail(GSV_ERR_INVALID, "the evaluator hashes the stream with host AES-NI threads");
+  try {
+    const gsv::Program& g = garbler->prog->prog;
+    const uint32_t B = garbler->B;
+    const uint64_t nq = (B + 3) / 4, total = std::max<uint64_t>(g.total_ct, 1);
+    auto link = std::make_shared<gsv_link>();
+    link->dev_g = garbler->device;
+    link->dev_e = evaluator->device;
+    if (link->dev_g != link->dev_e) {
+      int can = 0;
+      CUDA_TRY(cudaDeviceCanAccessPeer(&can, link->dev_g, link->dev_e));
+      if (!can) throw std::runtime_error("the garbler's GPU cannot store to the evaluator's GPU (no peer access)");
+      CUDA_TRY(cudaSetDevice(link->dev_g));
+      cudaError_t e = cudaDeviceEnablePeerAccess(link->dev_e, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_TRY(e);
+      cudaGetLastError();
+    }
+    CUDA_TRY(cudaSetDevice(link->dev_e));
+    uint64_t max_task_ct = 1;
+    for (const auto& t : g.tasks) max_task_ct = std::max<uint64_t>(max_task_ct, t.n_ct);
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    uint64_t budget = (uint64_t)(free_b * 0.85);
+    if (ring_bytes) budget = std::min<uint64_t>(budget, ring_bytes);
+    uint64_t ring = std::max<uint64_t>(budget / (nq * 64), 1);
+    if (ring >= total) {
+      link->ring_positions = 0;
+      link->cap = total;
+    } else {
+      if (ring < 2 * max_task_ct) throw std::runtime_error("ciphertext ring smaller than two tasks");
+      link->ring_positions = link->cap = ring;
+    }
+    CUDA_TRY(cudaMalloc(&link->ring, (size_t)link->cap * nq * 64));
+    CUDA_TRY(cudaHostAlloc((void**)&link->words, 4 * 64, cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(link->words, 0, 4 * 64);
+    unsigned long long* dv = nullptr;
+    CUDA_TRY(cudaHostGetDevicePointer((void**)&dv, link->words, 0));
+    link->ready_e = dv;
+    link->done_e = dv + 8;
+    CUDA_TRY(cudaSetDevice(link->dev_g));
+    CUDA_TRY(cudaHostGetDevicePointer((void**)&dv, link->words, 0));
+    link->ready_g = dv;
+    link->release_g = dv + 16;
+    // both ends schedule against a progress word: parking lists (the evaluator always, the garbler with a ring)
+    const uint64_t park_ring = link->ring_positions ? link->ring_positions : total;
+    for (gsv_session* s : {garbler, evaluator}) {
+      CUDA_TRY(cudaSetDevice(s->device));
+      s->park_q = std::max<uint64_t>(park_ring / 64, 1);
+      s->d_park_head.alloc((size_t)(total / s->park_q + 2));
+      s->d_park_next.alloc(std::max<size_t>(g.calls.size() * (size_t)s->n_groups, 1));
+    }
+    CUDA_TRY(cudaSetDevice(link->dev_e));
+    ensure_host_chain_resources(evaluator);
+    ensure_eval_buffers(evaluator);
+    garbler->link = evaluator->link = link;
+    garbler->link_garbler = true;
+    evaluator->link_garbler = false;
+    return GSV_OK;
+  } catch (const std::exception& e) {
+    return fail(GSV_ERR_CUDA, e.what());
+  }
+}
+
 void gsv_session_destroy(gsv_session* s) {
   if (s) cudaSetDevice(s->device);
   delete s;
@@ -1110,6 +1339,33 @@ int gsv_garble_batch(gsv_session* s, int hasher, const uint64_t* seeds, gsv_garb
       *reinterpret_cast<volatile unsigned long long*>(s->hc_ready) = 0;
       CUDA_TRY(cudaMemsetAsync(s->d_progress.p, 0, 8, s->stream));
     }
+    const bool linked = s->link && s->link_garbler;
+    if (linked) {
+      // ciphertexts go to the ring in the evaluator's memory; the publisher warp announces the finished frontier,
+      // the evaluator's host thread returns ring space through the release word
+      gsv_link& L = *s->link;
+      volatile unsigned long long* w = L.words;
+      w[0] = w[8] = w[16] = 0;
+      std::atomic_thread_fence(std::memory_order_seq_cst);
+      L.failed.store(false);
+      L.runs_started.fetch_add(1);
+      if (getenv("GSV_LINK_DEBUG")) fprintf(stderr, "[link] garbler: launching\n");
+      p.ct = L.ring;
+      p.ct_ring = L.ring_positions;
+      p.ct_pos_stride = 4;
+      p.ct_quad_stride = L.cap * 4;
+      p.ct_qshift = 2;
+      p.write_ct = 1;
+      p.host_chain = 1;
+      p.host_ready = L.ready_g;
+      p.flow_control = L.ring_positions ? 1u : 0u;
+      p.limit_add = p.free_until = L.ring_positions;
+      p.n_progress = 0;
+      p.ext_progress = L.release_g;
+      p.ct_sys = 1;
+      p.n_chain_warps = 1;
+      p.n_chain_ctas = 1;
+    }
     launch_engine<0>(s, hasher, p);
     launches += 2;  // k_sched_init + the persistent engine kernel
     CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
@@ -1118,7 +1374,14 @@ int gsv_garble_batch(gsv_session* s, int hasher, const uint64_t* seeds, gsv_garb
     if (s->ct_mode == GSV_CT_COMMIT_HOST) {
       host_commits.resize((size_t)B * 16);
       HostChainStats hs;
-      run_host_chain(s, host_commits.data(), &hs);  // returns when the last chain is folded
+      DrainSource src;
+      src.ring = s->d_ct.p;
+      src.cap = s->d_ct.n / ((size_t)((B + 3) / 4) * 4);
+      src.ring_positions = s->ct_ring;
+      src.ready = s->hc_ready;
+      src.watch = s->stream;
+      src.dev_progress = s->d_progress.p;
+      run_host_chain(s, src, host_commits.data(), &hs);  // returns when the last chain is folded
       res->host_fold_busy = (float)hs.fold_busy;
       res->host_drain_wait_kernel = (float)hs.drain_wait_ready;
       res->host_drain_wait_fold = (float)hs.drain_wait_slot;
@@ -1131,27 +1394,51 @@ int gsv_garble_batch(gsv_session* s, int hasher, const uint64_t* seeds, gsv_garb
     if (res->ct_commit && (s->ct_mode == GSV_CT_COMMIT || s->ct_mode == GSV_CT_KEEP))
       CUDA_TRY(cudaMemcpyAsync(res->ct_commit, s->d_commit.p, (size_t)B * 16, cudaMemcpyDeviceToHost, s->stream));
     if (res->ct_commit && s->ct_mode == GSV_CT_COMMIT_HOST) memcpy(res->ct_commit, host_commits.data(), host_commits.size());
-    auto gather = [&](const std::vector<uint32_t>& slots, uint8_t* host_out) {
-      if (!host_out || slots.empty()) return;
-      DevBuf<uint32_t> d_slots;
-      d_slots.upload(slots);
-      const size_t total = (size_t)B * slots.size();
-      if (s->d_io.n < total) s->d_io.alloc(total);
+    if (linked) {
+      // wait for the kernel; once the evaluator has given up, report instead of waiting for ever
+      std::chrono::steady_clock::time_point failed_at{};
+      for (;;) {
+        const cudaError_t q = cudaStreamQuery(s->stream);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) {
+          s->link->failed.store(true);
+          throw std::runtime_error(std::string("linked garbling kernel failed: ") + cudaGetErrorString(q));
+        }
+        if (s->link->failed.load()) {
+          const auto now = std::chrono::steady_clock::now();
+          if (failed_at == std::chrono::steady_clock::time_point{}) failed_at = now;
+          if (now - failed_at > std::chrono::seconds(10)) {
+            uint32_t sc[4] = {0, 0, 0, 0};
+            cudaStream_t aux;
+            cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking);
+            cudaMemcpyAsync(sc, s->d_ctrl.p + 4, 16, cudaMemcpyDeviceToHost, aux);
+            cudaStreamSynchronize(aux);
+            cudaStreamDestroy(aux);
+            volatile unsigned long long* w = s->link->words;
+            throw std::runtime_error("linked garbling kernel still running after the evaluator failed: published " + std::to_string(w[0]) +
+                                     ", release word " + std::to_string(w[16]) + ", queue head " + std::to_string(sc[0]) + " tail " +
+                                     std::to_string(sc[1]) + ", items completed " + std::to_string(sc[2]) + " of " +
+                                     std::to_string(g.calls.size() * (size_t)s->n_groups) + ", buckets released " + std::to_string(sc[3]));
+          }
+        }
+        std::this_thread::sleep_for(std::chrono::microseconds(200));
+      }
+    }
+    // labels of n consecutive entries of a device slot list -> host (staged through d_io)
+    auto gather = [&](const uint32_t* d_slots, size_t n, uint8_t* host_out) {
+      if (!host_out || n == 0) return;
+      const size_t total = (size_t)B * n;
       k_gather_slots<0><<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(
-          s->d_labels.p, nullptr, d_slots.p, (uint32_t)slots.size(), B, s->G, g.n_global_slots, s->d_io.p, nullptr);
+          s->d_labels.p, nullptr, d_slots, (uint32_t)n, B, s->G, g.n_global_slots, s->d_io.p, nullptr);
       CUDA_TRY(cudaGetLastError());
       launches++;
       CUDA_TRY(cudaMemcpyAsync(host_out, s->d_io.p, total * 16, cudaMemcpyDeviceToHost, s->stream));
       CUDA_TRY(cudaStreamSynchronize(s->stream));
     };
-    gather({0u}, res->false_label0);
-    gather({1u}, res->true_label0);
-    if (res->input_label0) {
-      std::vector<uint32_t> in(g.n_inputs);
-      for (uint32_t i = 0; i < g.n_inputs; i++) in[i] = 2 + i;
-      gather(in, res->input_label0);
-    }
-    gather(g.output_slots, res->output_label0);
+    gather(s->d_gather_slots.p, 1, res->false_label0);
+    gather(s->d_gather_slots.p + 1, 1, res->true_label0);
+    gather(s->d_gather_slots.p + 2, g.n_inputs, res->input_label0);
+    gather(s->d_output_slots.p, g.output_slots.size(), res->output_label0);
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     cudaEventElapsedTime(&res->ms_seed, s->ev[0], s->ev[1]);
     cudaEventElapsedTime(&res->ms_garble, s->ev[1], s->ev[2]);
@@ -1181,7 +1468,56 @@ int gsv_garble_batch(gsv_session* s, int hasher, const uint64_t* seeds, gsv_garb
     }
     res->n_ciphertexts = g.total_ct;
     res->n_launches = launches;
-    s->ct_valid = (s->ct_mode != GSV_CT_NONE);
+    s->ct_valid = (s->ct_mode != GSV_CT_NONE) && !linked;
+    return GSV_OK;
+  } catch (const std::exception& e) {
+    if (s->link) s->link->failed.store(true);
+    return fail(GSV_ERR_CUDA, e.what());
+  }
+}
+
+int gsv_session_set_ciphertext_files(gsv_session* s, const int* fds) {
+  if (!s) return fail(GSV_ERR_INVALID, "null argument");
+  if (!fds) {
+    s->ct_sink_fds.clear();
+    return GSV_OK;
+  }
+  if (s->ct_mode != GSV_CT_COMMIT_HOST && !(s->link && !s->link_garbler))
+    return fail(GSV_ERR_INVALID, "ciphertext files are written by the host drain: GSV_CT_COMMIT_HOST sessions and linked evaluators");
+  s->ct_sink_fds.assign(fds, fds + s->B);
+  return GSV_OK;
+}
+
+int gsv_session_expand_seeds(gsv_session* s, const uint64_t* seeds, gsv_garble_result* res) {
+  if (!s || !seeds || !res) return fail(GSV_ERR_INVALID, "null argument");
+  try {
+    CUDA_TRY(cudaSetDevice(s->device));
+    const gsv::Program& g = s->prog->prog;
+    const uint32_t B = s->B;
+    CUDA_TRY(cudaMemcpyAsync(s->d_seeds.p, seeds, (size_t)B * 8, cudaMemcpyHostToDevice, s->stream));
+    const uint32_t n_blocks = (3 + g.n_inputs + 3) / 4;
+    const size_t total = (size_t)B * n_blocks;
+    k_seed_expand<0><<<(unsigned)((total + 127) / 128), 128, 0, s->stream>>>(s->d_seeds.p, B, s->G, g.n_inputs, g.n_global_slots,
+                                                                              s->d_labels.p, s->d_delta.p);
+    CUDA_TRY(cudaGetLastError());
+    uint32_t launches = 1;
+    if (res->delta) CUDA_TRY(cudaMemcpyAsync(res->delta, s->d_delta.p, (size_t)B * 16, cudaMemcpyDeviceToHost, s->stream));
+    auto gather = [&](uint32_t first, uint32_t n, uint8_t* host_out) {
+      if (!host_out || n == 0) return;
+      const size_t cnt = (size_t)B * n;
+      k_gather_slots<0><<<(unsigned)((cnt + 255) / 256), 256, 0, s->stream>>>(s->d_labels.p, nullptr, s->d_gather_slots.p + first, n, B,
+                                                                              s->G, g.n_global_slots, s->d_io.p, nullptr);
+      CUDA_TRY(cudaGetLastError());
+      launches++;
+      CUDA_TRY(cudaMemcpyAsync(host_out, s->d_io.p, cnt * 16, cudaMemcpyDeviceToHost, s->stream));
+      CUDA_TRY(cudaStreamSynchronize(s->stream));
+    };
+    gather(0, 1, res->false_label0);
+    gather(1, 1, res->true_label0);
+    gather(2, g.n_inputs, res->input_label0);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    res->n_launches = launches;
+    res->n_ciphertexts = g.total_ct;
     return GSV_OK;
   } catch (const std::exception& e) {
     return fail(GSV_ERR_CUDA, e.what());
@@ -1219,7 +1555,11 @@ int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io) {
     if (n_in && (!io->input_active || !io->input_bits)) return fail(GSV_ERR_INVALID, "missing inputs");
     uint32_t launches = 0;
     uint64_t ct_avail = g.total_ct;
-    if (io->ct_streams) {
+    const bool linked = s->link && !s->link_garbler;
+    if (linked && getenv("GSV_LINK_DEBUG")) fprintf(stderr, "[link] evaluator: call entered\n");
+    if (linked) {
+      if (io->ct_streams) return fail(GSV_ERR_INVALID, "a linked evaluator takes its ciphertexts from the garbler session");
+    } else if (io->ct_streams) {
       // FileSource-style host streams: upload and interleave
       if (s->d_ct.n < (size_t)std::max<uint64_t>(g.total_ct, 1) * B) s->d_ct.alloc((size_t)std::max<uint64_t>(g.total_ct, 1) * B);
       ct_avail = std::min<uint64_t>(io->ct_stream_len, g.total_ct);
@@ -1236,14 +1576,10 @@ int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io) {
     } else if (!s->ct_valid || s->ct_ring || s->ct_mode == GSV_CT_COMMIT_HOST) {
       return fail(GSV_ERR_INVALID, "no ciphertext stream in the session (garble with GSV_CT_KEEP first)");
     }
-    if (s->d_vals.n < (size_t)s->B_pad * g.n_global_slots) s->d_vals.alloc((size_t)s->B_pad * g.n_global_slots);
+    ensure_eval_buffers(s);  // no-op after the first call (and done at link time for linked evaluators)
     // inputs -> device
-    DevBuf<uint4> d_true, d_false, d_in;
-    DevBuf<uint8_t> d_bits;
-    d_true.alloc(B);
-    d_false.alloc(B);
-    d_in.alloc(std::max<size_t>((size_t)B * n_in, 1));
-    d_bits.alloc(std::max<size_t>((size_t)B * n_in, 1));
+    DevBuf<uint4>&d_true = s->d_ev_true, &d_false = s->d_ev_false, &d_in = s->d_ev_in;
+    DevBuf<uint8_t>& d_bits = s->d_ev_bits;
     CUDA_TRY(cudaMemcpyAsync(d_true.p, io->true_label, (size_t)B * 16, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaMemcpyAsync(d_false.p, io->false_label, (size_t)B * 16, cudaMemcpyHostToDevice, s->stream));
     if (n_in) {
@@ -1263,13 +1599,125 @@ int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io) {
     CUDA_TRY(cudaEventRecord(s->ev[1], s->stream));
     EngineParams p = make_params(s);
     p.ct_capacity = ct_avail;
+    p.flow_control = 0;
+    p.ct_ring = 0;
+    std::vector<uint8_t> link_commits;
+    if (linked) {
+      // the ring is filled by the garbler's kernel; admit items against what it has published, publish what
+      // this kernel has consumed
+      gsv_link& L = *s->link;
+      const auto t_wait = std::chrono::steady_clock::now();
+      double start_limit_s = 60.0;
+      if (const char* e = getenv("GSV_LINK_TIMEOUT_S")) start_limit_s = std::max(1.0, atof(e));
+      while (L.runs_started.load() <= L.runs_consumed.load()) {  // the garbler resets the progress words first
+        if (L.failed.load() || std::chrono::duration<double>(std::chrono::steady_clock::now() - t_wait).count() > start_limit_s)
+          return fail(GSV_ERR_INVALID, "the linked garbler did not start (call gsv_garble_batch concurrently)");
+        std::this_thread::sleep_for(std::chrono::microseconds(100));
+      }
+      L.runs_consumed.fetch_add(1);
+      if (getenv("GSV_LINK_DEBUG")) fprintf(stderr, "[link] evaluator: garbler has started\n");
+      p.ct = L.ring;
+      p.ct_ring = L.ring_positions;
+      p.ct_pos_stride = 4;
+      p.ct_quad_stride = L.cap * 4;
+      p.ct_qshift = 2;
+      p.flow_control = 1;
+      p.limit_add = p.free_until = 0;
+      p.n_progress = 0;
+      p.ext_progress = L.ready_e;
+      p.host_chain = 1;
+      p.host_ready = L.done_e;
+      p.ct_sys = 1;
+      p.n_chain_warps = 1;
+      p.n_chain_ctas = 1;
+    }
     launch_engine<1>(s, hasher, p);
     launches += 2;
     CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
+    if (linked) {
+      // hash what arrives (the reference's evaluator hashes the channel while evaluating,
+      // examples/groth16_garble.rs:204-216): drain the ring to the host fold threads; a ring position is
+      // released to the garbler once it has been drained AND consumed by the evaluate kernel
+      gsv_link& L = *s->link;
+      std::atomic<uint64_t> copied_done{0};
+      volatile unsigned long long* w = L.words;
+      DrainSource src;
+      src.ring = L.ring;
+      src.cap = L.cap;
+      src.ring_positions = L.ring_positions;
+      src.ready = w;
+      src.watch = s->stream;
+      src.copied_done = &copied_done;
+      // watchdog: a stream that stops moving for GSV_LINK_TIMEOUT_S (default 60 s) is reported, not waited for
+      double stall_limit_s = 60.0;
+      if (const char* e = getenv("GSV_LINK_TIMEOUT_S")) stall_limit_s = std::max(1.0, atof(e));
+      auto last_move = std::chrono::steady_clock::now();
+      uint64_t last_sum = 0;
+      std::string stall_msg;
+      const bool dbg = getenv("GSV_LINK_DEBUG") != nullptr;
+      auto last_dbg = std::chrono::steady_clock::now();
+      if (dbg) fprintf(stderr, "[link] evaluator: kernel launched, draining\n");
+      src.tick = [&]() {
+        const uint64_t cd = copied_done.load(std::memory_order_acquire), done = w[8], rdy = w[0];
+        if (dbg && std::chrono::steady_clock::now() - last_dbg > std::chrono::seconds(1)) {
+          last_dbg = std::chrono::steady_clock::now();
+          fprintf(stderr, "[link] published %llu consumed %llu drained %llu released %llu\n", (unsigned long long)rdy,
+                  (unsigned long long)done, (unsigned long long)cd, (unsigned long long)w[16]);
+        }
+        const uint64_t rel = std::min<uint64_t>(cd, done);
+        if (rel > w[16]) {
+          std::atomic_thread_fence(std::memory_order_seq_cst);
+          w[16] = rel;
+        }
+        const auto now = std::chrono::steady_clock::now();
+        if (cd + done + rdy != last_sum) {
+          last_sum = cd + done + rdy;
+          last_move = now;
+        } else if (std::chrono::duration<double>(now - last_move).count() > stall_limit_s) {
+          stall_msg = "linked stream stalled: garbler published " + std::to_string(rdy) + ", evaluate kernel consumed " +
+                      std::to_string(done) + ", drained " + std::to_string(cd) + " of " + std::to_string(g.total_ct) + " ciphertexts";
+          return false;
+        }
+        return !L.failed.load();
+      };
+      link_commits.resize((size_t)B * 16);
+      try {
+        run_host_chain(s, src, link_commits.data(), nullptr);
+      } catch (const std::exception& e) {
+        uint32_t sc[4] = {0, 0, 0, 0};
+        cudaMemcpyAsync(sc, s->d_ctrl.p + 4, 16, cudaMemcpyDeviceToHost, s->copy_stream);
+        cudaStreamSynchronize(s->copy_stream);
+        L.failed.store(true);
+        w[16] = ~0ull >> 1;  // let the garbler run to completion
+        w[0] = ~0ull >> 1;   // ... and this session's own kernel (it then reads whatever is in the ring)
+        const auto t0 = std::chrono::steady_clock::now();
+        while (cudaStreamQuery(s->stream) == cudaErrorNotReady && std::chrono::steady_clock::now() - t0 < std::chrono::seconds(10))
+          std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        throw std::runtime_error((stall_msg.empty() ? std::string(e.what()) : stall_msg) + "; evaluate kernel: queue head " +
+                                 std::to_string(sc[0]) + " tail " + std::to_string(sc[1]) + ", items completed " + std::to_string(sc[2]) +
+                                 " of " + std::to_string(g.calls.size() * (size_t)s->n_groups) + ", buckets released " + std::to_string(sc[3]) +
+                                 (cudaStreamQuery(s->stream) == cudaErrorNotReady ? " (kernel still running)" : ""));
+      }
+      // keep returning ring space until the kernel has consumed the tail
+      while (cudaStreamQuery(s->stream) == cudaErrorNotReady) {
+        if (!src.tick()) {
+          uint32_t sc[4] = {0, 0, 0, 0};
+          cudaMemcpyAsync(sc, s->d_ctrl.p + 4, 16, cudaMemcpyDeviceToHost, s->copy_stream);
+          cudaStreamSynchronize(s->copy_stream);
+          L.failed.store(true);
+          w[16] = ~0ull >> 1;
+          throw std::runtime_error(stall_msg + "; evaluate kernel still running: queue head " + std::to_string(sc[0]) + " tail " +
+                                   std::to_string(sc[1]) + ", items completed " + std::to_string(sc[2]) + " of " +
+                                   std::to_string(g.calls.size() * (size_t)s->n_groups) + ", buckets released " + std::to_string(sc[3]));
+        }
+        std::this_thread::sleep_for(std::chrono::microseconds(50));
+      }
+    }
     // the evaluator's own chain hash over what it consumed (FileSource hashes while reading)
     const uint64_t used = std::min<uint64_t>(ct_avail, g.total_ct);
-    if (io->ct_commit) {
-    CUDA_TRY(cudaFuncSetAttribute(k_chain<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
+    if (io->ct_commit && linked) {
+      memcpy(io->ct_commit, link_commits.data(), link_commits.size());
+    } else if (io->ct_commit) {
     k_chain<0><<<(B + 31) / 32, 32, AES_TABLE_BYTES, s->stream>>>(s->d_ct.p, used, B, s->d_commit.p);
     CUDA_TRY(cudaGetLastError());
     launches++;
@@ -1277,11 +1725,9 @@ int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io) {
     CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
     uint32_t ctrl[4] = {0, 0, 0, 0};
     CUDA_TRY(cudaMemcpyAsync(ctrl, s->d_ctrl.p, 16, cudaMemcpyDeviceToHost, s->stream));
-    if (io->ct_commit) CUDA_TRY(cudaMemcpyAsync(io->ct_commit, s->d_commit.p, (size_t)B * 16, cudaMemcpyDeviceToHost, s->stream));
+    if (io->ct_commit && !linked) CUDA_TRY(cudaMemcpyAsync(io->ct_commit, s->d_commit.p, (size_t)B * 16, cudaMemcpyDeviceToHost, s->stream));
     if (n_out && (io->output_active || io->output_bits)) {
       const size_t total = (size_t)B * n_out;
-      if (s->d_io.n < total) s->d_io.alloc(total);
-      if (s->d_io_bits.n < total) s->d_io_bits.alloc(total);
       k_gather_slots<0><<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(
           s->d_labels.p, s->d_vals.p, s->d_output_slots.p, n_out, B, s->G, g.n_global_slots, s->d_io.p, s->d_io_bits.p);
       CUDA_TRY(cudaGetLastError());
@@ -1297,6 +1743,10 @@ int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io) {
     if (ctrl[1]) return fail(GSV_ERR_CT_EXHAUSTED, "Ciphertext source exhausted");
     return GSV_OK;
   } catch (const std::exception& e) {
+    if (s->link) {
+      s->link->failed.store(true);
+      reinterpret_cast<volatile unsigned long long*>(s->link->words)[16] = ~0ull >> 1;
+    }
     return fail(GSV_ERR_CUDA, e.what());
   }
 }
@@ -1310,7 +1760,6 @@ int gsv_commit_labels(int device, const uint8_t* labels, uint64_t n, uint8_t* ou
     d_in.alloc(n);
     d_out.alloc(n);
     CUDA_TRY(cudaMemcpy(d_in.p, labels, n * 16, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaFuncSetAttribute(k_commit_labels<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
     k_commit_labels<0><<<(unsigned)std::min<uint64_t>((n + 255) / 256, 296), 256, AES_TABLE_BYTES>>>(d_in.p, n, d_out.p);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(out, d_out.p, n * 16, cudaMemcpyDeviceToHost));
@@ -1333,8 +1782,6 @@ int gsv_hash_blocks(int device, int hasher, const uint8_t* x, const uint64_t* gi
     CUDA_TRY(cudaMemcpy(d_in.p, x, n * 16, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_gid.p, gid, n * 8, cudaMemcpyHostToDevice));
     const unsigned hb_grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 296);
-    CUDA_TRY(cudaFuncSetAttribute(k_hash_blocks<HASH_AES>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(k_hash_blocks<HASH_BLAKE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
     if (hasher == GSV_HASH_AES) k_hash_blocks<HASH_AES><<<hb_grid, 256, AES_TABLE_BYTES>>>(d_in.p, d_gid.p, n, d_out.p);
     else k_hash_blocks<HASH_BLAKE3><<<hb_grid, 256, AES_TABLE_BYTES>>>(d_in.p, d_gid.p, n, d_out.p);
     CUDA_TRY(cudaGetLastError());
@@ -1353,8 +1800,6 @@ int gsv_bench_hash_latency(int device, int hasher, uint32_t warps_per_sm, uint64
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     DevBuf<unsigned long long> out;
     out.alloc(2);
-    CUDA_TRY(cudaFuncSetAttribute(k_hash_latency<HASH_AES>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(k_hash_latency<HASH_BLAKE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
     if (hasher == GSV_HASH_AES) k_hash_latency<HASH_AES><<<prop.multiProcessorCount, 32 * warps_per_sm, AES_TABLE_BYTES>>>(n, out.p);
     else k_hash_latency<HASH_BLAKE3><<<prop.multiProcessorCount, 32 * warps_per_sm, AES_TABLE_BYTES>>>(n, out.p);
     CUDA_TRY(cudaGetLastError());
@@ -1374,8 +1819,6 @@ int gsv_bench_hash(int device, int hasher, uint64_t n_blocks, int iters, double*
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     const unsigned grid = (unsigned)prop.multiProcessorCount * 2, block = 512;
-    CUDA_TRY(cudaFuncSetAttribute(k_bench_hash<HASH_AES>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(k_bench_hash<HASH_BLAKE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_TABLE_BYTES));
     const unsigned long long threads = (unsigned long long)grid * block;
     unsigned long long per_thread = std::max<unsigned long long>(1, n_blocks / (2 * threads));
     DevBuf<uint4> sink;

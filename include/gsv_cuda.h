@@ -193,6 +193,18 @@ typedef struct {
 gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options* opt);
 void gsv_session_destroy(gsv_session* s);
 
+/* Garbler -> evaluator streaming (streaming_garbling_with_sender + streaming_evaluation over a channel,
+ * examples/groth16_garble.rs:170-267, tests/garbler_evaluator_connection.rs:64-156): links a garbling
+ * session to an evaluating session of the same program and batch size.  The ciphertexts never touch the
+ * host: they travel through a ring in the EVALUATOR's device memory that the garbler's kernel fills
+ * directly -- peer stores over NVLink when the two sessions are on different GPUs -- behind progress words;
+ * nothing is kept.  ring_bytes caps the ring (0 = 85 % of the evaluator GPU's free memory).
+ * Afterwards gsv_garble_batch(garbler) and gsv_evaluate_batch(evaluator) (ct_streams = NULL) must be called
+ * CONCURRENTLY from two host threads, once per run; the garbler's ct_mode is ignored (its ct_commit is not
+ * written), the evaluator's ct_commit is the chain hash of what it received (host AES-NI threads draining its
+ * own ring), to be compared with the garbler's earlier commitment exactly as the reference's evaluator does. */
+int gsv_session_link(gsv_session* garbler, gsv_session* evaluator, uint64_t ring_bytes);
+
 typedef struct {
   /* all optional (NULL = not wanted); host pointers */
   uint8_t* delta;         /* B * 16        secret                                        */
@@ -245,6 +257,19 @@ int gsv_host_chain_fold_quads(uint8_t* h, const uint8_t* base, uint64_t quad_byt
 
 /* streaming_garbling for B instances: instance i uses seeds[i] (garble_mode.rs:80-97). */
 int gsv_garble_batch(gsv_session* s, int hasher, const uint64_t* seeds, gsv_garble_result* res);
+
+/* FileCiphertextHandler (src/cut_and_choose/ciphertext_repository.rs:59-136): while a GSV_CT_COMMIT_HOST session
+ * garbles (or a linked evaluator receives), instance i's ciphertexts are also written to the open file
+ * descriptor fds[i] in the gc_{i}.bin format (16-byte records, emission order, no header; pwrite at the
+ * record's offset).  fds: B descriptors (-1 = skip that instance); NULL clears the sink.  The caller owns the
+ * descriptors.  This is how finalized cut-and-choose instances (47.7 GB each for the verifier) leave the GPU:
+ * straight from the pinned drain buffers, never through a resident copy of the stream. */
+int gsv_session_set_ciphertext_files(gsv_session* s, const int* fds);
+
+/* Only the seed expansion of gsv_garble_batch (GarbleMode::new + EncodeInput, garble_mode.rs:80-97,116-118):
+ * fills res->delta / false_label0 / true_label0 / input_label0 (each optional) for seeds[0..B) without
+ * garbling.  What a garbler needs to build the evaluator's input message before a streamed run. */
+int gsv_session_expand_seeds(gsv_session* s, const uint64_t* seeds, gsv_garble_result* res);
 
 /* Copies ciphertexts [first, first+count) of `instance` to `out` in the reference stream
  * format (count * 16 bytes, emission order = gc_{i}.bin, ciphertext_source.rs:95-101).

@@ -381,3 +381,62 @@ def test_cut_and_choose_protocol_round_trip(gsv, circuit):
     with pytest.raises(cc.ConsistencyError) as e:
         ev.evaluate_from(closed, [cc.EvaluatorCaseInput(c0.index, c0.input_active, c0.input_bits, c0.false_label, c0.false_label)] + cases[1:])
     assert e.value.kind == "TrueConstantMismatch"
+
+
+@pytest.mark.parametrize("mode,B,ring_mb", [(1, 4, 12), (1, 6, 0), (2, 40, 96)])
+def test_linked_garbler_evaluator_stream(gsv, orc, circuit, mode, B, ring_mb, monkeypatch):
+    """Garbler -> evaluator streaming (examples/groth16_garble.rs:170-267, tests/garbler_evaluator_connection.rs): the
+    garbler's kernel fills a ring in the evaluator's memory (the second GPU when there is one, peer stores), the
+    evaluator consumes it behind the progress words and hashes what it received.  Checked against the oracle:
+    evaluator's chain hash == the garbler's commitment, active output labels == select(value), bits == plaintext."""
+    monkeypatch.setenv("GSV_HOST_CHAIN_BUF_MB", "1")
+    p, st = circuit("fq12_mul")
+    two = gsv.device_count() >= 2
+    sm = 0 if two else 64   # one GPU: the two persistent grids share the SMs
+    gs = gsv.Session(p, B, device=0, ct_mode=gsv.CT_NONE, exec_mode=mode, group=2 if mode == 1 else 0, sm_limit=sm)
+    es = gsv.Session(p, B, device=1 if two else 0, ct_mode=gsv.CT_NONE, exec_mode=mode, group=2 if mode == 1 else 0, sm_limit=sm)
+    gsv.link_sessions(gs, es, ring_bytes=ring_mb << 20)
+    rng = np.random.default_rng(5)
+    for run in range(2):   # a link serves repeated runs
+        seeds = [0, 42] + list(range(100 * run + 10, 100 * run + 10 + B - 2))
+        bits = rng.integers(0, 2, (B, p.n_inputs), dtype=np.uint8)
+        gres, ev = gsv.stream_garble_evaluate(gs, es, seeds, gsv.HASH_AES, bits)
+        for i in (0, 1, B - 1):
+            ref = st.garble(orc.HASH_AES, seeds[i], want_ct=False)
+            assert bytes(ev.ct_commit[i]) == ref["ct_commit"]
+            want_bits = st.execute(bits[i])
+            assert np.array_equal(ev.output_bits[i], want_bits)
+            delta = np.frombuffer(ref["delta"], np.uint8)
+            assert np.array_equal(ev.output_active[i], ref["output_label0"] ^ (delta[None, :] * want_bits[:, None]))
+            assert np.array_equal(gres.output_label0[i], ref["output_label0"])
+
+
+def test_ciphertext_files_from_host_drain(gsv, orc, circuit, tmp_path, monkeypatch):
+    """FileCiphertextHandler / FileSource (ciphertext_repository.rs:59-136, ciphertext_source.rs:35-106): a
+    GSV_CT_COMMIT_HOST run writes gc_{i}.bin straight from the drain buffers (small ring and drain buffers, so the
+    files are assembled from many wrapped chunks); the bytes equal the oracle's stream and evaluate correctly."""
+    monkeypatch.setenv("GSV_HOST_CHAIN_BUF_MB", "1")
+    p, st = circuit("fq12_mul")
+    B = 5
+    seeds = [0, 42, 7, 8, 9]
+    paths = [str(tmp_path / f"gc_{i}.bin") if i != 3 else None for i in range(B)]   # instance 3: not kept
+    sess = gsv.Session(p, B, ct_mode=gsv.CT_COMMIT_HOST, exec_mode=1, group=1, ct_ring_log2=19)
+    sess.set_ciphertext_files(paths)
+    res = sess.garble(seeds, gsv.HASH_AES)
+    sess.set_ciphertext_files(None)
+    ref = st.garble(orc.HASH_AES, seeds[1])
+    assert bytes(res.ct_commit[1]) == ref["ct_commit"]
+    got = np.fromfile(paths[1], np.uint8).reshape(-1, 16)
+    assert got.shape[0] == p.n_ciphertexts and np.array_equal(got, ref["cts"])
+    assert not (tmp_path / "gc_3.bin").exists()
+    # evaluate instance 4 from its file (FileSource), alone in a one-instance session
+    rng = np.random.default_rng(11)
+    bits = rng.integers(0, 2, (1, p.n_inputs), dtype=np.uint8)
+    active = res.input_label0[4:5] ^ (res.delta[4:5, None, :] * bits[:, :, None])
+    ev = gsv.Session(p, 1, ct_mode=gsv.CT_NONE, exec_mode=1, group=1).evaluate(
+        gsv.HASH_AES, res.true_label1[4:5], res.false_label0[4:5], active, bits,
+        ct_streams=[np.fromfile(paths[4], np.uint8)])
+    want = st.execute(bits[0])
+    assert np.array_equal(ev.output_bits[0], want)
+    assert np.array_equal(ev.output_active[0], res.output_label0[4] ^ (res.delta[4][None, :] * want[:, None]))
+    assert np.array_equal(ev.ct_commit[0], res.ct_commit[4])
