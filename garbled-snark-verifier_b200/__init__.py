@@ -115,7 +115,7 @@ class _EvaluateIO(C.Structure):
         ("ms_commit", C.c_float),
         ("ms_total", C.c_float),
         ("n_launches", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("ct_ring_log2", C.c_uint32),
     ]
 
 
@@ -341,6 +341,18 @@ class Session:
                             r.ms_commit, r.ms_total, r.n_launches, r.host_fold_busy, r.host_drain_wait_kernel,
                             r.host_drain_wait_fold)
 
+    def execute(self, input_bits: np.ndarray):
+        """ExecuteMode on the GPU: boolean evaluation of the planned circuit for input_bits[n, n_inputs]
+        (n <= 128 * n_instances), bit-sliced.  Returns (output_bits[n, n_outputs], kernel milliseconds)."""
+        lib = load_library()
+        p = self.program
+        ib = np.ascontiguousarray(input_bits, np.uint8).reshape(-1, p.n_inputs)
+        ob = np.zeros((ib.shape[0], p.n_outputs), np.uint8)
+        ms = C.c_float(0)
+        lib.gsv_execute_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_float)]
+        _check(lib.gsv_execute_batch(self._h, _ptr(ib), ib.shape[0], _ptr(ob), C.byref(ms)))
+        return ob, ms.value
+
     def set_ciphertext_files(self, paths: Optional[Sequence[Optional[str]]]) -> None:
         """gc_{i}.bin writers (ciphertext_repository.rs:94-106) for the next garbling runs of a CT_COMMIT_HOST
         session (or the runs a linked evaluator receives): instance i's stream goes to paths[i] (None = skip).
@@ -386,7 +398,8 @@ class Session:
 
     def evaluate(self, hasher: int, true_label: np.ndarray, false_label: np.ndarray,
                  input_active: np.ndarray, input_bits: np.ndarray,
-                 ct_streams: Optional[Sequence[np.ndarray]] = None, want_commit: bool = True) -> EvalResult:
+                 ct_streams: Optional[Sequence[np.ndarray]] = None, want_commit: bool = True,
+                 ct_ring_log2: int = 0) -> EvalResult:
         lib = load_library()
         B, p = self.n_instances, self.program
         tl = np.ascontiguousarray(true_label, np.uint8).reshape(B, 16)
@@ -400,13 +413,15 @@ class Session:
         io.true_label, io.false_label, io.input_active, io.input_bits = _ptr(tl), _ptr(fl), _ptr(ia), _ptr(ib)
         keep = None
         if ct_streams is not None:
-            keep = [np.ascontiguousarray(s, np.uint8) for s in ct_streams]
+            # np.memmap'ed gc_{i}.bin files are passed through as they are (no copy): the library reads them
+            keep = [s if isinstance(s, np.memmap) and s.dtype == np.uint8 else np.ascontiguousarray(s, np.uint8) for s in ct_streams]
             lens = {k.size // 16 for k in keep}
             if len(keep) != B or len(lens) != 1:
                 raise ValueError("need B ciphertext streams of equal length")
             arr = (C.c_void_p * B)(*[k.ctypes.data for k in keep])
             io.ct_streams = C.cast(arr, C.POINTER(C.c_void_p))
             io.ct_stream_len = lens.pop()
+            io.ct_ring_log2 = ct_ring_log2
         io.output_active, io.output_bits, io.ct_commit = _ptr(oa), _ptr(ob), _ptr(cc if want_commit else None)
         _check(lib.gsv_evaluate_batch(self._h, hasher, C.byref(io)))
         return EvalResult(oa, ob, cc, io.ms_evaluate, io.ms_commit, io.ms_total, io.n_launches)

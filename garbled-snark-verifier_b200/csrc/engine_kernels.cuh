@@ -454,7 +454,9 @@ __device__ __forceinline__ void publish_warp(const EngineParams& p) {
   }
 }
 
-// MODE 0 = garble (labels are label0, ciphertexts produced), MODE 1 = evaluate.
+// MODE 0 = garble (labels are label0, ciphertexts produced), MODE 1 = evaluate, MODE 2 = execute: plain boolean
+// evaluation (ExecuteMode, src/circuit/modes/execute_mode.rs) bit-sliced 128 wide -- a "label" is then the
+// wire's value in 128 independent executions, gates are bitwise operations, nothing is hashed.
 // At most ENGINE_MAX_THREADS threads per CTA: 128 registers per thread are available, which lets ptxas keep
 // a round's table lookups in flight together (with the 64 registers of a 1024-thread CTA every lookup was
 // consumed ~8 instructions after its issue and a worker alone on its scheduler paid the shared-memory
@@ -665,6 +667,13 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
               sts128(lab_s + sc * SLOT_B, xor4(hs, and4(delta, 0u - (type & 1u))));
             }
           }
+        } else if (MODE == 2) {
+          if (act) {  // ((a ^ alpha_a) & (b ^ alpha_b)) ^ alpha_c on 128 executions (gate_type.rs:20-37)
+            const uint4 la = lds128(lab_s + sa * SLOT_B), lb = lds128(lab_s + sb * SLOT_B);
+            const uint32_t ma = 0u - ((type >> 2) & 1u), mb = 0u - ((type >> 1) & 1u), mc = 0u - (type & 1u);
+            sts128(lab_s + sc * SLOT_B, make_uint4(((la.x ^ ma) & (lb.x ^ mb)) ^ mc, ((la.y ^ ma) & (lb.y ^ mb)) ^ mc,
+                                                   ((la.z ^ ma) & (lb.z ^ mb)) ^ mc, ((la.w ^ ma) & (lb.w ^ mb)) ^ mc));
+          }
         } else if (act) {
           const uint4 la = lds128(lab_s + sa * SLOT_B), lb = lds128(lab_s + sb * SLOT_B);
           const uint32_t va = lds8(sval_s + sa * G), vb = lds8(sval_s + sb * G);
@@ -693,6 +702,8 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
           uint4 lc = (type == 10) ? la : xor4(la, lb);
           if (MODE == 0) {
             if (type != 8) lc = xor4(lc, delta);  // Xnor / Not flip the zero label
+          } else if (MODE == 2) {
+            if (type != 8) lc = make_uint4(~lc.x, ~lc.y, ~lc.z, ~lc.w);  // Xnor / Not
           } else {
             sts8(sval_s + sc * G, gate_value(type, lds8(sval_s + sa * G), lds8(sval_s + sb * G)));
           }

@@ -105,6 +105,7 @@ void preload_engine() {
   preload(k_engine<G, HASH_AES, 1>);
   preload(k_engine<G, HASH_BLAKE3, 0>);
   preload(k_engine<G, HASH_BLAKE3, 1>);
+  preload(k_engine<G, HASH_AES, 2>);
 }
 void preload_kernels() {
   preload_engine<1>();
@@ -828,13 +829,16 @@ void launch_engine(gsv_session* s, int hasher, const EngineParams& p) {
     CUDA_TRY(cudaGetLastError());
   }
   if (s->lane_mode) {
+    if constexpr (MODE == 2) throw std::runtime_error("execute mode runs on the levelised kernel (exec_mode 1)");
     dim3 lgrid(s->sm_count), lblock(32 * s->n_workers);
-    if (hasher == GSV_HASH_AES) {
-      k_lane<HASH_AES, MODE><<<lgrid, lblock, AES_TABLE_BYTES, s->stream>>>(p);
-    } else if (hasher == GSV_HASH_BLAKE3) {
-      k_lane<HASH_BLAKE3, MODE><<<lgrid, lblock, AES_TABLE_BYTES, s->stream>>>(p);
-    } else {
-      throw std::runtime_error("unknown hasher");
+    if constexpr (MODE != 2) {
+      if (hasher == GSV_HASH_AES) {
+        k_lane<HASH_AES, MODE><<<lgrid, lblock, AES_TABLE_BYTES, s->stream>>>(p);
+      } else if (hasher == GSV_HASH_BLAKE3) {
+        k_lane<HASH_BLAKE3, MODE><<<lgrid, lblock, AES_TABLE_BYTES, s->stream>>>(p);
+      } else {
+        throw std::runtime_error("unknown hasher");
+      }
     }
     CUDA_TRY(cudaGetLastError());
     return;
@@ -853,9 +857,13 @@ void launch_engine(gsv_session* s, int hasher, const EngineParams& p) {
     case 8: GSV_LAUNCH(8, HH); break;            \
     default: throw std::runtime_error("bad group size"); \
   }
-  if (hasher == GSV_HASH_AES) { GSV_LAUNCH_G(HASH_AES) }
-  else if (hasher == GSV_HASH_BLAKE3) { GSV_LAUNCH_G(HASH_BLAKE3) }
-  else throw std::runtime_error("unknown hasher");
+  if constexpr (MODE == 2) {
+    GSV_LAUNCH_G(HASH_AES)  // execute mode hashes nothing: one instantiation
+  } else {
+    if (hasher == GSV_HASH_AES) { GSV_LAUNCH_G(HASH_AES) }
+    else if (hasher == GSV_HASH_BLAKE3) { GSV_LAUNCH_G(HASH_BLAKE3) }
+    else throw std::runtime_error("unknown hasher");
+  }
 #undef GSV_LAUNCH_G
 #undef GSV_LAUNCH
   CUDA_TRY(cudaGetLastError());
@@ -1555,21 +1563,44 @@ int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io) {
     if (n_in && (!io->input_active || !io->input_bits)) return fail(GSV_ERR_INVALID, "missing inputs");
     uint32_t launches = 0;
     uint64_t ct_avail = g.total_ct;
+    bool host_fed = false;     // ciphertexts fed from host streams through a ring while the kernel runs
+    uint64_t fed_ring = 0;
     const bool linked = s->link && !s->link_garbler;
     if (linked && getenv("GSV_LINK_DEBUG")) fprintf(stderr, "[link] evaluator: call entered\n");
     if (linked) {
       if (io->ct_streams) return fail(GSV_ERR_INVALID, "a linked evaluator takes its ciphertexts from the garbler session");
     } else if (io->ct_streams) {
-      // FileSource-style host streams: upload and interleave
-      if (s->d_ct.n < (size_t)std::max<uint64_t>(g.total_ct, 1) * B) s->d_ct.alloc((size_t)std::max<uint64_t>(g.total_ct, 1) * B);
+      // FileSource-style host streams (ciphertext_source.rs:35-106).  Small: upload and interleave, the kernel
+      // reads a resident [position][B] buffer.  Large (or io->ct_ring_log2 set): the streams are FED through a
+      // ring while the kernel runs (below), so 47.7 GB-per-instance verifier streams never have to fit in HBM.
       ct_avail = std::min<uint64_t>(io->ct_stream_len, g.total_ct);
-      if (ct_avail) {
-        if (s->d_stage.n < ct_avail) s->d_stage.alloc(ct_avail);
-        for (uint32_t i = 0; i < B; i++) {
-          CUDA_TRY(cudaMemcpyAsync(s->d_stage.p, io->ct_streams[i], ct_avail * 16, cudaMemcpyHostToDevice, s->stream));
-          k_ct_insert<0><<<(unsigned)((ct_avail + 255) / 256), 256, 0, s->stream>>>(s->d_ct.p, B, i, 0, ct_avail, s->d_stage.p);
-          CUDA_TRY(cudaGetLastError());
-          launches++;
+      size_t free_b = 0, total_b = 0;
+      CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+      const uint64_t resident_bytes = std::max<uint64_t>(g.total_ct, 1) * B * 16;
+      host_fed = io->ct_ring_log2 != 0 || (s->d_ct.n < (size_t)std::max<uint64_t>(g.total_ct, 1) * B && resident_bytes > free_b / 2);
+      if (!host_fed) {
+        if (s->d_ct.n < (size_t)std::max<uint64_t>(g.total_ct, 1) * B) s->d_ct.alloc((size_t)std::max<uint64_t>(g.total_ct, 1) * B);
+        if (ct_avail) {
+          if (s->d_stage.n < ct_avail) s->d_stage.alloc(ct_avail);
+          for (uint32_t i = 0; i < B; i++) {
+            CUDA_TRY(cudaMemcpyAsync(s->d_stage.p, io->ct_streams[i], ct_avail * 16, cudaMemcpyHostToDevice, s->stream));
+            k_ct_insert<0><<<(unsigned)((ct_avail + 255) / 256), 256, 0, s->stream>>>(s->d_ct.p, B, i, 0, ct_avail, s->d_stage.p);
+            CUDA_TRY(cudaGetLastError());
+            launches++;
+          }
+        }
+      } else {
+        uint64_t max_task_ct = 1;
+        for (const auto& t : g.tasks) max_task_ct = std::max<uint64_t>(max_task_ct, t.n_ct);
+        fed_ring = io->ct_ring_log2 ? (1ull << io->ct_ring_log2) : std::max<uint64_t>((uint64_t)(free_b * 0.4) / ((uint64_t)B * 16), 1);
+        fed_ring = std::min<uint64_t>(fed_ring, std::max<uint64_t>(g.total_ct, 1));
+        if (fed_ring < 2 * max_task_ct && fed_ring < g.total_ct) throw std::runtime_error("ciphertext ring smaller than two tasks");
+        if (s->d_ct.n < (size_t)fed_ring * B) s->d_ct.alloc((size_t)fed_ring * B);
+        ensure_host_chain_resources(s);
+        if (s->d_park_head.n == 0) {
+          s->park_q = std::max<uint64_t>(fed_ring / 64, 1);
+          s->d_park_head.alloc((size_t)(std::max<uint64_t>(g.total_ct, 1) / s->park_q + 2));
+          s->d_park_next.alloc(std::max<size_t>(g.calls.size() * (size_t)s->n_groups, 1));
         }
       }
       ct_avail = io->ct_stream_len;
@@ -1631,9 +1662,83 @@ int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io) {
       p.n_chain_warps = 1;
       p.n_chain_ctas = 1;
     }
+    if (host_fed) {
+      // instance-major ring [instance][position]; the feeder below publishes how much of the stream has landed in
+      // hc_ready[0], the kernel's publisher warp what it has consumed in hc_ready[4] (mapped host memory)
+      volatile unsigned long long* w = s->hc_ready;
+      w[0] = w[4] = 0;
+      std::atomic_thread_fence(std::memory_order_seq_cst);
+      p.ct = s->d_ct.p;
+      p.ct_ring = fed_ring >= g.total_ct ? 0 : fed_ring;
+      p.ct_pos_stride = 1;
+      p.ct_quad_stride = fed_ring;
+      p.ct_qshift = 0;
+      p.flow_control = 1;
+      p.limit_add = p.free_until = 0;
+      p.n_progress = 0;
+      p.ext_progress = s->hc_ready_dev;
+      p.host_chain = 1;
+      p.host_ready = s->hc_ready_dev + 4;
+      p.n_chain_warps = 1;
+      p.n_chain_ctas = 1;
+    }
     launch_engine<1>(s, hasher, p);
     launches += 2;
     CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
+    std::vector<uint8_t> fed_commits;
+    if (host_fed) {
+      // ---- FileSource: feed the ring and hash the streams on host threads at the same time
+      const uint64_t avail_total = std::min<uint64_t>(io->ct_stream_len, g.total_ct);
+      volatile unsigned long long* w = s->hc_ready;
+      fed_commits.assign((size_t)B * 16, 0);
+      std::vector<std::thread> folders;
+      if (io->ct_commit && gsv::host_chain_available()) {
+        const uint32_t T = std::max<uint32_t>(1, std::min<uint32_t>(s->host_threads, (B + 3) / 4));
+        for (uint32_t t = 0; t < T; t++)
+          folders.emplace_back([&, t]() {
+            const uint32_t i0 = (uint32_t)((uint64_t)B * t / T), i1 = (uint32_t)((uint64_t)B * (t + 1) / T);
+            if (i1 > i0) gsv::host_chain_fold_streams(fed_commits.data() + (size_t)i0 * 16, io->ct_streams + i0, 0, avail_total, i1 - i0);
+          });
+      }
+      std::string err;
+      try {
+        const uint64_t ring = fed_ring;
+        const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(ring / 4, (8u << 20) / 16));
+        uint64_t fed = 0;
+        auto last_move = std::chrono::steady_clock::now();
+        while (fed < avail_total) {
+          const uint64_t done = p.ct_ring ? w[4] : 0;
+          const uint64_t room_end = p.ct_ring ? done + ring : avail_total;
+          uint64_t n = std::min<uint64_t>({chunk, avail_total - fed, room_end > fed ? room_end - fed : 0, ring - fed % ring});
+          if (n == 0) {
+            const cudaError_t q = cudaStreamQuery(s->stream);
+            if (q != cudaErrorNotReady) throw std::runtime_error(q == cudaSuccess ? "evaluate kernel ended before the stream was consumed"
+                                                                                  : cudaGetErrorString(q));
+            if (std::chrono::steady_clock::now() - last_move > std::chrono::seconds(120)) throw std::runtime_error("ciphertext feed stalled");
+            std::this_thread::sleep_for(std::chrono::microseconds(50));
+            continue;
+          }
+          last_move = std::chrono::steady_clock::now();
+          for (uint32_t i = 0; i < B; i++)
+            CUDA_TRY(cudaMemcpyAsync(s->d_ct.p + (size_t)i * ring + fed % ring, io->ct_streams[i] + fed * 16, n * 16,
+                                     cudaMemcpyHostToDevice, s->copy_stream));
+          CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+          fed += n;
+          std::atomic_thread_fence(std::memory_order_seq_cst);
+          w[0] = fed;
+        }
+        // a short stream: let the kernel run into the exhaustion check instead of waiting for more
+        if (avail_total < g.total_ct) w[0] = ~0ull >> 1;
+      } catch (const std::exception& e) {
+        err = e.what();
+        w[0] = ~0ull >> 1;
+      }
+      for (auto& t : folders) t.join();
+      if (!err.empty()) {
+        cudaStreamSynchronize(s->stream);
+        throw std::runtime_error(err);
+      }
+    }
     if (linked) {
       // hash what arrives (the reference's evaluator hashes the channel while evaluating,
       // examples/groth16_garble.rs:204-216): drain the ring to the host fold threads; a ring position is
@@ -1717,6 +1822,8 @@ int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io) {
     const uint64_t used = std::min<uint64_t>(ct_avail, g.total_ct);
     if (io->ct_commit && linked) {
       memcpy(io->ct_commit, link_commits.data(), link_commits.size());
+    } else if (io->ct_commit && host_fed) {
+      memcpy(io->ct_commit, fed_commits.data(), fed_commits.size());
     } else if (io->ct_commit) {
     k_chain<0><<<(B + 31) / 32, 32, AES_TABLE_BYTES, s->stream>>>(s->d_ct.p, used, B, s->d_commit.p);
     CUDA_TRY(cudaGetLastError());
@@ -1725,7 +1832,7 @@ int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io) {
     CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
     uint32_t ctrl[4] = {0, 0, 0, 0};
     CUDA_TRY(cudaMemcpyAsync(ctrl, s->d_ctrl.p, 16, cudaMemcpyDeviceToHost, s->stream));
-    if (io->ct_commit && !linked) CUDA_TRY(cudaMemcpyAsync(io->ct_commit, s->d_commit.p, (size_t)B * 16, cudaMemcpyDeviceToHost, s->stream));
+    if (io->ct_commit && !linked && !host_fed) CUDA_TRY(cudaMemcpyAsync(io->ct_commit, s->d_commit.p, (size_t)B * 16, cudaMemcpyDeviceToHost, s->stream));
     if (n_out && (io->output_active || io->output_bits)) {
       const size_t total = (size_t)B * n_out;
       k_gather_slots<0><<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(
@@ -1747,6 +1854,69 @@ int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io) {
       s->link->failed.store(true);
       reinterpret_cast<volatile unsigned long long*>(s->link->words)[16] = ~0ull >> 1;
     }
+    return fail(GSV_ERR_CUDA, e.what());
+  }
+}
+
+int gsv_execute_batch(gsv_session* s, const uint8_t* input_bits, uint32_t n_exec, uint8_t* output_bits, float* ms) {
+  if (!s || !input_bits || !output_bits) return fail(GSV_ERR_INVALID, "null argument");
+  try {
+    CUDA_TRY(cudaSetDevice(s->device));
+    const gsv::Program& g = s->prog->prog;
+    const uint32_t B = s->B, n_in = g.n_inputs, n_out = (uint32_t)g.output_slots.size();
+    if (n_exec == 0 || n_exec > 128u * B) return fail(GSV_ERR_INVALID, "a session of B instances executes at most 128 * B inputs at once");
+    if (s->lane_mode) return fail(GSV_ERR_INVALID, "execute mode runs on the levelised kernel (exec_mode 1)");
+    ensure_eval_buffers(s);
+    // bit-slice: execution e -> instance e / 128, bit e % 128 of the wire's 16-byte slot
+    std::vector<uint32_t> packed((size_t)B * n_in * 4, 0u);
+    for (uint32_t e = 0; e < n_exec; e++) {
+      const uint32_t inst = e >> 7, w = (e >> 5) & 3u, bit = e & 31u;
+      const uint8_t* row = input_bits + (size_t)e * n_in;
+      uint32_t* dst = packed.data() + (size_t)inst * n_in * 4 + w;
+      for (uint32_t j = 0; j < n_in; j++) dst[4 * j] |= (uint32_t)(row[j] & 1u) << bit;
+    }
+    std::vector<uint32_t> ones((size_t)B * 4, 0xFFFFFFFFu);
+    if (n_in) CUDA_TRY(cudaMemcpyAsync(s->d_ev_in.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->d_ev_true.p, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->d_ev_false.p, 0, (size_t)B * 16, s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->d_ev_bits.p, 0, std::max<size_t>((size_t)B * n_in, 1), s->stream));
+    s->epoch++;
+    CUDA_TRY(cudaMemsetAsync(s->d_ctrl.p, 0, 16, s->stream));
+    {
+      const size_t total = (size_t)B * (n_in + 2);
+      k_scatter_inputs<0><<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(
+          s->d_ev_in.p, s->d_ev_bits.p, s->d_ev_true.p, s->d_ev_false.p, n_in, B, s->G, g.n_global_slots, s->d_labels.p, s->d_vals.p);
+      CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaEventRecord(s->ev[1], s->stream));
+    EngineParams p = make_params(s);
+    p.flow_control = 0;
+    p.ct_ring = 0;
+    p.host_chain = 0;
+    launch_engine<2>(s, GSV_HASH_AES, p);
+    CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
+    std::vector<uint32_t> out((size_t)B * std::max<uint32_t>(n_out, 1) * 4, 0u);
+    if (n_out) {
+      const size_t total = (size_t)B * n_out;
+      k_gather_slots<0><<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(
+          s->d_labels.p, nullptr, s->d_output_slots.p, n_out, B, s->G, g.n_global_slots, s->d_io.p, nullptr);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaMemcpyAsync(out.data(), s->d_io.p, total * 16, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (ms) cudaEventElapsedTime(ms, s->ev[1], s->ev[2]);
+    for (uint32_t e = 0; e < n_exec; e++) {
+      const uint32_t inst = e >> 7, w = (e >> 5) & 3u, bit = e & 31u;
+      for (uint32_t k = 0; k < n_out; k++) {
+        const uint32_t slot = g.output_slots[k];
+        // outputs wired straight to a constant never pass through the kernel's slots 0 / 1 differently: same read
+        output_bits[(size_t)e * n_out + k] = (uint8_t)((out[((size_t)inst * n_out + k) * 4 + w] >> bit) & 1u);
+        (void)slot;
+      }
+    }
+    s->ct_valid = false;  // the label slots now hold plaintext slices
+    return GSV_OK;
+  } catch (const std::exception& e) {
     return fail(GSV_ERR_CUDA, e.what());
   }
 }

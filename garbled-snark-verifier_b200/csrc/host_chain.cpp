@@ -172,6 +172,46 @@ void host_chain_fold(uint8_t* h, const uint8_t* base, size_t pos_stride, size_t 
 }
 
 
+// W chains from W unrelated buffers (see fold_w for the merged last round)
+template <int W>
+void fold_ptrs(uint8_t* h, const uint8_t* const* src0, size_t n_pos, const RoundKeys& rk) {
+  if (n_pos == 0) return;
+  __m128i t[W];
+  const uint8_t* src[W];
+  const __m128i k10_0 = _mm_xor_si128(rk.k[10], rk.k[0]);
+  for (int i = 0; i < W; i++) {
+    src[i] = src0[i];
+    t[i] = _mm_xor_si128(_mm_xor_si128(_mm_loadu_si128(reinterpret_cast<const __m128i*>(h) + i),
+                                       _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[i]))), rk.k[0]);
+    src[i] += 16;
+  }
+  for (size_t p = 1;; p++) {
+    for (int r = 1; r < 10; r++)
+      for (int i = 0; i < W; i++) t[i] = _mm_aesenc_si128(t[i], rk.k[r]);
+    if (p == n_pos) break;
+    for (int i = 0; i < W; i++) {
+      t[i] = _mm_aesenclast_si128(t[i], _mm_xor_si128(k10_0, _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[i]))));
+      src[i] += 16;
+    }
+  }
+  for (int i = 0; i < W; i++)
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(h) + i, _mm_aesenclast_si128(t[i], rk.k[10]));
+}
+
+void host_chain_fold_streams(uint8_t* h, const uint8_t* const* streams, uint64_t first, size_t n_pos, uint32_t n_inst) {
+  static const RoundKeys rk = make_keys();
+  const uint8_t* p[4];
+  uint32_t i = 0;
+  for (; i + 4 <= n_inst; i += 4) {
+    for (int j = 0; j < 4; j++) p[j] = streams[i + j] + first * 16;
+    fold_ptrs<4>(h + 16 * i, p, n_pos, rk);
+  }
+  for (; i < n_inst; i++) {
+    p[0] = streams[i] + first * 16;
+    fold_ptrs<1>(h + 16 * i, p, n_pos, rk);
+  }
+}
+
 void host_chain_fold_quads(uint8_t* h, const uint8_t* base, size_t quad_bytes, size_t n_pos, uint32_t n_quads) {
   static const RoundKeys rk = make_keys();
   uint32_t q = 0;

@@ -28,4 +28,9 @@ void host_chain_fold(uint8_t* h, const uint8_t* base, size_t pos_stride, size_t 
 // 4 * n_quads chain states.  One 512-bit load per quad and step with VAES; 128-bit AES-NI otherwise.
 void host_chain_fold_quads(uint8_t* h, const uint8_t* base, size_t quad_bytes, size_t n_pos, uint32_t n_quads);
 
+
+// n_inst independent streams given by pointer (gc_{i}.bin images in host memory, FileSource): positions
+// [first, first + n_pos) of every stream are folded into h (n_inst states), up to four chains interleaved.
+void host_chain_fold_streams(uint8_t* h, const uint8_t* const* streams, uint64_t first, size_t n_pos, uint32_t n_inst);
+
 }  // namespace gsv

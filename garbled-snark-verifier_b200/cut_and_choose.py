@@ -230,24 +230,46 @@ class EvaluatorCaseInput:
     false_label: np.ndarray   # [16]  false.select(false)
 
 
-def open_commit(garbler: "Garbler", to_finalize: List[int]):
-    """`Garbler::open_commit` for the local shard: seeds of the opened instances, and for the finalized
-    ones a re-garbling whose ciphertext stream stays on the GPU (the `Sender<S>` handler; the stream must
-    fit HBM -- 87 MB per Fq12-mul instance, 47.7 GB per verifier instance).  Returns
-    (open: [(index, seed)], closed: {index: ciphertext stream [n_ct, 16] on the host})."""
-    from . import CT_KEEP_RAW, Session
+def open_commit(garbler: "Garbler", to_finalize: List[int], ct_dir: Optional[str] = None):
+    """`Garbler::open_commit` for the local shard (garbler.rs:259-319): seeds of the opened instances, and for the
+    finalized ones a re-garbling that hands the ciphertext stream over.  Returns (open: [(index, seed)], closed).
+
+    ct_dir given (the reference's `FileCiphertextHandlerProvider`, ciphertext_repository.rs:59-136): the finalized
+    instances are re-garbled in ONE GSV_CT_COMMIT_HOST run whose host drain writes `ct_dir/gc_{index}.bin` directly
+    from the pinned buffers -- nothing is kept in HBM, so verifier instances (47.7 GB each) work; closed maps
+    index -> file path.  Without ct_dir the streams are kept on the GPU (`Sender<S>` handler; must fit HBM) and
+    closed maps index -> [n_ct, 16] array."""
+    import os
+
+    from . import CT_COMMIT_HOST, CT_KEEP_RAW, Session
 
     mine = [i for i in to_finalize if garbler.first <= i < garbler.first + garbler.count]
     open_ = [(garbler.first + k, int(garbler.seeds[k])) for k in range(garbler.count)
              if garbler.first + k not in mine]
     closed = {}
-    if mine:
+    if mine and ct_dir is not None:
+        os.makedirs(ct_dir, exist_ok=True)
+        paths = [os.path.join(ct_dir, f"gc_{i}.bin") for i in mine]
+        sess = Session(garbler.program, len(mine), device=garbler.device, ct_mode=CT_COMMIT_HOST, exec_mode=1)
+        sess.set_ciphertext_files(paths)
+        sess.garble([int(garbler.seeds_all[i]) for i in mine], garbler.hasher, want_inputs=False, want_outputs=False)
+        sess.set_ciphertext_files(None)
+        sess.close()
+        closed = dict(zip(mine, paths))
+    elif mine:
         sess = Session(garbler.program, len(mine), device=garbler.device, ct_mode=CT_KEEP_RAW)
         sess.garble([int(garbler.seeds_all[i]) for i in mine], garbler.hasher, want_inputs=False, want_outputs=False)
         for k, i in enumerate(mine):
             closed[i] = sess.read_ciphertexts(k)   # the bytes of gc_{i}.bin (ciphertext_repository.rs:94-106)
         sess.close()
     return open_, closed
+
+
+def _as_stream(x) -> np.ndarray:
+    """A closed ciphertext stream as a flat uint8 array; file paths are memory-mapped (FileSource)."""
+    if isinstance(x, (str, bytes)) or hasattr(x, "__fspath__"):
+        return np.memmap(x, dtype=np.uint8, mode="r")
+    return np.ascontiguousarray(x, np.uint8).reshape(-1)
 
 
 def prepare_input_labels(garbler: "Garbler", to_finalize: List[int], input_bits: np.ndarray) -> List[EvaluatorCaseInput]:
@@ -299,16 +321,31 @@ class Evaluator:
         for i in self.to_finalize:
             if i not in closed_streams:
                 raise ConsistencyError("MissingCiphertextHash", i)
-            st = np.ascontiguousarray(closed_streams[i], np.uint8).reshape(-1, 1, 16)
-            h = host_chain_fold(np.zeros((1, 16), np.uint8), st)[0]
-            if not np.array_equal(h, self.commits.ct_commit()[i]):
+        # fold the received streams (files are read chunk by chunk), all finalized instances interleaved
+        fin = list(self.to_finalize)
+        streams = [_as_stream(closed_streams[i]) for i in fin]
+        h = np.zeros((len(fin), 16), np.uint8)
+        n_pos = min(s.size for s in streams) // 16 if streams else 0
+        if any(s.size != streams[0].size for s in streams):
+            n_pos = 0   # ragged: fold one by one below
+        step = 1 << 22
+        for a in range(0, n_pos, step):
+            b = min(n_pos, a + step)
+            h = host_chain_fold(h, np.stack([s[16 * a:16 * b].reshape(-1, 16) for s in streams]), instance_major=True)
+        if n_pos == 0:
+            for k, s_ in enumerate(streams):
+                for a in range(0, s_.size // 16, step):
+                    b = min(s_.size // 16, a + step)
+                    h[k:k + 1] = host_chain_fold(h[k:k + 1], s_[16 * a:16 * b].reshape(1, -1, 16), instance_major=True)
+        for k, i in enumerate(fin):
+            if not np.array_equal(h[k], self.commits.ct_commit()[i]):
                 raise ConsistencyError("CiphertextMismatch", i, "ciphertext corrupted")
 
     def evaluate_from(self, closed_streams, cases: List[EvaluatorCaseInput]):
         """evaluator.rs:338-476: for every finalized instance check the constant and input-label commits,
         evaluate from its ciphertext stream (one batched GPU call), re-check the chain hash and the output
         label commit.  Returns [(index, output bits [n_out], active output labels [n_out, 16])]."""
-        from . import CT_KEEP, Session, commit_labels
+        from . import CT_NONE, Session, commit_labels
 
         p, n = self.program, len(cases)
         if n == 0:
@@ -334,10 +371,12 @@ class Evaluator:
             bad = np.nonzero((sel != in_c[k]).any(axis=1))[0]
             if bad.size:
                 raise ConsistencyError("InputLabelsMismatch", c.index, f"label_index {int(bad[0])}")
-        sess = Session(p, n, device=self.device, ct_mode=CT_KEEP)
+        # streams may be arrays or gc_{i}.bin paths; the library uploads them whole when they fit and otherwise feeds
+        # them through a ring while the kernel runs (FileSource: hashed on host threads while being consumed)
+        sess = Session(p, n, device=self.device, ct_mode=CT_NONE)
         ev = sess.evaluate(self.hasher, np.stack([c.true_label for c in cases]), np.stack([c.false_label for c in cases]),
                            np.stack([c.input_active for c in cases]), np.stack([c.input_bits for c in cases]),
-                           ct_streams=[closed_streams[i] for i in idx])
+                           ct_streams=[_as_stream(closed_streams[i]) for i in idx])
         sess.close()
         out_c = commit_labels(ev.output_active, device=self.device).reshape(n, p.n_outputs, 16)
         res = []

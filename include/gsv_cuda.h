@@ -283,8 +283,9 @@ typedef struct {
   const uint8_t* false_label;   /* B * 16   false constant's label0                              */
   const uint8_t* input_active;  /* B * n_inputs * 16                                             */
   const uint8_t* input_bits;    /* B * n_inputs (0/1)                                            */
-  /* ciphertext source: NULL = the session's own kept stream (garbler and evaluator share the
-   * GPU); otherwise B host streams of n_ciphertexts*16 bytes each (FileSource layout).           */
+  /* ciphertext source: NULL = the session's own kept stream (garbler and evaluator share the GPU) or the linked
+   * garbler; otherwise B host streams of n_ciphertexts*16 bytes each (FileSource layout, e.g. mmap'ed
+   * gc_{i}.bin files).                                                                            */
   const uint8_t* const* ct_streams;
   uint64_t ct_stream_len;       /* ciphertexts available per host stream                         */
   /* outputs (host pointers, optional) */
@@ -295,11 +296,20 @@ typedef struct {
   float ms_commit;
   float ms_total;
   uint32_t n_launches;
-  uint32_t reserved;
+  uint32_t ct_ring_log2;        /* in, with ct_streams: 0 = automatic (the streams are uploaded whole when they fit in
+                                   half of the free HBM, otherwise FED through a ring while the kernel runs and hashed
+                                   by host threads, FileSource); n > 0 forces a ring of 2^n ciphertexts per instance */
 } gsv_evaluate_io;
 
 /* streaming_evaluation for B instances (evaluate_mode.rs:70-158). */
 int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io);
+
+/* ExecuteMode on the GPU (src/circuit/modes/execute_mode.rs; the reference's IS_PRE_BOOLEAN_EXEC pre-check,
+ * examples/groth16_cut_and_choose.rs:235-254): plain boolean evaluation of the planned circuit for n_exec
+ * independent inputs at once, bit-sliced 128 per instance slot of the session (n_exec <= 128 * B), on the
+ * levelised kernel with bitwise gates and no hashing.  input_bits: n_exec * n_inputs bytes (0/1), output_bits:
+ * n_exec * n_outputs.  *ms (optional) receives the kernel's device time. */
+int gsv_execute_batch(gsv_session* s, const uint8_t* input_bits, uint32_t n_exec, uint8_t* output_bits, float* ms);
 
 /* commit(label) = AES128_K(label) for n labels (src/cut_and_choose/mod.rs:41-48). */
 int gsv_commit_labels(int device, const uint8_t* labels, uint64_t n, uint8_t* out);

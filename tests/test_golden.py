@@ -105,3 +105,9 @@ def test_full_verifier_garbling_matches_oracle_fixture(gsv):
         assert bytes(res.input_label0[i, 0]).hex() == v["input_label0_first"]
         assert bytes(res.output_label0[i, 0]).hex() == v["output_label0"]
         assert bytes(res.ct_commit[i]).hex() == v["ct_commit"]
+    # ExecuteMode on the GPU over the same planned program (the reference's pre-check,
+    # examples/groth16_cut_and_choose.rs:235-254): the synthetic proof verifies, its tampered variant does not
+    bits = np.stack([gsv.groth16_synthetic_inputs(), gsv.groth16_synthetic_inputs(flip_public=True)] * 3)
+    out, ms = sess.execute(bits)
+    assert out[:, 0].tolist() == [1, 0, 1, 0, 1, 0]
+    assert ms < 60e3

@@ -2,6 +2,8 @@
 the B200 must equal the CPU oracle's on the same seeds (bit-exact; integer/byte work)."""
 import random
 
+import os
+
 import numpy as np
 import pytest
 
@@ -383,6 +385,40 @@ def test_cut_and_choose_protocol_round_trip(gsv, circuit):
     assert e.value.kind == "TrueConstantMismatch"
 
 
+def test_cut_and_choose_with_ciphertext_files(gsv, circuit, tmp_path):
+    """The same protocol with the reference's file handlers (FileCiphertextHandlerProvider / FileSource,
+    ciphertext_repository.rs:59-136): finalized instances are re-garbled straight into gc_{i}.bin by the host drain,
+    the evaluator folds and evaluates from the files; a flipped byte in a file is caught."""
+    import importlib
+
+    cc = importlib.import_module("garbled-snark-verifier_b200.cut_and_choose")
+    import bn254_ref as bn
+
+    p, _ = circuit("fq_mul")
+    total, fin = 4, 2
+    garbler = cc.Garbler(p, total, master_seed=7)
+    garbler.create()
+    commits = garbler.commit()
+    ev = cc.Evaluator(p, total, fin, rng_seed=3, commits=commits)
+    open_, closed = cc.open_commit(garbler, ev.to_finalize, ct_dir=str(tmp_path))
+    assert all(isinstance(v, str) and os.path.getsize(v) == 16 * p.n_ciphertexts for v in closed.values())
+    ev.run_regarbling(open_, closed)
+    a, b = 5, bn.P - 2
+    bits = np.array(bn.bits_le(bn.to_mont(a)) + bn.bits_le(bn.to_mont(b)), np.uint8)
+    res = ev.evaluate_from(closed, cc.prepare_input_labels(garbler, ev.to_finalize, bits))
+    for _, out_bits, _ in res:
+        assert bn.from_bits(list(out_bits)) == bn.to_mont(a * b % bn.P)
+    victim = closed[ev.to_finalize[1]]
+    with open(victim, "r+b") as f:
+        f.seek(16 * 777 + 5)
+        byte = f.read(1)
+        f.seek(16 * 777 + 5)
+        f.write(bytes([byte[0] ^ 0x10]))
+    with pytest.raises(cc.ConsistencyError) as e:
+        ev.run_regarbling(open_, closed)
+    assert e.value.kind == "CiphertextMismatch" and e.value.index == ev.to_finalize[1]
+
+
 @pytest.mark.parametrize("mode,B,ring_mb", [(1, 4, 12), (1, 6, 0), (2, 40, 96)])
 def test_linked_garbler_evaluator_stream(gsv, orc, circuit, mode, B, ring_mb, monkeypatch):
     """Garbler -> evaluator streaming (examples/groth16_garble.rs:170-267, tests/garbler_evaluator_connection.rs): the
@@ -440,3 +476,54 @@ def test_ciphertext_files_from_host_drain(gsv, orc, circuit, tmp_path, monkeypat
     assert np.array_equal(ev.output_bits[0], want)
     assert np.array_equal(ev.output_active[0], res.output_label0[4] ^ (res.delta[4][None, :] * want[:, None]))
     assert np.array_equal(ev.ct_commit[0], res.ct_commit[4])
+
+
+@pytest.mark.parametrize("name,B,G,n", [("gate_zoo", 1, 1, 128), ("fq_mul", 2, 2, 200), ("fq12_mul", 4, 4, 300)])
+def test_execute_mode_on_gpu(gsv, circuit, name, B, G, n):
+    """ExecuteMode on the GPU (bit-sliced 128 executions per instance slot) == the host walker of the recorded
+    circuit (gsv_program_execute) and, for Fq mul, the BN254 product."""
+    p, st = circuit(name)
+    rng = np.random.default_rng(21)
+    bits = rng.integers(0, 2, (n, p.n_inputs), dtype=np.uint8)
+    sess = gsv.Session(p, B, ct_mode=gsv.CT_NONE, exec_mode=1, group=G)
+    out, ms = sess.execute(bits)
+    for e in (0, 1, 31, 32, 127, n - 1):
+        assert np.array_equal(out[e], st.execute(bits[e])), e
+    # garbling afterwards still works on the same session (label slots are re-seeded)
+    res = sess.garble(list(range(B)), gsv.HASH_AES)
+    ref = st.garble(0, 0, want_ct=False)
+    assert np.array_equal(res.output_label0[0], ref["output_label0"])
+    with pytest.raises(gsv.GsvError):
+        sess.execute(np.zeros((128 * B + 1, p.n_inputs), np.uint8))
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_evaluate_fed_from_host_streams_through_a_ring(gsv, orc, circuit, tmp_path, mode):
+    """FileSource at scale (ciphertext_source.rs:35-106): gc_{i}.bin images (np.memmap) are fed through a small
+    device ring WHILE the evaluate kernel runs and hashed on host threads; same outputs and chain hash as the
+    resident path, and a truncated file is reported as "Ciphertext source exhausted"."""
+    p, st = circuit("fq12_mul")
+    B = 3 if mode == 1 else 33
+    seeds = list(range(50, 50 + B))
+    g = gsv.Session(p, B, ct_mode=gsv.CT_KEEP, exec_mode=mode, group=1 if mode == 1 else 0)
+    res = g.garble(seeds, gsv.HASH_AES)
+    files = []
+    for i in range(B):
+        path = tmp_path / f"gc_{i}.bin"
+        g.read_ciphertexts(i).tofile(path)
+        files.append(np.memmap(path, dtype=np.uint8, mode="r"))
+    g.close()
+    rng = np.random.default_rng(13)
+    bits = rng.integers(0, 2, (B, p.n_inputs), dtype=np.uint8)
+    active = res.input_label0 ^ (res.delta[:, None, :] * bits[:, :, None])
+    e = gsv.Session(p, B, ct_mode=gsv.CT_NONE, exec_mode=mode, group=1 if mode == 1 else 0)
+    ev = e.evaluate(gsv.HASH_AES, res.true_label1, res.false_label0, active, bits, ct_streams=files, ct_ring_log2=18)
+    assert np.array_equal(ev.ct_commit, res.ct_commit)
+    for i in (0, B - 1):
+        want = st.execute(bits[i])
+        assert np.array_equal(ev.output_bits[i], want)
+        assert np.array_equal(ev.output_active[i], res.output_label0[i] ^ (res.delta[i][None, :] * want[:, None]))
+    short = [f[: 16 * (p.n_ciphertexts - 5)] for f in files]
+    with pytest.raises(gsv.GsvError) as ex:
+        e.evaluate(gsv.HASH_AES, res.true_label1, res.false_label0, active, bits, ct_streams=short, ct_ring_log2=18)
+    assert ex.value.code == -5
