@@ -54,6 +54,23 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def plan_cache_dir():
+    """The ranks of a job (and successive runs on one box) plan the circuit once and share the result through a
+    file (GSV_PLAN_CACHE_DIR, see gsv_program_build): 23 s and 17 GB of host memory per process otherwise."""
+    if "GSV_PLAN_CACHE_DIR" in os.environ:
+        return
+    for d in ("/dev/shm", "/tmp"):
+        path = os.path.join(d, "gsv_plan_cache")
+        try:
+            os.makedirs(path, exist_ok=True)
+            st = os.statvfs(path)
+            if st.f_bavail * st.f_frsize > 12 << 30:
+                os.environ["GSV_PLAN_CACHE_DIR"] = path
+                return
+        except OSError:
+            pass
+
+
 def host_cpus():
     """(logical CPUs this process may use, physical cores of the host)."""
     try:
@@ -242,6 +259,7 @@ def run_mpc(args):
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     two = torch.cuda.device_count() >= 2 and args.gpus >= 2
     hasher = g.HASH_AES if args.hasher == "aes" else g.HASH_BLAKE3
+    plan_cache_dir()
     t_plan = time.perf_counter()
     prog = g.Program(args.circuit)
     t_plan = time.perf_counter() - t_plan
@@ -323,6 +341,7 @@ def main():
     ap.add_argument("--group", type=int, default=None)
     ap.add_argument("--ct-mode", default=None, choices=["commit", "commit_host", "none"])
     ap.add_argument("--worker-threads", type=int, default=0)
+    ap.add_argument("--max-task-slots", type=int, default=0, help="planner: shared-memory label slots per task (0 = default)")
     ap.add_argument("--host-threads", type=int, default=0, help="fold threads per session (0: from the rank's CPU share)")
     ap.add_argument("--hasher", default="aes", choices=["aes", "blake3"])
     ap.add_argument("--no-commit", action="store_true", help="drop ciphertexts (the `()` handler)")
@@ -337,6 +356,7 @@ def main():
                           ct_mode="none", steps=2),
               "batch": dict(circuit="fq12_mul", instances=6144, sessions=1, exec_mode=2, group=0, ct_mode="commit",
                             steps=3)}[args.workload]
+    args.sessions_auto = args.sessions is None
     for k, v in preset.items():
         if getattr(args, k) is None:
             setattr(args, k, v)
@@ -369,8 +389,9 @@ def main():
 
     hasher = g.HASH_AES if args.hasher == "aes" else g.HASH_BLAKE3
     ct_mode = {"none": g.CT_NONE, "commit": g.CT_COMMIT, "commit_host": g.CT_COMMIT_HOST}[args.ct_mode]
+    plan_cache_dir()
     t_plan = time.perf_counter()
-    prog = g.Program(args.circuit)
+    prog = g.Program(args.circuit, max_task_slots=args.max_task_slots)
     t_plan = time.perf_counter() - t_plan
     B, S = args.instances, max(1, args.sessions)
     lane = args.exec_mode == 2 or (args.exec_mode == 0 and args.group == 0 and B >= 128)
@@ -380,7 +401,11 @@ def main():
     # drain thread (mostly asleep) and `fold_threads` AES-NI fold threads
     logical, physical = host_cpus()
     cpu_share = max(1, logical // max(1, local_world))
-    fold_threads = args.host_threads or max(1, min((B + 3) // 4, max(1, cpu_share - 1) // S))
+    if args.sessions_auto and ct_mode == g.CT_COMMIT_HOST and cpu_share < 6:
+        # few host CPUs per rank (8 GPUs on a 32-CPU host): one fold thread per session, each interleaving all four
+        # quads of its session (the VAES throughput cap, 640 M blocks/s per thread), and one session per CPU
+        S = max(S, min(4, cpu_share))
+    fold_threads = args.host_threads or max(1, min((B + 3) // 4, max(1, cpu_share - (1 if cpu_share >= 6 else 0)) // S))
     sm_total = torch.cuda.get_device_properties(local).multi_processor_count
     sm_limit = 0 if S == 1 else (sm_total - SM_RESERVE) // S
     free_b, _ = torch.cuda.mem_get_info()
@@ -558,7 +583,7 @@ def main():
                             + (" (BASELINE.json configs 2/4: Groth16 verifier, 1 public input, synthetic vk; "
                                "11.46 G gates here vs the reference's 11.17 G for its own vk)"
                                if args.circuit == "groth16_verify_compressed" else ""),
-                "kernel": kernel_name, "plan_s": round(t_plan, 1),
+                "kernel": kernel_name, "plan_s": round(t_plan, 1), "plan_cache": os.environ.get("GSV_PLAN_CACHE_DIR"),
                 "gates_per_instance": prog.n_gates, "ciphertexts_per_instance": prog.n_ciphertexts,
                 "instances_per_step": B, "steps_in_flight": S, "instances_in_flight_per_gpu": B * min(S, args.steps),
                 "seeds": "ChaCha20Rng::seed_from_u64(1234) u64 draws (garbler.rs:201-203)",

@@ -4,6 +4,8 @@
 
 #include <cuda_runtime.h>
 #include <unistd.h>
+#include <fcntl.h>
+#include <sys/file.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -188,6 +190,120 @@ struct gsv_ctx {
 };
 
 namespace {
+
+// ---- plan cache.  Planning the verifier takes ~23 s and ~17 GB of host memory per process; ranks of one job (and
+// successive runs on one box) share the result through a file: GSV_PLAN_CACHE_DIR/<circuit>.<options>.plan, written
+// once under an advisory lock.  A program loaded from the cache has no recorded circuit (template DAG): the
+// host-side walkers (gsv_program_execute, _flat_stream, _export_templates, _depth) refuse it.
+constexpr uint64_t PLAN_MAGIC = 0x67737650'4c414e32ull;  // "gsvPLAN2"
+struct PlanWriter {
+  FILE* f;
+  bool ok = true;
+  void raw(const void* p, size_t n) { if (n && fwrite(p, 1, n, f) != n) ok = false; }
+  template <typename T> void pod(const T& v) { raw(&v, sizeof(T)); }
+  template <typename T> void vec(const std::vector<T>& v) { pod<uint64_t>(v.size()); raw(v.data(), v.size() * sizeof(T)); }
+  void str(const std::string& v) { pod<uint64_t>(v.size()); raw(v.data(), v.size()); }
+};
+struct PlanReader {
+  FILE* f;
+  bool ok = true;
+  void raw(void* p, size_t n) { if (n && fread(p, 1, n, f) != n) ok = false; }
+  template <typename T> void pod(T& v) { raw(&v, sizeof(T)); }
+  template <typename T> void vec(std::vector<T>& v) {
+    uint64_t n = 0;
+    pod(n);
+    if (!ok || n > (1ull << 36) / sizeof(T)) { ok = false; return; }
+    v.resize(n);
+    raw(v.data(), n * sizeof(T));
+  }
+  void str(std::string& v) {
+    uint64_t n = 0;
+    pod(n);
+    if (!ok || n > (1u << 20)) { ok = false; return; }
+    v.resize(n);
+    raw(&v[0], n);
+  }
+};
+template <typename IO, typename P>
+void plan_io(IO& io, P& g) {  // the same field walk for writing (const-cast) and reading
+  uint64_t nt = g.tasks.size();
+  io.pod(nt);
+  g.tasks.resize(nt);
+  for (auto& t : g.tasks) {
+    io.str(t.key);
+    io.pod(t.n_in); io.pod(t.n_out); io.pod(t.n_slots); io.pod(t.n_levels); io.pod(t.max_width);
+    io.pod(t.n_gates_total); io.pod(t.n_ct); io.pod(t.n_live);
+    io.vec(t.gates); io.vec(t.level_off); io.vec(t.in_slot); io.vec(t.out_slot); io.vec(t.out_pos);
+    io.vec(t.seq_gates); io.vec(t.seq_in_slot); io.vec(t.seq_out_slot); io.pod(t.n_seq_slots);
+    io.vec(t.pipe_in_need); io.vec(t.pipe_out_ready); io.pod(t.pipe_depth);
+  }
+  io.vec(g.calls); io.vec(g.call_slots); io.vec(g.deps);
+  io.pod(g.n_global_slots); io.pod(g.n_inputs); io.vec(g.output_slots);
+  io.pod(g.total_gates); io.pod(g.total_ct); io.pod(g.total_live);
+  io.pod(g.max_task_slots); io.pod(g.max_task_seq_slots); io.pod(g.has_levelised); io.pod(g.max_task_in);
+  io.pod(g.max_call_deps);
+  for (auto& c : g.type_count) io.pod(c);
+}
+void derive_program_stats(gsv_program* p) {
+  for (const auto& t : p->prog.tasks) p->max_task_levels = std::max(p->max_task_levels, t.n_levels);
+  for (const auto& c : p->prog.calls) p->sum_call_levels += p->prog.tasks[c.task].n_levels;
+  const auto& g = p->prog;
+  std::vector<uint64_t> fg(g.calls.size()), fl(g.calls.size());
+  for (size_t i = 0; i < g.calls.size(); i++) {
+    const auto& c = g.calls[i];
+    uint64_t sg = 0, sl = 0;
+    for (uint32_t d = 0; d < c.n_deps; d++) {
+      sg = std::max(sg, fg[g.deps[c.dep_off + d]]);
+      sl = std::max(sl, fl[g.deps[c.dep_off + d]]);
+    }
+    fg[i] = sg + g.tasks[c.task].n_gates_total;
+    fl[i] = sl + g.tasks[c.task].n_levels;
+    p->critical_path_gates = std::max(p->critical_path_gates, fg[i]);
+    p->critical_path_levels = std::max(p->critical_path_levels, fl[i]);
+  }
+}
+std::string plan_cache_path(const std::string& circuit, const gsv_plan_options* opt) {
+  const char* dir = getenv("GSV_PLAN_CACHE_DIR");
+  if (!dir || !*dir) return "";
+  // the file name carries the plan options and this library build's stamp: a rebuilt library never reads old plans
+  uint32_t stamp = 2166136261u;
+  for (const char* c = __DATE__ " " __TIME__; *c; c++) stamp = (stamp ^ (uint8_t)*c) * 16777619u;
+  char buf[160];
+  snprintf(buf, sizeof buf, ".g%llu.s%u.l%u.%08x.plan", opt ? (unsigned long long)opt->max_task_gates : 0ull,
+           opt ? opt->max_task_slots : 0u, opt ? opt->lane_only : 0u, stamp);
+  std::string name = circuit;
+  for (char& c : name)
+    if (!isalnum((unsigned char)c) && c != '_') c = '_';
+  return std::string(dir) + "/" + name + buf;
+}
+gsv_program* load_plan(const std::string& path) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return nullptr;
+  PlanReader r{f};
+  uint64_t magic = 0;
+  r.pod(magic);
+  auto p = std::make_unique<gsv_program>();
+  if (r.ok && magic == PLAN_MAGIC) plan_io(r, p->prog);
+  uint64_t tail = 0;
+  r.pod(tail);
+  fclose(f);
+  if (!r.ok || magic != PLAN_MAGIC || tail != PLAN_MAGIC) return nullptr;  // truncated / foreign file: plan afresh
+  derive_program_stats(p.get());
+  return p.release();
+}
+void store_plan(const std::string& path, gsv_program* p) {
+  const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  PlanWriter w{f};
+  w.pod(PLAN_MAGIC);
+  plan_io(w, p->prog);
+  w.pod(PLAN_MAGIC);
+  const bool ok = w.ok && fclose(f) == 0;
+  if (ok) rename(tmp.c_str(), path.c_str());
+  else remove(tmp.c_str());
+}
+
 gsv_program* finish_program(std::unique_ptr<gsv::Builder> b, uint32_t root, const gsv_plan_options* opt) {
   gsv::PlanOptions po;
   if (opt) {
@@ -270,6 +386,30 @@ gsv_program* finish_program(std::unique_ptr<gsv::Builder> b, uint32_t root, cons
       sum_true += g.tasks[c.task].pipe_depth;
       sum_dev += g.tasks[c.task].n_levels;
     }
+    for (uint64_t W : {16ull, 32ull, 64ull, 128ull}) {
+      // the same with windows of W levels: inputs gathered at the start of the window that first reads them, outputs
+      // published at the end of the window that completes them (+ 2 levels of polling latency)
+      std::vector<uint64_t> st(g.n_global_slots, 0);
+      uint64_t cw = 0;
+      for (const auto& c : g.calls) {
+        const gsv::Task& t = g.tasks[c.task];
+        uint64_t S = 0;
+        for (uint32_t i = 0; i < t.n_in; i++) {
+          if (t.in_slot[i] == 0xFFFF) continue;
+          const uint32_t sl = g.call_slots[c.in_off + i];
+          const uint64_t need = (i < t.pipe_in_need.size() ? t.pipe_in_need[i] : 1);
+          const uint64_t need_w = (need ? (need - 1) / W * W : 0);  // level at whose start the input must be there
+          if (st[sl] + 2 > need_w) S = std::max(S, st[sl] + 2 - need_w);
+        }
+        for (uint32_t k = 0; k < t.n_out; k++) {
+          const uint32_t sl = g.call_slots[c.out_off + k];
+          const uint64_t rdy = k < t.pipe_out_ready.size() ? t.pipe_out_ready[k] : t.pipe_depth;
+          st[sl] = S + std::min<uint64_t>((rdy + W - 1) / W * W, t.pipe_depth);
+        }
+        cw = std::max(cw, S + t.pipe_depth);
+      }
+      fprintf(stderr, "[plan] windowed pipelining, W = %llu levels: critical path %llu\n", (unsigned long long)W, (unsigned long long)cw);
+    }
     fprintf(stderr, "[plan] critical path in levels: RAW only / true depths %llu, RAW+WAR / true depths %llu, "
             "RAW+WAR / device levels (128-gate cap) %llu; level-pipelined %llu; sum of call levels true %llu device %llu\n",
             (unsigned long long)crit_plain, (unsigned long long)c1, (unsigned long long)c2, (unsigned long long)crit,
@@ -324,10 +464,31 @@ gsv_program* gsv_program_record(const char* name, uint32_t n_inputs, uint32_t n_
 
 gsv_program* gsv_program_build(const char* circuit, const gsv_plan_options* opt) {
   try {
-    auto b = std::make_unique<gsv::Builder>();
     std::string c = circuit ? circuit : "";
-    const uint32_t r = gsv::build_named_circuit(*b, c);
-    return finish_program(std::move(b), r, opt);
+    const std::string cache = plan_cache_path(c, opt);
+    int lock_fd = -1;
+    if (!cache.empty()) {
+      if (gsv_program* hit = load_plan(cache)) return hit;
+      // one process plans, the others wait for its file
+      lock_fd = open((cache + ".lock").c_str(), O_CREAT | O_RDWR, 0644);
+      if (lock_fd >= 0) flock(lock_fd, LOCK_EX);
+      if (gsv_program* hit = load_plan(cache)) {
+        if (lock_fd >= 0) close(lock_fd);
+        return hit;
+      }
+    }
+    auto b = std::make_unique<gsv::Builder>();
+    gsv_program* p = nullptr;
+    try {
+      const uint32_t r = gsv::build_named_circuit(*b, c);
+      p = finish_program(std::move(b), r, opt);
+      if (p && !cache.empty()) store_plan(cache, p);
+    } catch (...) {
+      if (lock_fd >= 0) close(lock_fd);
+      throw;
+    }
+    if (lock_fd >= 0) close(lock_fd);
+    return p;
   } catch (const std::exception& e) {
     fail(GSV_ERR_INVALID, e.what());
     return nullptr;
@@ -338,6 +499,7 @@ void gsv_program_destroy(gsv_program* p) { delete p; }
 
 int gsv_program_execute(const gsv_program* p, const uint8_t* input_bits, uint8_t* output_bits, uint64_t* gates_executed) {
   if (!p || !input_bits || !output_bits) return fail(GSV_ERR_INVALID, "null argument");
+  if (!p->builder) return fail(GSV_ERR_INVALID, "program came from the plan cache: no recorded circuit to walk");
   try {
     const gsv::Template& rt = p->builder->tmpl(p->root);
     std::vector<uint8_t> in(input_bits, input_bits + rt.n_in);
@@ -353,6 +515,7 @@ int gsv_program_export_templates(const gsv_program* p, uint64_t sizes[6], uint32
                                  uint32_t* gates, uint32_t* calls, uint32_t* items, uint32_t* call_wires,
                                  uint32_t* outs) {
   if (!p || !sizes) return fail(GSV_ERR_INVALID, "null argument");
+  if (!p->builder) return fail(GSV_ERR_INVALID, "program came from the plan cache: no recorded circuit to export");
   if (!gsv::export_templates(*p->builder, sizes, tmpl, gates, calls, items, call_wires, outs))
     return fail(GSV_ERR_INVALID, "template DAG too large to export");
   if (root) *root = p->root;
@@ -375,6 +538,7 @@ int gsv_host_chain_fold_quads(uint8_t* h, const uint8_t* base, uint64_t quad_byt
 
 int gsv_program_depth(const gsv_program* p, uint64_t* depth_all, uint64_t* depth_nonfree) {
   if (!p) return fail(GSV_ERR_INVALID, "null argument");
+  if (!p->builder) return fail(GSV_ERR_INVALID, "program came from the plan cache: no recorded circuit");
   try {
     gsv::circuit_depth(*p->builder, p->root, depth_all, depth_nonfree);
     return GSV_OK;
@@ -524,6 +688,7 @@ int gsv_program_get_info(const gsv_program* p, gsv_program_info* out) {
 int64_t gsv_program_flat_stream(const gsv_program* p, uint8_t* type, uint32_t* a, uint32_t* b, uint32_t* c,
                                 uint64_t capacity, uint32_t* outputs, uint32_t* n_wires) {
   if (!p) return fail(GSV_ERR_INVALID, "null program");
+  if (!p->builder) return fail(GSV_ERR_INVALID, "program came from the plan cache: no recorded circuit to flatten");
   try {
     const gsv::Template& rt = p->builder->tmpl(p->root);
     if (!type) {

@@ -79,7 +79,7 @@ if "small" in what:
 
 if "verifier" in what:
     t = time.perf_counter()
-    p = g.Program("groth16_verify_compressed")
+    p = g.Program("groth16_verify_compressed", max_task_slots=int(kv.get("slots", "0")))
     print(f"verifier: planned in {time.perf_counter() - t:.1f} s, gates {p.n_gates} calls {p.n_calls} "
           f"critical path {p.critical_path_levels} levels, sum of call levels {p.sum_call_levels}", flush=True)
     run(p, int(kv.get("B", "32")), kv.get("verifier_shapes", "4x256").split(","), reps=1)
