@@ -42,6 +42,10 @@ ALGO_BYTES_PER_GATE = 52.3   # 48 B free gate, 64 B non-fr
 AES_BLOCKS_PER_GATE_GARBLE = 2.0  # per NON-FREE gate; + 1 chain block when committing
 PCIE_D2H_GBS = 57.2          # measured on this pool (profiles/r02_probe.md): pinned D2H, 1 GiB copies
 SM_RESERVE = 4               # SMs left free of persistent CTAs (NCCL / utility kernels must always fit)
+# DRAM traffic of the levelised kernel with ciphertexts dropped, from ncu (dram__bytes_read.sum + dram__bytes_write.sum of
+# k_engine<4,0,0> on the verifier x 16: 6.69 GB + 17.07 GB per launch, profiles/r02_traffic_verifier_B16_nocommit.csv):
+# labels live in shared memory and L2, only task inputs / outputs and the program reach DRAM
+LABEL_DRAM_BYTES_PER_GATE = (6694099712 + 17072106240) / (16 * 11457232209)
 
 
 def measured_peaks():
@@ -523,8 +527,15 @@ def main():
         per_launch = k_gates * ALGO_BYTES_PER_GATE / (k_ms * 1e-3) / 1e9
         busy = garble_ms / (span_ms * max(conc, 1))        # share of the span a session's kernel is running
         achieved = per_launch * conc * min(1.0, busy)
+        traffic = traffic_note = None
+        if not lane and args.circuit == "groth16_verify_compressed":
+            ct_bytes = 16 * prog.n_ciphertexts * B if args.ct_mode != "none" else 0
+            traffic = k_gates * LABEL_DRAM_BYTES_PER_GATE + ct_bytes * (2 if args.ct_mode == "commit_host" else 1)
+            traffic_note = ("per launch: label / program traffic measured by ncu on this kernel with ciphertexts dropped "
+                            "(0.13 B per gate: labels stay in shared memory and L2) + the ciphertext stream (16 B x n_ct x B, "
+                            "written by the kernel, read once by the drain); far below the algorithmic 52.3 B per gate")
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": kernel_name, "kernel_ms": k_ms, "peak_source": peak_src,
+                    "traffic": traffic, "traffic_note": traffic_note, "kernel": kernel_name, "kernel_ms": k_ms, "peak_source": peak_src,
                     "algorithmic_bytes_per_gate": ALGO_BYTES_PER_GATE,
                     "concurrent_launches": conc, "sms_per_launch": sm_limit or sm_total,
                     "per_launch": {"achieved": per_launch, "frac": per_launch / peak},

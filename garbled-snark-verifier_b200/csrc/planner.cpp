@@ -18,6 +18,14 @@ namespace {
 
 constexpr uint32_t UNSET = 0xFFFFFFFEu;
 
+// device level of the record that writes wire `w` (records are `order` in device order)
+uint32_t out_dev_level_of_wire(const FlatStream& fs, const std::vector<uint32_t>& order, const std::vector<uint32_t>& dev_level,
+                               uint32_t w) {
+  for (size_t k = order.size(); k-- > 0;)
+    if (fs.c[order[k]] == w) return dev_level[k];
+  throw std::logic_error("output wire has no producing gate");
+}
+
 // Levelise + slot-pack one flat SSA stream (ids: 0/1 consts, [2, 2+n_in) inputs, then defs).
 Task compile_flat(const FlatStream& fs, const std::string& key, const PlanOptions& opt) {
   Task t;
@@ -66,9 +74,14 @@ Task compile_flat(const FlatStream& fs, const std::string& key, const PlanOption
       if (o != WIRE_DEAD && o >= first_def) t.pipe_out_ready.push_back(wlevel[o]);
     t.pipe_depth = depth;
   }
-  // ---- ALAP levels: as late as the consumers allow; sinks (outputs, unread wires) at `depth`
+  // ---- ALAP levels: as late as the consumers allow; sinks (unread wires) at `depth`.  Outputs: at `depth` too,
+  // or -- when calls are pipelined (opt.pipeline) -- at their EARLIEST level, so that a consumer call can start on
+  // them while this task is still running.
   if (opt.alap) {
     std::vector<uint32_t> req(nw, depth);  // latest level at which the wire must be available
+    if (opt.pipeline)
+      for (uint32_t o : fs.outputs)
+        if (o != WIRE_DEAD && o >= first_def) req[o] = std::min(req[o], wlevel[o]);
     for (size_t gi = ng; gi-- > 0;) {
       if (fs.c[gi] == WIRE_DEAD) continue;
       uint32_t l = req[fs.c[gi]];
@@ -162,6 +175,64 @@ Task compile_flat(const FlatStream& fs, const std::string& key, const PlanOption
   }
   t.level_off.push_back((uint32_t)t.gates.size());
   t.n_levels = (uint32_t)t.level_off.size() - 1;
+  {
+    // ---- windows (call pipelining): inputs are gathered at the start of the window of W device levels that first
+    // reads them, produced outputs are published at the end of the window that completes them.  Without
+    // pipelining there is ONE window: everything gathered up front, everything published at the end.
+    const uint32_t W = opt.pipeline ? std::max<uint32_t>(opt.window_levels, 1) : 0xFFFFFFFFu;
+    t.window_levels = W;
+    const uint32_t n_win = t.n_levels == 0 ? 1 : (opt.pipeline ? (t.n_levels + W - 1) / W : 1);
+    std::vector<uint32_t> dev_level(t.gates.size(), 0);  // device level of every record
+    for (uint32_t l = 0; l < t.n_levels; l++)
+      for (uint32_t k = t.level_off[l]; k < t.level_off[l + 1]; k++) dev_level[k] = l;
+    std::vector<uint32_t> slot_first_read(next_slot, 0xFFFFFFFFu), slot_written(next_slot, 0xFFFFFFFFu);
+    // input slots are never reused before the input's last read and hold nothing else before it, so the first
+    // read of the SLOT is the first read of the input
+    std::vector<uint32_t> in_need(fs.n_inputs, 0xFFFFFFFFu);
+    {
+      std::vector<uint8_t> is_in_slot(next_slot, 0);
+      for (uint32_t i = 0; i < fs.n_inputs; i++)
+        if (t.in_slot[i] != 0xFFFF) is_in_slot[t.in_slot[i]] = 1;
+      std::vector<uint8_t> overwritten(next_slot, 0);
+      for (size_t k = 0; k < t.gates.size(); k++) {
+        const DevGate& dg = t.gates[k];
+        for (uint16_t sl : {dg.a, dg.b})
+          if (is_in_slot[sl] && !overwritten[sl]) slot_first_read[sl] = std::min(slot_first_read[sl], dev_level[k]);
+      }
+      // (gates are in level order; a slot is only re-assigned after its wire's last read, see the colouring)
+      for (size_t k = 0; k < t.gates.size(); k++) overwritten[t.gates[k].c] = 0;
+      for (uint32_t i = 0; i < fs.n_inputs; i++)
+        if (t.in_slot[i] != 0xFFFF) in_need[i] = slot_first_read[t.in_slot[i]];
+    }
+    t.win_in_off.assign(n_win + 1, 0);
+    t.win_out_off.assign(n_win + 1, 0);
+    std::vector<std::vector<uint16_t>> ins(n_win), outs(n_win);
+    for (uint32_t i = 0; i < fs.n_inputs; i++)
+      if (t.in_slot[i] != 0xFFFF) ins[opt.pipeline && in_need[i] != 0xFFFFFFFFu ? in_need[i] / W : 0].push_back((uint16_t)i);
+    if (fs.n_inputs > 0xFFFF) throw std::length_error("task with more than 65535 inputs: " + key);
+    t.out_ready_level.clear();
+    {
+      uint32_t kk = 0;
+      for (size_t j = 0; j < fs.outputs.size(); j++) {
+        const uint32_t o = fs.outputs[j];
+        if (o == WIRE_DEAD || o < first_def) continue;
+        // device level of the gate that writes this output
+        uint32_t lv = t.n_levels ? t.n_levels - 1 : 0;
+        if (opt.pipeline) lv = out_dev_level_of_wire(fs, order, dev_level, o);
+        t.out_ready_level.push_back(lv);
+        outs[opt.pipeline ? lv / W : 0].push_back((uint16_t)kk);
+        kk++;
+      }
+      if (kk > 0xFFFF) throw std::length_error("task with more than 65535 outputs: " + key);
+    }
+    for (uint32_t w = 0; w < n_win; w++) {
+      t.win_in_off[w + 1] = t.win_in_off[w] + (uint32_t)ins[w].size();
+      t.win_out_off[w + 1] = t.win_out_off[w] + (uint32_t)outs[w].size();
+      t.win_in.insert(t.win_in.end(), ins[w].begin(), ins[w].end());
+      t.win_out.insert(t.win_out.end(), outs[w].begin(), outs[w].end());
+    }
+    t.in_need_level = in_need;
+  }
   // level header, carried by the level's first record: width - 1 in flags bits 1-7 and the number of
   // non-free gates (they come first) in the top byte of ct_off (a task has < 2^24 ciphertexts)
   if (n_ct >= (1u << 24)) throw std::length_error("task with 2^24 or more ciphertexts: " + key);

@@ -65,6 +65,14 @@ struct Task {
   // level" statistics; the device programs do not use it yet.
   std::vector<uint32_t> pipe_in_need, pipe_out_ready;
   uint32_t pipe_depth = 0;
+  // Windows of the levelised form (call pipelining, planner.cpp): window w = device levels [w * window_levels,
+  // (w + 1) * window_levels).  win_in[win_in_off[w] .. win_in_off[w + 1]) = input positions to gather before window
+  // w (the window that first reads them), win_out likewise = indices of the produced outputs that are final at the
+  // end of window w.  Plans without pipelining have one window.
+  uint32_t window_levels = 0xFFFFFFFFu;
+  std::vector<uint16_t> win_in, win_out;
+  std::vector<uint32_t> win_in_off, win_out_off;
+  std::vector<uint32_t> in_need_level, out_ready_level;  // per input position (0xFFFFFFFF: never read) / produced output
 };
 
 struct Call {
@@ -75,6 +83,10 @@ struct Call {
   uint32_t out_off;   // into Program::call_slots, task.n_out entries
   uint32_t dep_off;   // into Program::deps
   uint32_t n_deps;
+  // The first n_start_deps entries are START dependencies (producers of this call's inputs: with pipelining the call
+  // may start once they have STARTED and then waits for each input's ready flag), the rest DONE dependencies (readers
+  // of the global slots this call overwrites: they must have completed).  Without pipelining all are DONE.
+  uint32_t n_start_deps = 0;
 };
 
 struct Program {
@@ -91,6 +103,7 @@ struct Program {
   uint32_t max_task_slots = 0;
   uint32_t max_task_seq_slots = 0;
   bool has_levelised = true;         // false: planned lane-only (PlanOptions::build_levelised off)
+  bool pipelined = false;            // calls carry start dependencies and tasks window tables (PlanOptions::pipeline)
   uint32_t max_task_in = 0;
   uint32_t max_call_deps = 0;
   uint64_t type_count[11] = {0};
@@ -107,6 +120,8 @@ struct PlanOptions {
   uint64_t small_task_gates = 8192;  // bodies up to this size are tasks even when they occur once
   uint64_t min_shared_calls = 4;     // larger bodies become tasks only if they occur this often
   bool build_levelised = true;       // false: lane-mode form only (large circuits)
+  bool pipeline = false;             // pipeline calls level-window by level-window (levelised form only)
+  uint32_t window_levels = 64;       // device levels per window
 };
 
 // Cuts, flattens, levelises and packs.  Throws on circuits it cannot plan.
