@@ -39,7 +39,8 @@ class GsvError(RuntimeError):
 
 
 class _PlanOptions(C.Structure):
-    _fields_ = [("max_task_gates", C.c_uint64), ("max_task_slots", C.c_uint32), ("lane_only", C.c_uint32)]
+    _fields_ = [("max_task_gates", C.c_uint64), ("max_task_slots", C.c_uint32), ("lane_only", C.c_uint32),
+                ("pipeline", C.c_uint32), ("window_levels", C.c_uint32)]
 
 
 class _ProgramInfo(C.Structure):
@@ -174,9 +175,11 @@ def _ptr(a: Optional[np.ndarray]):
 class Program:
     """A recorded + planned circuit (the once-per-topology flatten step)."""
 
-    def __init__(self, circuit: str, max_task_slots: int = 0, max_task_gates: int = 0, lane_only: bool = False):
+    def __init__(self, circuit: str, max_task_slots: int = 0, max_task_gates: int = 0, lane_only: bool = False,
+                 pipeline: Optional[bool] = None, window_levels: int = 0):
         lib = load_library()
-        opt = _PlanOptions(max_task_gates, max_task_slots, 1 if lane_only else 0)
+        opt = _PlanOptions(max_task_gates, max_task_slots, 1 if lane_only else 0,
+                           0 if pipeline is None else (1 if pipeline else 2), window_levels)
         self._h = lib.gsv_program_build(circuit.encode(), C.byref(opt))
         if not self._h:
             raise GsvError(-1, lib.gsv_last_error().decode())

@@ -30,6 +30,9 @@ struct DevTaskD {
   uint32_t gate_off, n_gates, n_levels, n_in, n_out, n_slots, in_slot_off, out_slot_off;
   uint32_t n_ct;
   uint32_t seq_gate_off, n_seq_gates, n_seq_slots;  // lane-mode (emission order) form
+  // windows of the levelised form (program.h): n_windows + 1 offsets each, starting at win_off; the offsets index
+  // win_in / win_out relative to win_in_base / win_out_base
+  uint32_t n_windows, window_levels, win_off, win_in_base, win_out_base;
 };
 struct DevCallD {
   uint32_t task, in_off, out_off, dep_off, n_deps, pad;
@@ -59,8 +62,17 @@ struct EngineParams {
   // dataflow scheduler: ready queue of work items (call * n_groups + group)
   unsigned long long* queue;  // [1 << queue_log2]: (round + 1) << 32 | item
   uint32_t* pending;          // [item]: producers / slot owners still running
-  const uint32_t* succ_off;   // [n_calls + 1] CSR of the reverse dependency edges
+  const uint32_t* succ_off;   // [n_calls + 1] CSR of the reverse DONE-dependency edges (released at completion)
   const uint32_t* succ;
+  // call pipelining (program.h): reverse START-dependency edges, released when an item starts; window tables;
+  // one ready flag per (group, global slot), == epoch once the slot's current value is valid
+  const uint32_t* start_succ_off;
+  const uint32_t* start_succ;
+  const uint32_t* win_in_off;
+  const uint32_t* win_out_off;
+  const uint16_t* win_in;
+  const uint16_t* win_out;
+  uint32_t* slot_flags;       // null: the plan is not pipelined (every input is complete before an item starts)
   uint32_t* sched;            // [0] queue head, [1] queue tail, [2] items completed, [3] park buckets released
   uint32_t queue_log2;
   // ring governor (commit modes with a ciphertext ring): items that would overrun the ring are parked
@@ -368,6 +380,18 @@ __device__ __forceinline__ void governor_warp(const EngineParams& p) {
 // its global stores and synchronised with the others before.
 constexpr uint32_t SCHED_NONE = 0xFFFFFFFEu;
 // worker of nthreads threads; `keep` is the worker's shared-memory word (SCHED_NONE on entry)
+// an item has STARTED (its output slots' ready flags are invalidated): consumers waiting only for that may start
+__device__ __forceinline__ void sched_started_cta(const EngineParams& p, uint32_t call_i, uint32_t grp, uint32_t tid,
+                                                  uint32_t nthreads) {
+  const uint32_t lo = p.start_succ_off[call_i], hi = p.start_succ_off[call_i + 1];
+  for (uint32_t k = lo + tid; k < hi; k += nthreads) {
+    const uint32_t it = p.start_succ[k] * p.n_groups + grp;
+    if (atomicSub(p.pending + it, 1u) == 1u) {
+      __threadfence();
+      sched_push(p, it);
+    }
+  }
+}
 __device__ __forceinline__ void sched_complete_cta(const EngineParams& p, uint32_t call_i, uint32_t grp, uint32_t tid,
                                                    uint32_t nthreads, uint32_t* keep) {
   const uint32_t lo = p.succ_off[call_i], hi = p.succ_off[call_i + 1];
@@ -566,20 +590,54 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
     // this thread's instance column of the ciphertext buffer (written when garbling, read when evaluating)
     const uint32_t ginst = grp * G + inst;
     uint4* const ct_out = p.ct + (size_t)(ginst >> p.ct_qshift) * p.ct_quad_stride + (ginst & ((1u << p.ct_qshift) - 1u));
+    // Call pipelining (program.h): the item's levels are cut into windows; the inputs a window reads first are
+    // gathered at its start -- each behind the ready flag of its global slot, its producer may still be running --
+    // and the outputs a window completes are published (label, fence, flag) at its end.  Plans without
+    // pipelining have one window and no flags.
+    uint32_t* const sflags = p.slot_flags ? p.slot_flags + gbase : nullptr;
+    if (sflags) {
+      // the values in this call's output slots are dead (their readers are done dependencies): invalidate them,
+      // then let the consumers that only waited for that start
+      for (uint32_t k = wt; k < task.n_out; k += NT) *(volatile uint32_t*)(sflags + p.call_slots[call.out_off + k]) = 0u;
+      __threadfence();
+      named_bar(bar_id, NT);
+      sched_started_cta(p, call_i, grp, wt, NT);
+    }
+    auto gather_window = [&](uint32_t w) {
+      const uint32_t lo = p.win_in_off[task.win_off + w], hi = p.win_in_off[task.win_off + w + 1];
+      for (uint32_t k = wt; k < (hi - lo) * G; k += NT) {
+        const uint32_t pos = p.win_in[task.win_in_base + lo + k / G];
+        const uint32_t s = p.in_slot[task.in_slot_off + pos];
+        const uint32_t gs = p.call_slots[call.in_off + pos];
+        if (sflags)
+          while (ld_acquire(sflags + gs) != p.epoch) __nanosleep(64);
+        const size_t gi = (gbase + gs) * G + inst;
+        lab[s * G + inst] = __ldcg(p.labels + gi);
+        if (MODE == 1) sval[s * G + inst] = __ldcg(p.vals + gi);
+      }
+    };
+    auto publish_window = [&](uint32_t w) {
+      const uint32_t lo = p.win_out_off[task.win_off + w], hi = p.win_out_off[task.win_off + w + 1];
+      for (uint32_t k = wt; k < (hi - lo) * G; k += NT) {
+        const uint32_t idx = p.win_out[task.win_out_base + lo + k / G];
+        const uint32_t s = p.out_slot[task.out_slot_off + idx];
+        const size_t gi = (gbase + p.call_slots[call.out_off + idx]) * G + inst;
+        p.labels[gi] = lab[s * G + inst];
+        if (MODE == 1) p.vals[gi] = sval[s * G + inst];
+      }
+      if (sflags) {
+        __threadfence();
+        named_bar(bar_id, NT);
+        for (uint32_t k = lo + wt; k < hi; k += NT)
+          *(volatile uint32_t*)(sflags + p.call_slots[call.out_off + p.win_out[task.win_out_base + k]]) = p.epoch;
+      }
+    };
     if (wt < 2 * G) {
       const uint32_t s = wt / G;
       lab[s * G + inst] = __ldcg(p.labels + (gbase + s) * G + inst);
       if (MODE == 1) sval[s * G + inst] = (uint8_t)s;
     }
-    for (uint32_t k = wt; k < task.n_in * G; k += NT) {
-      const uint32_t pos = k / G;
-      const uint32_t s = p.in_slot[task.in_slot_off + pos];
-      if (s != 0xFFFFu) {
-        const size_t gi = (gbase + p.call_slots[call.in_off + pos]) * G + inst;
-        lab[s * G + inst] = __ldcg(p.labels + gi);
-        if (MODE == 1) sval[s * G + inst] = __ldcg(p.vals + gi);
-      }
-    }
+    gather_window(0);
     cp_async_wait<0>();  // chunks 0..3 have landed
     named_bar(bar_id, NT);
     lap(PROF_GATHER);
@@ -627,7 +685,14 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
         n_nf1 = h1.w >> 24;
       }
     }
-    for (uint32_t lvl = 0; lvl < task.n_levels; ++lvl) {
+    uint32_t lvl = 0;
+    for (uint32_t win = 0; win < task.n_windows; ++win) {
+    if (win) {
+      gather_window(win);
+      named_bar(bar_id, NT);
+    }
+    const uint32_t lvl_end = task.n_levels - lvl > task.window_levels ? lvl + task.window_levels : task.n_levels;
+    for (; lvl < lvl_end; ++lvl) {
       // ---- prefetch: first records of level lvl + 1, header of level lvl + 2
       const uint32_t pos1 = pos + n_tot, pos2 = pos1 + n_tot1;
       uint4 rec_a1 = zero4, rec_f1 = zero4;
@@ -733,16 +798,10 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
         n_nf1 = h2.w >> 24;
       }
     }
-    cp_async_wait<0>();
-
-    // ---- scatter produced labels to the instance's global slots
-    for (uint32_t k = wt; k < task.n_out * G; k += NT) {
-      const uint32_t pos = k / G;
-      const uint32_t s = p.out_slot[task.out_slot_off + pos];
-      const size_t gi = (gbase + p.call_slots[call.out_off + pos]) * G + inst;
-      p.labels[gi] = lab[s * G + inst];
-      if (MODE == 1) p.vals[gi] = sval[s * G + inst];
+    // ---- scatter the labels this window completed to the instance's global slots
+    publish_window(win);
     }
+    cp_async_wait<0>();
     if (p.ct_sys) __threadfence_system();  // ciphertexts stored to a peer's ring are ordered before the flags
     else __threadfence();
     named_bar(bar_id, NT);
@@ -1024,6 +1083,13 @@ __global__ void __launch_bounds__(32) k_chain(const uint4* __restrict__ ct, unsi
 }
 
 // ---- small utility kernels
+// call pipelining: the constants and the circuit inputs (global slots [0, n) of every instance group) are valid from the start
+template <int DUMMY>
+__global__ void k_mark_slots(uint32_t* flags, uint32_t n_groups, uint32_t n_global_slots, uint32_t n, uint32_t epoch) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (size_t)n_groups * n) flags[(i / n) * n_global_slots + i % n] = epoch;
+}
+
 // labels of selected global slots -> dense [instance][j] (and optionally the value bits)
 template <int DUMMY>
 __global__ void k_gather_slots(const uint4* labels, const uint8_t* vals, const uint32_t* slots, uint32_t n,

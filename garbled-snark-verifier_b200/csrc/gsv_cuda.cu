@@ -119,6 +119,7 @@ void preload_kernels() {
   preload(k_lane<HASH_BLAKE3, 0>);
   preload(k_lane<HASH_BLAKE3, 1>);
   preload(k_sched_init);
+  preload(k_mark_slots<0>);
   preload(k_seed_expand<0>);
   preload(k_chain<0>);
   preload(k_gather_slots<0>);
@@ -236,28 +237,53 @@ void plan_io(IO& io, P& g) {  // the same field walk for writing (const-cast) an
     io.vec(t.gates); io.vec(t.level_off); io.vec(t.in_slot); io.vec(t.out_slot); io.vec(t.out_pos);
     io.vec(t.seq_gates); io.vec(t.seq_in_slot); io.vec(t.seq_out_slot); io.pod(t.n_seq_slots);
     io.vec(t.pipe_in_need); io.vec(t.pipe_out_ready); io.pod(t.pipe_depth);
+    io.pod(t.window_levels); io.vec(t.win_in); io.vec(t.win_out); io.vec(t.win_in_off); io.vec(t.win_out_off);
+    io.vec(t.in_need_level); io.vec(t.out_ready_level);
   }
   io.vec(g.calls); io.vec(g.call_slots); io.vec(g.deps);
   io.pod(g.n_global_slots); io.pod(g.n_inputs); io.vec(g.output_slots);
   io.pod(g.total_gates); io.pod(g.total_ct); io.pod(g.total_live);
   io.pod(g.max_task_slots); io.pod(g.max_task_seq_slots); io.pod(g.has_levelised); io.pod(g.max_task_in);
-  io.pod(g.max_call_deps);
+  io.pod(g.max_call_deps); io.pod(g.pipelined);
   for (auto& c : g.type_count) io.pod(c);
 }
 void derive_program_stats(gsv_program* p) {
+  p->max_task_levels = 0;
+  p->sum_call_levels = p->critical_path_gates = p->critical_path_levels = 0;
   for (const auto& t : p->prog.tasks) p->max_task_levels = std::max(p->max_task_levels, t.n_levels);
   for (const auto& c : p->prog.calls) p->sum_call_levels += p->prog.tasks[c.task].n_levels;
+  // dependency-chain lengths: what bounds one instance's latency however many SMs there are.  Levels: per-wire
+  // model (pipelined consumers need an input at the start of the window that first reads it, producers publish an
+  // output at the end of the window that completes it, + 2 levels of polling; otherwise at the call's end); done
+  // dependencies always wait for the end.
   const auto& g = p->prog;
   std::vector<uint64_t> fg(g.calls.size()), fl(g.calls.size());
+  std::vector<uint32_t> st(g.n_global_slots, 0);
   for (size_t i = 0; i < g.calls.size(); i++) {
     const auto& c = g.calls[i];
-    uint64_t sg = 0, sl = 0;
+    const gsv::Task& t = g.tasks[c.task];
+    uint64_t sg = 0, S = 0;
     for (uint32_t d = 0; d < c.n_deps; d++) {
       sg = std::max(sg, fg[g.deps[c.dep_off + d]]);
-      sl = std::max(sl, fl[g.deps[c.dep_off + d]]);
+      if (d >= c.n_start_deps) S = std::max(S, fl[g.deps[c.dep_off + d]]);
     }
-    fg[i] = sg + g.tasks[c.task].n_gates_total;
-    fl[i] = sl + g.tasks[c.task].n_levels;
+    if (g.pipelined) {
+      for (uint32_t k = 0; k < t.n_in; k++) {
+        if (k >= t.in_need_level.size() || t.in_need_level[k] == 0xFFFFFFFFu) continue;
+        const uint64_t need = t.in_need_level[k] / t.window_levels * (uint64_t)t.window_levels;
+        const uint64_t avail = (uint64_t)st[g.call_slots[c.in_off + k]] + 2;
+        if (avail > need) S = std::max(S, avail - need);
+      }
+      for (uint32_t k = 0; k < t.n_out; k++) {
+        uint64_t r = t.n_levels;
+        if (k < t.out_ready_level.size()) r = std::min<uint64_t>(r, (t.out_ready_level[k] / t.window_levels + 1) * (uint64_t)t.window_levels);
+        st[g.call_slots[c.out_off + k]] = (uint32_t)(S + r);
+      }
+    } else {
+      for (uint32_t d = 0; d < c.n_start_deps; d++) S = std::max(S, fl[g.deps[c.dep_off + d]]);
+    }
+    fg[i] = sg + t.n_gates_total;
+    fl[i] = S + t.n_levels;
     p->critical_path_gates = std::max(p->critical_path_gates, fg[i]);
     p->critical_path_levels = std::max(p->critical_path_levels, fl[i]);
   }
@@ -269,8 +295,13 @@ std::string plan_cache_path(const std::string& circuit, const gsv_plan_options* 
   uint32_t stamp = 2166136261u;
   for (const char* c = __DATE__ " " __TIME__; *c; c++) stamp = (stamp ^ (uint8_t)*c) * 16777619u;
   char buf[160];
-  snprintf(buf, sizeof buf, ".g%llu.s%u.l%u.%08x.plan", opt ? (unsigned long long)opt->max_task_gates : 0ull,
-           opt ? opt->max_task_slots : 0u, opt ? opt->lane_only : 0u, stamp);
+  uint32_t pl = opt ? opt->pipeline : 0;
+  if (pl == 0) {
+    const char* e = getenv("GSV_PIPELINE");
+    pl = (e && atoi(e) > 0) ? 1 : 2;
+  }
+  snprintf(buf, sizeof buf, ".g%llu.s%u.l%u.p%u.w%u.%08x.plan", opt ? (unsigned long long)opt->max_task_gates : 0ull,
+           opt ? opt->max_task_slots : 0u, opt ? opt->lane_only : 0u, pl, opt ? opt->window_levels : 0u, stamp);
   std::string name = circuit;
   for (char& c : name)
     if (!isalnum((unsigned char)c) && c != '_') c = '_';
@@ -313,12 +344,20 @@ gsv_program* finish_program(std::unique_ptr<gsv::Builder> b, uint32_t root, cons
       po.build_levelised = false;
       po.max_global_slots = 1u << 20;  // lane mode serves thousands of instances: memory before critical path
     }
+    if (opt->window_levels) po.window_levels = opt->window_levels;
+  }
+  {
+    uint32_t pl = opt ? opt->pipeline : 0;
+    if (pl == 0) {
+      const char* e = getenv("GSV_PIPELINE");
+      pl = (e && atoi(e) > 0) ? 1 : 2;
+    }
+    po.pipeline = pl == 1 && po.build_levelised;
   }
   auto p = std::make_unique<gsv_program>();
   p->prog = gsv::plan_program(*b, root, po);
   p->builder = std::move(b);
   p->root = root;
-  for (const auto& t : p->prog.tasks) p->max_task_levels = std::max(p->max_task_levels, t.n_levels);
   if (getenv("GSV_PLAN_DEBUG")) {  // largest working sets, for choosing max_task_slots
     std::vector<const gsv::Task*> ts;
     for (const auto& t : p->prog.tasks) ts.push_back(&t);
@@ -327,24 +366,7 @@ gsv_program* finish_program(std::unique_ptr<gsv::Builder> b, uint32_t root, cons
       fprintf(stderr, "[plan] slots %u levels %u gates %llu in %u out %u  %s\n", ts[i]->n_slots, ts[i]->n_levels,
               (unsigned long long)ts[i]->n_gates_total, ts[i]->n_in, ts[i]->n_out, ts[i]->key.substr(0, 80).c_str());
   }
-  for (const auto& c : p->prog.calls) p->sum_call_levels += p->prog.tasks[c.task].n_levels;
-  {
-    // dependency-chain lengths: what bounds one instance's latency however many SMs there are
-    const auto& g = p->prog;
-    std::vector<uint64_t> fg(g.calls.size()), fl(g.calls.size());
-    for (size_t i = 0; i < g.calls.size(); i++) {
-      const auto& c = g.calls[i];
-      uint64_t sg = 0, sl = 0;
-      for (uint32_t d = 0; d < c.n_deps; d++) {
-        sg = std::max(sg, fg[g.deps[c.dep_off + d]]);
-        sl = std::max(sl, fl[g.deps[c.dep_off + d]]);
-      }
-      fg[i] = sg + g.tasks[c.task].n_gates_total;
-      fl[i] = sl + g.tasks[c.task].n_levels;
-      p->critical_path_gates = std::max(p->critical_path_gates, fg[i]);
-      p->critical_path_levels = std::max(p->critical_path_levels, fl[i]);
-    }
-  }
+  derive_program_stats(p.get());
   if (getenv("GSV_PLAN_DEBUG") && p->prog.has_levelised) {
     // what the critical path would be if a consumer level only waited for the producer LEVELS it needs
     const auto& g = p->prog;
@@ -569,8 +591,12 @@ int gsv_program_execute_plan(const gsv_program* p, int lane_form, const uint8_t*
     // last writer if nobody read it (WAR / WAW), directly in the call's dependency list.
     std::vector<int64_t> last_writer(g.n_global_slots, -1);
     std::vector<std::vector<uint32_t>> readers_since(g.n_global_slots);
+    // the dependency list is two sorted ranges: start dependencies, then done dependencies
+    auto has_done_dep = [&](const gsv::Call& c, uint32_t d) {
+      return std::binary_search(g.deps.begin() + c.dep_off + c.n_start_deps, g.deps.begin() + c.dep_off + c.n_deps, d);
+    };
     auto has_dep = [&](const gsv::Call& c, uint32_t d) {
-      return std::binary_search(g.deps.begin() + c.dep_off, g.deps.begin() + c.dep_off + c.n_deps, d);
+      return std::binary_search(g.deps.begin() + c.dep_off, g.deps.begin() + c.dep_off + c.n_start_deps, d) || has_done_dep(c, d);
     };
     for (size_t ci = 0; ci < g.calls.size(); ci++) {
       const gsv::Call& c = g.calls[ci];
@@ -586,11 +612,11 @@ int gsv_program_execute_plan(const gsv_program* p, int lane_form, const uint8_t*
       for (uint32_t k = 0; k < t.n_out; k++) {
         const uint32_t sl = g.call_slots[c.out_off + k];
         for (uint32_t r : readers_since[sl])
-          if (r != (uint32_t)ci && !has_dep(c, r))
-            throw std::runtime_error("plan misses a WAR edge: call " + std::to_string(ci) + " overwrites slot " +
+          if (r != (uint32_t)ci && !has_done_dep(c, r))
+            throw std::runtime_error("plan misses a WAR edge (must be a done dependency): call " + std::to_string(ci) + " overwrites slot " +
                                      std::to_string(sl) + " read by call " + std::to_string(r));
         if (readers_since[sl].empty() && last_writer[sl] >= 0 && last_writer[sl] != (int64_t)ci &&
-            !has_dep(c, (uint32_t)last_writer[sl]))
+            !has_done_dep(c, (uint32_t)last_writer[sl]))
           throw std::runtime_error("plan misses a WAW edge on slot " + std::to_string(sl));
       }
       for (uint32_t k = 0; k < t.n_out; k++) {
@@ -604,14 +630,42 @@ int gsv_program_execute_plan(const gsv_program* p, int lane_form, const uint8_t*
       loc.assign(std::max<uint32_t>(lane_form ? t.n_seq_slots : t.n_slots, 2), 0xFF);
       loc[0] = 0;
       loc[1] = 1;
-      for (uint32_t i = 0; i < t.n_in; i++)
-        if (in_slot[i] != 0xFFFF) loc[in_slot[i]] = glob[g.call_slots[c.in_off + i]];
-      for (const gsv::DevGate& dg : gates) {
+      auto run = [&](const gsv::DevGate& dg) {
         const uint8_t a = loc[dg.a], b = loc[dg.type == gsv::NOT ? dg.a : dg.b];
         if ((a | b) > 1) throw std::runtime_error("plan reads an unwritten slot in call " + std::to_string(ci) + " (" + t.key + ")");
         loc[dg.c] = eval(dg.type, a, b);
+      };
+      if (lane_form) {
+        for (uint32_t i = 0; i < t.n_in; i++)
+          if (in_slot[i] != 0xFFFF) loc[in_slot[i]] = glob[g.call_slots[c.in_off + i]];
+        for (const gsv::DevGate& dg : gates) run(dg);
+        for (uint32_t k = 0; k < t.n_out; k++) glob[g.call_slots[c.out_off + k]] = loc[out_slot[k]];
+      } else {
+        // exactly what the kernel does: window by window, inputs gathered when their window starts, outputs
+        // published when their window ends (one window for plans without pipelining)
+        const uint32_t n_win = (uint32_t)t.win_in_off.size() - 1;
+        size_t n_gathered = 0, n_published = 0;
+        for (uint32_t w = 0; w < n_win; w++) {
+          for (uint32_t q = t.win_in_off[w]; q < t.win_in_off[w + 1]; q++, n_gathered++) {
+            const uint32_t i = t.win_in[q];
+            loc[in_slot[i]] = glob[g.call_slots[c.in_off + i]];
+          }
+          const uint64_t l0 = (uint64_t)w * t.window_levels, l1 = std::min<uint64_t>(t.n_levels, l0 + t.window_levels);
+          for (uint64_t l = l0; l < l1; l++)
+            for (uint32_t k = t.level_off[l]; k < t.level_off[l + 1]; k++) run(gates[k]);
+          for (uint32_t q = t.win_out_off[w]; q < t.win_out_off[w + 1]; q++, n_published++) {
+            const uint32_t k = t.win_out[q];
+            if (loc[out_slot[k]] > 1) throw std::runtime_error("plan publishes an output before it is written: " + t.key);
+            glob[g.call_slots[c.out_off + k]] = loc[out_slot[k]];
+          }
+        }
+        size_t n_read = 0;
+        for (uint32_t i = 0; i < t.n_in; i++) n_read += in_slot[i] != 0xFFFF;
+        if (n_gathered != n_read || n_published != t.n_out) throw std::runtime_error("window tables incomplete in " + t.key);
+        for (uint32_t k = 0; k < t.n_out; k++)
+          if (glob[g.call_slots[c.out_off + k]] != loc[out_slot[k]])
+            throw std::runtime_error("an output slot of " + t.key + " changed after it was published");
       }
-      for (uint32_t k = 0; k < t.n_out; k++) glob[g.call_slots[c.out_off + k]] = loc[out_slot[k]];
     }
     for (size_t j = 0; j < g.output_slots.size(); j++) {
       if (glob[g.output_slots[j]] > 1) throw std::runtime_error("circuit output slot never written");
@@ -768,6 +822,9 @@ struct gsv_session {
   DevBuf<uint8_t> d_ev_bits;
   DevBuf<uint32_t> d_flags, d_ctrl;  // d_ctrl[1] = error flag, [4..6] = scheduler head / tail / completed
   DevBuf<uint32_t> d_succ_off, d_succ, d_pending;
+  // call pipelining (program.h): reverse start-dependency edges, window tables, per (group, slot) ready flags
+  DevBuf<uint32_t> d_start_succ_off, d_start_succ, d_win_in_off, d_win_out_off, d_slot_flags;
+  DevBuf<uint16_t> d_win_in, d_win_out;
   DevBuf<unsigned long long> d_queue, d_limit;
   DevBuf<uint32_t> d_park_head, d_park_next;
   uint64_t park_q = 1;
@@ -818,8 +875,19 @@ void upload_program(gsv_session* s) {
   std::vector<uint4> seq_gates;
   std::vector<uint16_t> seq_in_slot, seq_out_slot;
   std::vector<DevTaskD> tasks;
+  std::vector<uint32_t> win_in_off, win_out_off;
+  std::vector<uint16_t> win_in, win_out;
   for (const gsv::Task& t : g.tasks) {
     DevTaskD d;
+    d.n_windows = (uint32_t)t.win_in_off.size() - 1;
+    d.window_levels = t.window_levels;
+    d.win_off = (uint32_t)win_in_off.size();
+    d.win_in_base = (uint32_t)win_in.size();
+    d.win_out_base = (uint32_t)win_out.size();
+    win_in_off.insert(win_in_off.end(), t.win_in_off.begin(), t.win_in_off.end());
+    win_out_off.insert(win_out_off.end(), t.win_out_off.begin(), t.win_out_off.end());
+    win_in.insert(win_in.end(), t.win_in.begin(), t.win_in.end());
+    win_out.insert(win_out.end(), t.win_out.begin(), t.win_out.end());
     d.gate_off = (uint32_t)gates.size();
     d.n_gates = (uint32_t)t.gates.size();
     d.n_levels = t.n_levels;
@@ -879,6 +947,12 @@ void upload_program(gsv_session* s) {
   s->d_in_slot.upload(in_slot);
   s->d_out_slot.upload(out_slot);
   s->d_tasks.upload(tasks);
+  if (win_in.empty()) win_in.push_back(0);
+  if (win_out.empty()) win_out.push_back(0);
+  s->d_win_in_off.upload(win_in_off);
+  s->d_win_out_off.upload(win_out_off);
+  s->d_win_in.upload(win_in);
+  s->d_win_out.upload(win_out);
   s->d_calls.upload(calls);
   std::vector<uint32_t> cs = g.call_slots, dp = g.deps, os = g.output_slots;
   if (cs.empty()) cs.push_back(0);
@@ -938,6 +1012,13 @@ EngineParams make_params(gsv_session* s) {
   p.pending = s->d_pending.p;
   p.succ_off = s->d_succ_off.p;
   p.succ = s->d_succ.p;
+  p.start_succ_off = s->d_start_succ_off.p;
+  p.start_succ = s->d_start_succ.p;
+  p.win_in_off = s->d_win_in_off.p;
+  p.win_out_off = s->d_win_out_off.p;
+  p.win_in = s->d_win_in.p;
+  p.win_out = s->d_win_out.p;
+  p.slot_flags = s->d_slot_flags.n ? s->d_slot_flags.p : nullptr;
   p.queue_log2 = s->queue_log2;
   p.sched_limit = s->d_limit.p;
   p.park_head = s->d_park_head.p;
@@ -988,6 +1069,11 @@ void launch_engine(gsv_session* s, int hasher, const EngineParams& p) {
   CUDA_TRY(cudaMemsetAsync(s->d_ctrl.p + 4, 0, 16, s->stream));
   CUDA_TRY(cudaMemsetAsync(s->d_queue.p, 0, s->d_queue.n * 8, s->stream));
   if (s->d_park_head.n) CUDA_TRY(cudaMemsetAsync(s->d_park_head.p, 0xFF, s->d_park_head.n * 4, s->stream));
+  if (p.slot_flags) {  // pipelined plan: constants and circuit inputs are valid from the start
+    const uint32_t n = 2 + s->prog->prog.n_inputs;
+    k_mark_slots<0><<<(unsigned)(((size_t)p.n_groups * n + 255) / 256), 256, 0, s->stream>>>(p.slot_flags, p.n_groups, p.n_global_slots, n, p.epoch);
+    CUDA_TRY(cudaGetLastError());
+  }
   {
     const size_t n_items = (size_t)p.n_calls * p.n_groups;
     k_sched_init<<<(unsigned)std::min<size_t>((n_items + 255) / 256 + 1, 4096), 256, 0, s->stream>>>(p);
@@ -1352,14 +1438,29 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
       // scheduler state: reverse dependency edges, per-item counters, the ready queue
       const size_t n_items = g.calls.size() * (size_t)s->n_groups;
       if (n_items >= (1ull << 30)) throw std::runtime_error("too many work items (calls x instance groups)");
-      std::vector<uint32_t> succ_off(g.calls.size() + 1, 0), succ(g.deps.size());
-      for (uint32_t d : g.deps) succ_off[d + 1]++;
-      for (size_t i = 0; i < g.calls.size(); i++) succ_off[i + 1] += succ_off[i];
-      std::vector<uint32_t> fill(succ_off.begin(), succ_off.end() - 1);
-      for (size_t c = 0; c < g.calls.size(); c++)
-        for (uint32_t k = 0; k < g.calls[c].n_deps; k++) succ[fill[g.deps[g.calls[c].dep_off + k]]++] = (uint32_t)c;
-      s->d_succ_off.upload(succ_off);
-      s->d_succ.upload(succ);
+      // Pipelined plans on the levelised kernel: a call's START dependencies (the producers of its inputs) are
+      // released when the producer starts, the rest at completion.  Lane mode runs whole calls: every edge is
+      // released at completion.
+      const bool piped = g.pipelined && !s->lane_mode;
+      auto reverse_edges = [&](bool start_edges, DevBuf<uint32_t>& d_off, DevBuf<uint32_t>& d_edges) {
+        auto lo = [&](const gsv::Call& c) { return !piped ? 0u : start_edges ? 0u : c.n_start_deps; };
+        auto hi = [&](const gsv::Call& c) { return !piped ? (start_edges ? 0u : c.n_deps) : start_edges ? c.n_start_deps : c.n_deps; };
+        std::vector<uint32_t> off(g.calls.size() + 1, 0);
+        for (const gsv::Call& c : g.calls)
+          for (uint32_t k = lo(c); k < hi(c); k++) off[g.deps[c.dep_off + k] + 1]++;
+        for (size_t i = 0; i < g.calls.size(); i++) off[i + 1] += off[i];
+        std::vector<uint32_t> edges(std::max<size_t>(off.back(), 1), 0), fill(off.begin(), off.end() - 1);
+        for (size_t c = 0; c < g.calls.size(); c++)
+          for (uint32_t k = lo(g.calls[c]); k < hi(g.calls[c]); k++) edges[fill[g.deps[g.calls[c].dep_off + k]]++] = (uint32_t)c;
+        d_off.upload(off);
+        d_edges.upload(edges);
+      };
+      reverse_edges(false, s->d_succ_off, s->d_succ);
+      reverse_edges(true, s->d_start_succ_off, s->d_start_succ);
+      if (piped) {
+        s->d_slot_flags.alloc((size_t)s->n_groups * g.n_global_slots);
+        CUDA_TRY(cudaMemset(s->d_slot_flags.p, 0, s->d_slot_flags.n * 4));
+      }
       s->d_pending.alloc(std::max<size_t>(n_items, 1));
       s->queue_log2 = 4;
       while ((1ull << s->queue_log2) < 2 * n_items) s->queue_log2++;

@@ -1,6 +1,7 @@
 // planner.cpp -- cuts the template DAG into shared-memory-sized tasks, levelises them and
 // emits the call list with global slots and dependencies.  See program.h.
 #include <algorithm>
+#include <iterator>
 #include <atomic>
 #include <memory>
 #include <thread>
@@ -17,14 +18,6 @@ namespace gsv {
 namespace {
 
 constexpr uint32_t UNSET = 0xFFFFFFFEu;
-
-// device level of the record that writes wire `w` (records are `order` in device order)
-uint32_t out_dev_level_of_wire(const FlatStream& fs, const std::vector<uint32_t>& order, const std::vector<uint32_t>& dev_level,
-                               uint32_t w) {
-  for (size_t k = order.size(); k-- > 0;)
-    if (fs.c[order[k]] == w) return dev_level[k];
-  throw std::logic_error("output wire has no producing gate");
-}
 
 // Levelise + slot-pack one flat SSA stream (ids: 0/1 consts, [2, 2+n_in) inputs, then defs).
 Task compile_flat(const FlatStream& fs, const std::string& key, const PlanOptions& opt) {
@@ -185,25 +178,17 @@ Task compile_flat(const FlatStream& fs, const std::string& key, const PlanOption
     std::vector<uint32_t> dev_level(t.gates.size(), 0);  // device level of every record
     for (uint32_t l = 0; l < t.n_levels; l++)
       for (uint32_t k = t.level_off[l]; k < t.level_off[l + 1]; k++) dev_level[k] = l;
-    std::vector<uint32_t> slot_first_read(next_slot, 0xFFFFFFFFu), slot_written(next_slot, 0xFFFFFFFFu);
-    // input slots are never reused before the input's last read and hold nothing else before it, so the first
-    // read of the SLOT is the first read of the input
-    std::vector<uint32_t> in_need(fs.n_inputs, 0xFFFFFFFFu);
-    {
-      std::vector<uint8_t> is_in_slot(next_slot, 0);
-      for (uint32_t i = 0; i < fs.n_inputs; i++)
-        if (t.in_slot[i] != 0xFFFF) is_in_slot[t.in_slot[i]] = 1;
-      std::vector<uint8_t> overwritten(next_slot, 0);
-      for (size_t k = 0; k < t.gates.size(); k++) {
-        const DevGate& dg = t.gates[k];
-        for (uint16_t sl : {dg.a, dg.b})
-          if (is_in_slot[sl] && !overwritten[sl]) slot_first_read[sl] = std::min(slot_first_read[sl], dev_level[k]);
-      }
-      // (gates are in level order; a slot is only re-assigned after its wire's last read, see the colouring)
-      for (size_t k = 0; k < t.gates.size(); k++) overwritten[t.gates[k].c] = 0;
-      for (uint32_t i = 0; i < fs.n_inputs; i++)
-        if (t.in_slot[i] != 0xFFFF) in_need[i] = slot_first_read[t.in_slot[i]];
+    // first device level that reads each wire / device level that writes it (order[k] is the gate of record k)
+    std::vector<uint32_t> first_read(nw, 0xFFFFFFFFu), written_at(nw, 0);
+    for (size_t k = 0; k < t.gates.size(); k++) {
+      const uint32_t g = order[k];
+      first_read[fs.a[g]] = std::min(first_read[fs.a[g]], dev_level[k]);
+      first_read[fs.b[g]] = std::min(first_read[fs.b[g]], dev_level[k]);
+      written_at[fs.c[g]] = dev_level[k];
     }
+    std::vector<uint32_t> in_need(fs.n_inputs, 0xFFFFFFFFu);
+    for (uint32_t i = 0; i < fs.n_inputs; i++)
+      if (t.in_slot[i] != 0xFFFF) in_need[i] = first_read[WIRE_MIN + i];
     t.win_in_off.assign(n_win + 1, 0);
     t.win_out_off.assign(n_win + 1, 0);
     std::vector<std::vector<uint16_t>> ins(n_win), outs(n_win);
@@ -218,7 +203,7 @@ Task compile_flat(const FlatStream& fs, const std::string& key, const PlanOption
         if (o == WIRE_DEAD || o < first_def) continue;
         // device level of the gate that writes this output
         uint32_t lv = t.n_levels ? t.n_levels - 1 : 0;
-        if (opt.pipeline) lv = out_dev_level_of_wire(fs, order, dev_level, o);
+        if (opt.pipeline) lv = written_at[o];
         t.out_ready_level.push_back(lv);
         outs[opt.pipeline ? lv / W : 0].push_back((uint16_t)kk);
         kk++;
@@ -256,6 +241,8 @@ lane_form:
     t.n_slots = 2;
     t.level_off.assign(1, 0);
     t.in_slot.assign(fs.n_inputs, 0xFFFF);
+    t.win_in_off.assign(2, 0);
+    t.win_out_off.assign(2, 0);
   }
   // ---- produced outputs
   for (size_t j = 0; j < fs.outputs.size(); j++) {
@@ -442,6 +429,8 @@ struct Planner {
       e.level_off.assign(1, 0);
       e.seq_in_slot.assign(t.n_in, 0xFFFF);
       e.n_seq_slots = 2;
+      e.win_in_off.assign(2, 0);   // one empty window
+      e.win_out_off.assign(2, 0);
       prog.tasks.push_back(std::move(e));
       return kind[ti] = (int64_t)prog.tasks.size() - 1;
     }
@@ -497,6 +486,7 @@ struct Planner {
     deps.erase(std::unique(deps.begin(), deps.end()), deps.end());
     c.dep_off = (uint32_t)prog.deps.size();
     c.n_deps = (uint32_t)deps.size();
+    c.n_start_deps = opt.pipeline ? c.n_deps : 0;  // producers: start dependencies when calls are pipelined
     prog.deps.insert(prog.deps.end(), deps.begin(), deps.end());
     prog.max_call_deps = std::max(prog.max_call_deps, c.n_deps);
     prog.calls.push_back(c);
@@ -732,7 +722,35 @@ Program plan_program(const Builder& b, uint32_t root, const PlanOptions& opt) {
     for (uint32_t w = 0; w < first_wire; w++) slot_of[w] = w;
     uint32_t next_slot = first_wire;
     std::vector<std::vector<uint32_t>> war(n_calls);
+    // finish[] / begin[]: earliest completion / start of every call over the edges chosen so far.  Pipelined plans: a
+    // consumer starts one window after its producers START and cannot finish before one window after they finish.
     std::vector<uint64_t> finish(n_calls, 0);
+    // when every inter-task wire is available (in levels): a pipelined consumer needs input i only at the start of
+    // the window that first reads it, a pipelined producer publishes output k at the end of the window that
+    // completes it (+ 2 levels of flag-polling latency); without pipelining: at the call's end
+    std::vector<uint32_t> ready_t(n_w, 0);
+    auto call_start = [&](const Call& call, const Task& task) {
+      uint64_t S = 0;
+      for (uint32_t i = 0; i < task.n_in; i++) {
+        if (task.in_slot[i] == 0xFFFF && task.seq_in_slot[i] == 0xFFFF) continue;
+        const uint32_t w = prog.call_slots[call.in_off + i];
+        if (w < first_wire) continue;
+        uint64_t need = 0;
+        if (opt.pipeline && i < task.in_need_level.size() && task.in_need_level[i] != 0xFFFFFFFFu)
+          need = task.in_need_level[i] / task.window_levels * (uint64_t)task.window_levels;
+        const uint64_t avail = ready_t[w] + (opt.pipeline ? 2 : 0);
+        if (avail > need) S = std::max(S, avail - need);
+      }
+      return S;
+    };
+    auto publish = [&](const Call& call, const Task& task, uint64_t S) {
+      for (uint32_t k = 0; k < task.n_out; k++) {
+        uint64_t r = std::max<uint64_t>(1, opt.build_levelised ? task.n_levels : task.n_gates_total);
+        if (opt.pipeline && k < task.out_ready_level.size())
+          r = std::min<uint64_t>(r, (task.out_ready_level[k] / task.window_levels + 1) * (uint64_t)task.window_levels);
+        ready_t[prog.call_slots[call.out_off + k]] = (uint32_t)std::min<uint64_t>(S + r, 0xFFFFFFFFu);
+      }
+    };
     auto weight = [&](uint32_t c) -> uint64_t {
       const Task& t = prog.tasks[prog.calls[c].task];
       return std::max<uint64_t>(1, opt.build_levelised ? t.n_levels : t.n_gates_total);
@@ -746,8 +764,7 @@ Program plan_program(const Builder& b, uint32_t root, const PlanOptions& opt) {
       for (uint32_t pc : release_at[c]) waiting[block_size[pc]].push_back(FreeBlock{block_base[pc], pc, c});
       const Call& call = prog.calls[c];
       const Task& task = prog.tasks[call.task];
-      uint64_t start = 0;  // earliest start over the RAW edges
-      for (uint32_t d = 0; d < call.n_deps; d++) start = std::max(start, finish[prog.deps[call.dep_off + d]]);
+      uint64_t start = call_start(call, task);  // earliest start over the RAW edges
       // unique produced wires of this call, in output order
       std::vector<uint32_t> uniq;
       for (uint32_t k = 0; k < task.n_out; k++) {
@@ -795,6 +812,7 @@ Program plan_program(const Builder& b, uint32_t root, const PlanOptions& opt) {
         next_slot += size;
       }
       finish[c] = start + weight(c);
+      publish(call, task, start);
       for (uint32_t k = 0; k < size; k++) slot_of[uniq[k]] = base + k;
       block_base[c] = base;
       block_size[c] = size;
@@ -812,9 +830,23 @@ Program plan_program(const Builder& b, uint32_t root, const PlanOptions& opt) {
     for (uint32_t c = 0; c < n_calls; c++) {
       Call& call = prog.calls[c];
       std::vector<uint32_t> d(prog.deps.begin() + call.dep_off, prog.deps.begin() + call.dep_off + call.n_deps);
-      d.insert(d.end(), war[c].begin(), war[c].end());
-      std::sort(d.begin(), d.end());
-      d.erase(std::unique(d.begin(), d.end()), d.end());
+      std::vector<uint32_t> w = war[c];
+      std::sort(w.begin(), w.end());
+      w.erase(std::unique(w.begin(), w.end()), w.end());
+      if (opt.pipeline) {
+        // start dependencies (producers) first, then done dependencies (readers of the slots taken over); a call
+        // that is both must have completed
+        std::vector<uint32_t> st;
+        std::set_difference(d.begin(), d.end(), w.begin(), w.end(), std::back_inserter(st));
+        call.n_start_deps = (uint32_t)st.size();
+        d = st;
+        d.insert(d.end(), w.begin(), w.end());
+      } else {
+        d.insert(d.end(), w.begin(), w.end());
+        std::sort(d.begin(), d.end());
+        d.erase(std::unique(d.begin(), d.end()), d.end());
+        call.n_start_deps = 0;
+      }
       call.dep_off = (uint32_t)deps.size();
       call.n_deps = (uint32_t)d.size();
       deps.insert(deps.end(), d.begin(), d.end());
@@ -833,6 +865,7 @@ Program plan_program(const Builder& b, uint32_t root, const PlanOptions& opt) {
     prog.max_task_seq_slots = std::max(prog.max_task_seq_slots, t.n_seq_slots);
     prog.has_levelised = opt.build_levelised;
   }
+  prog.pipelined = opt.pipeline && opt.build_levelised;
   if (prog.total_gates != rt.total_gates || prog.total_ct != rt.total_ct)
     throw std::logic_error("planner lost gates: " + std::to_string(prog.total_gates) + " vs " +
                            std::to_string(rt.total_gates));
