@@ -281,6 +281,16 @@ __device__ __forceinline__ void chain_warp(const EngineParams& p, const uint32_t
 // tickets in FIFO order.  Unlike claiming items in emission order, a worker never sits on an item
 // whose inputs are not there, so all of the circuit's call-level parallelism is exposed however many
 // instance groups share the workers.  Each slot of the circular queue is tagged with its round.
+// named barrier over n threads that also ANDs a predicate across them
+__device__ __forceinline__ bool named_bar_and(uint32_t id, uint32_t n, bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %3, 0;\n\tbarrier.red.and.pred p, %1, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r)
+      : "r"(id), "r"(n), "r"((uint32_t)pred)
+      : "memory");
+  return r != 0u;
+}
 constexpr uint32_t SCHED_DONE = 0xFFFFFFFFu;
 __device__ __forceinline__ void sched_push(const EngineParams& p, uint32_t item) {
   const uint32_t pos = atomicAdd(p.sched + 1, 1u);
@@ -561,12 +571,34 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
     }
     named_bar(bar_id, NT);
     const uint32_t item = *ctrl;
-    lap(PROF_WAIT);
     if (item == SCHED_DONE) break;
     const uint32_t call_i = item / p.n_groups;
     const uint32_t grp = item - call_i * p.n_groups;
     const DevCallD call = p.calls[call_i];
     const DevTaskD task = p.tasks[call.task];
+    // Call pipelining (program.h): the item's levels are cut into windows; the inputs a window reads first are
+    // gathered at its start -- each behind the ready flag of its global slot, its producer may still be running --
+    // and the outputs a window completes are published (label, fence, flag) at its end.  Plans without
+    // pipelining have one window and no flags.
+    const size_t gbase = (size_t)grp * p.n_global_slots;
+    uint32_t* const sflags = p.slot_flags ? p.slot_flags + gbase : nullptr;
+    if (sflags) {
+      // An item is queued as soon as its producers have STARTED.  It only occupies the worker once the inputs of
+      // its first window are there; until then it goes back to the end of the queue, so workers are not held by
+      // items whose producers are still far from publishing.
+      bool ok = true;
+      const uint32_t lo = p.win_in_off[task.win_off], hi = p.win_in_off[task.win_off + 1];
+      for (uint32_t k = lo + wt; k < hi; k += NT)
+        ok &= *(volatile uint32_t*)(sflags + p.call_slots[call.in_off + p.win_in[task.win_in_base + k]]) == p.epoch;
+      if (!named_bar_and(bar_id, NT, ok)) {
+        if (wt == 0) {
+          __nanosleep(256);
+          sched_push(p, item);
+        }
+        continue;
+      }
+    }
+    lap(PROF_WAIT);
 
     // ---- start streaming the task's gate records (independent of the producers)
     const uint4* gsrc = p.gates + task.gate_off;
@@ -584,17 +616,11 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
     // ring position of the call's first ciphertext (a task never exceeds half the ring)
     const unsigned long long ct_pos0 = p.ct_ring ? call.ct_base % p.ct_ring : call.ct_base;
     // ---- gather inputs (and the two constant wires) into shared memory
-    const size_t gbase = (size_t)grp * p.n_global_slots;
     uint4 delta = make_uint4(0, 0, 0, 0);
     if (MODE == 0) delta = p.delta[grp * G + inst];
     // this thread's instance column of the ciphertext buffer (written when garbling, read when evaluating)
     const uint32_t ginst = grp * G + inst;
     uint4* const ct_out = p.ct + (size_t)(ginst >> p.ct_qshift) * p.ct_quad_stride + (ginst & ((1u << p.ct_qshift) - 1u));
-    // Call pipelining (program.h): the item's levels are cut into windows; the inputs a window reads first are
-    // gathered at its start -- each behind the ready flag of its global slot, its producer may still be running --
-    // and the outputs a window completes are published (label, fence, flag) at its end.  Plans without
-    // pipelining have one window and no flags.
-    uint32_t* const sflags = p.slot_flags ? p.slot_flags + gbase : nullptr;
     if (sflags) {
       // the values in this call's output slots are dead (their readers are done dependencies): invalidate them,
       // then let the consumers that only waited for that start

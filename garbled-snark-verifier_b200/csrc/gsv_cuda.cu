@@ -288,6 +288,13 @@ void derive_program_stats(gsv_program* p) {
     p->critical_path_levels = std::max(p->critical_path_levels, fl[i]);
   }
 }
+// gsv_plan_options.pipeline: 1 on, 2 off, 0 = default (on; GSV_PIPELINE=0 in the environment turns it off)
+uint32_t pipeline_option(const gsv_plan_options* opt) {
+  if (opt && opt->pipeline) return opt->pipeline == 1 ? 1u : 2u;
+  const char* e = getenv("GSV_PIPELINE");
+  return (e && atoi(e) == 0) ? 2u : 1u;
+}
+
 std::string plan_cache_path(const std::string& circuit, const gsv_plan_options* opt) {
   const char* dir = getenv("GSV_PLAN_CACHE_DIR");
   if (!dir || !*dir) return "";
@@ -295,11 +302,7 @@ std::string plan_cache_path(const std::string& circuit, const gsv_plan_options* 
   uint32_t stamp = 2166136261u;
   for (const char* c = __DATE__ " " __TIME__; *c; c++) stamp = (stamp ^ (uint8_t)*c) * 16777619u;
   char buf[160];
-  uint32_t pl = opt ? opt->pipeline : 0;
-  if (pl == 0) {
-    const char* e = getenv("GSV_PIPELINE");
-    pl = (e && atoi(e) > 0) ? 1 : 2;
-  }
+  const uint32_t pl = pipeline_option(opt);
   snprintf(buf, sizeof buf, ".g%llu.s%u.l%u.p%u.w%u.%08x.plan", opt ? (unsigned long long)opt->max_task_gates : 0ull,
            opt ? opt->max_task_slots : 0u, opt ? opt->lane_only : 0u, pl, opt ? opt->window_levels : 0u, stamp);
   std::string name = circuit;
@@ -346,14 +349,7 @@ gsv_program* finish_program(std::unique_ptr<gsv::Builder> b, uint32_t root, cons
     }
     if (opt->window_levels) po.window_levels = opt->window_levels;
   }
-  {
-    uint32_t pl = opt ? opt->pipeline : 0;
-    if (pl == 0) {
-      const char* e = getenv("GSV_PIPELINE");
-      pl = (e && atoi(e) > 0) ? 1 : 2;
-    }
-    po.pipeline = pl == 1 && po.build_levelised;
-  }
+  po.pipeline = pipeline_option(opt) == 1 && po.build_levelised;
   auto p = std::make_unique<gsv_program>();
   p->prog = gsv::plan_program(*b, root, po);
   p->builder = std::move(b);
@@ -368,6 +364,21 @@ gsv_program* finish_program(std::unique_ptr<gsv::Builder> b, uint32_t root, cons
   }
   derive_program_stats(p.get());
   if (getenv("GSV_PLAN_DEBUG") && p->prog.has_levelised) {
+    {  // worker time (levels, AES gates) by the shared-memory footprint of the task: what smaller workers could take
+      const uint32_t edges[] = {128, 256, 384, 512, 640, 768, 1024, 1280, 1536, 2048, 0xFFFFFFFFu};
+      uint64_t lv[11] = {0}, ct[11] = {0}, n[11] = {0};
+      for (const auto& c : p->prog.calls) {
+        const gsv::Task& t = p->prog.tasks[c.task];
+        int b = 0;
+        while (t.n_slots > edges[b]) b++;
+        lv[b] += t.n_levels;
+        ct[b] += t.n_ct;
+        n[b]++;
+      }
+      for (int b = 0; b < 11; b++)
+        fprintf(stderr, "[plan] tasks with <= %u slots: %llu calls, %llu levels, %llu ciphertexts\n", edges[b],
+                (unsigned long long)n[b], (unsigned long long)lv[b], (unsigned long long)ct[b]);
+    }
     // what the critical path would be if a consumer level only waited for the producer LEVELS it needs
     const auto& g = p->prog;
     std::vector<uint64_t> slot_time(g.n_global_slots, 0);

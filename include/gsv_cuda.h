@@ -101,9 +101,10 @@ typedef struct {
   uint64_t max_task_gates; /* 0 = default (600000) */
   uint32_t max_task_slots; /* 0 = default (1536 shared-memory label slots per instance) */
   uint32_t lane_only;      /* 1 = build only the lane-mode (emission order) task form: large circuits */
-  uint32_t pipeline;       /* call pipelining of the levelised form: a consumer call starts once its producers have
-                              STARTED and gathers each input when its ready flag is set, producers publish outputs
-                              window by window.  0 = default (GSV_PIPELINE environment variable, else off), 1 = on, 2 = off */
+  uint32_t pipeline;       /* call pipelining of the levelised form: a consumer call is queued once its producers have
+                              STARTED, runs once the inputs of its first window are there and gathers every later input
+                              when its ready flag is set; producers publish outputs window by window.
+                              0 = default (on; GSV_PIPELINE=0 in the environment turns it off), 1 = on, 2 = off */
   uint32_t window_levels;  /* device levels per pipelining window; 0 = default (64) */
 } gsv_plan_options;
 
