@@ -257,3 +257,24 @@ def test_lane_only_plan_keeps_dependencies(gsv):
     assert both.critical_path_gates > both.n_gates // 8
     assert lane.critical_path_gates > lane.n_gates // 8
     assert lane.critical_path_levels == 0 and both.critical_path_levels > 0
+
+
+@pytest.mark.parametrize("window", [1, 16, 64])
+@pytest.mark.parametrize("name", ["fq_mul", "fq12_mul", "g1_add"])
+def test_call_pipelining_plans(gsv, name, window):
+    """Call pipelining (PlanOptions.pipeline): the same calls with START / DONE dependencies and window tables.  The
+    host walker runs every call window by window -- inputs gathered at the window that first reads them, outputs
+    published at the window that completes them -- and audits that every reader of a slot a call overwrites is one
+    of its DONE dependencies; the critical path in levels can only shrink."""
+    plain = gsv.Program(name, pipeline=False)
+    piped = gsv.Program(name, pipeline=True, window_levels=window)
+    assert (piped.n_calls, piped.n_gates, piped.n_ciphertexts) == (plain.n_calls, plain.n_gates, plain.n_ciphertexts)
+    assert piped.critical_path_levels <= plain.critical_path_levels
+    if plain.n_calls > 1:
+        assert piped.critical_path_levels < plain.critical_path_levels
+    rng = np.random.default_rng(9)
+    for _ in range(2):
+        bits = rng.integers(0, 2, plain.n_inputs, dtype=np.uint8)
+        want = plain.execute(bits)
+        assert np.array_equal(piped.execute_plan(bits, lane_form=False), want)
+        assert np.array_equal(piped.execute_plan(bits, lane_form=True), want)

@@ -527,3 +527,37 @@ def test_evaluate_fed_from_host_streams_through_a_ring(gsv, orc, circuit, tmp_pa
     with pytest.raises(gsv.GsvError) as ex:
         e.evaluate(gsv.HASH_AES, res.true_label1, res.false_label0, active, bits, ct_streams=short, ct_ring_log2=18)
     assert ex.value.code == -5
+
+
+@pytest.mark.parametrize("name,B,G,window", [("fq_mul", 4, 2, 16), ("fq12_mul", 8, 4, 64), ("fq12_mul", 3, 1, 1),
+                                             ("fq_inverse", 4, 4, 64)])
+def test_call_pipelining_matches_the_plain_plan(gsv, name, B, G, window):
+    """Call pipelining (gsv_plan_options.pipeline: calls queued when their producers START, inputs gathered
+    window by window behind per-slot ready flags, outputs published early) changes the schedule only: labels,
+    the whole ciphertext stream, its chain commitment, the evaluation and ExecuteMode are those of the plain plan."""
+    seeds = list(range(900, 900 + B))
+    plain = gsv.Program(name, pipeline=False)
+    piped = gsv.Program(name, pipeline=True, window_levels=window)
+    assert piped.n_calls == plain.n_calls and piped.n_ciphertexts == plain.n_ciphertexts
+    assert piped.critical_path_levels <= plain.critical_path_levels
+    out = []
+    for p in (plain, piped):
+        s = gsv.Session(p, B, group=G, ct_mode=gsv.CT_KEEP, exec_mode=1)
+        for _ in range(2):  # twice: the ready flags of the first call are stale in the second (epochs)
+            r = s.garble(seeds, gsv.HASH_AES)
+        out.append((s, r))
+    (s0, r0), (s1, r1) = out
+    for f in ("delta", "input_label0", "output_label0", "ct_commit"):
+        assert np.array_equal(getattr(r0, f), getattr(r1, f)), f
+    assert np.array_equal(s0.read_ciphertexts(B - 1), s1.read_ciphertexts(B - 1))
+    rng = np.random.default_rng(11)
+    bits = rng.integers(0, 2, (B, piped.n_inputs), dtype=np.uint8)
+    ev = s1.evaluate(gsv.HASH_AES, r1.true_label1, r1.false_label0, _eval_inputs(r1, bits), bits)
+    want = np.stack([piped.execute(b) for b in bits])
+    assert np.array_equal(ev.output_bits, want)
+    assert np.array_equal(ev.ct_commit, r0.ct_commit)
+    sel = r0.output_label0.copy()
+    sel[want.astype(bool)] ^= np.broadcast_to(r0.delta[:, None, :], sel.shape)[want.astype(bool)]
+    assert np.array_equal(ev.output_active, sel)
+    got, _ = s1.execute(bits)
+    assert np.array_equal(got, want)
