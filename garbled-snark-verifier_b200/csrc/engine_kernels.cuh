@@ -689,9 +689,11 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
     constexpr uint32_t SLOT_B = 16u * G;                      // bytes per label slot (G instances)
     const uint32_t lab_s = (uint32_t)__cvta_generic_to_shared(lab) + inst * 16u;
     const uint32_t sval_s = (uint32_t)__cvta_generic_to_shared(sval) + inst;
-    const uint32_t f_idx = wt / G;                            // gate index inside a free pass
+    // gate index inside a free pass, counted from the worker's LAST threads: the non-free gates start at its
+    // first threads, so in a narrow level the free gates run in other warps, beside the hashes, not after them
+    const uint32_t f_idx = (NT - 1u - wt) / G;
     const uint32_t f_per_pass = NT / G;
-    const uint32_t a_idx = MODE == 0 ? wt / (2 * G) : f_idx;  // gate index inside an AES pass
+    const uint32_t a_idx = MODE == 0 ? wt / (2 * G) : wt / G;  // gate index inside an AES pass
     const uint32_t a_per_pass = MODE == 0 ? NT / (2 * G) : f_per_pass;
     const uint32_t half = (wt / G) & 1u;                      // garbling: which of the two hashes
     auto rec_at = [&](uint32_t idx) { return lds128(ring_s + ((idx & RMASK) << 4)); };

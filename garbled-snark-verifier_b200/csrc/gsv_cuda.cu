@@ -1653,6 +1653,7 @@ int gsv_garble_batch(gsv_session* s, int hasher, const uint64_t* seeds, gsv_garb
     }
     launch_engine<0>(s, hasher, p);
     launches += 2;  // k_sched_init + the persistent engine kernel
+    if (s->d_slot_flags.n) launches++;  // k_mark_slots (pipelined plan)
     CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
     std::vector<uint8_t> host_commits;
     double host_ms = 0.0;
@@ -1961,6 +1962,7 @@ int gsv_evaluate_batch(gsv_session* s, int hasher, gsv_evaluate_io* io) {
     }
     launch_engine<1>(s, hasher, p);
     launches += 2;
+    if (s->d_slot_flags.n) launches++;  // k_mark_slots (pipelined plan)
     CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
     std::vector<uint8_t> fed_commits;
     if (host_fed) {

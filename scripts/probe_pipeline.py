@@ -1,7 +1,7 @@
 """Call pipelining probe: the same circuit planned without and with pipelining (PlanOptions.pipeline), garbled with the
 same seeds -- results must be identical (labels and chain commitments), times are compared.
 
-usage: probe_pipeline.py [circuits=fq_mul,fq12_mul,fq12_inverse,g1_msm1] [B=16] [G=4] [W=64,16] [ct_modes=0,1] [reps=3] [execute]
+usage: probe_pipeline.py [circuits=fq_mul,fq12_mul,fq12_inverse,g1_msm1] [B=16] [G=4] [W=64,16] [ct_modes=0,1] [reps=3] [execute] [noref]
 """
 import json
 import os
@@ -18,7 +18,7 @@ B, G = int(kv.get("B", 16)), int(kv.get("G", 4))
 rows = []
 for circ in kv.get("circuits", "fq_mul,fq12_mul,fq12_inverse,g1_msm1").split(","):
     ref = None
-    for W in [0] + [int(w) for w in kv.get("W", "64,16").split(",")]:
+    for W in ([] if "noref" in flags else [0]) + [int(w) for w in kv.get("W", "64,16").split(",")]:
         prog = g.Program(circ, pipeline=bool(W), window_levels=W)
         for ct_mode in [int(m) for m in kv.get("ct_modes", "0,1").split(",")]:
             s = g.Session(prog, B, group=G, ct_mode=ct_mode, exec_mode=1)
@@ -31,7 +31,7 @@ for circ in kv.get("circuits", "fq_mul,fq12_mul,fq12_inverse,g1_msm1").split(","
             if W == 0:
                 ref = ref or {}
                 ref[key] = got
-            same = ref[key] == got
+            same = ref is None or ref[key] == got
             row = dict(circuit=circ, window=W, ct_mode=ct_mode, ms=round(best.ms_garble, 3), same=same,
                        crit=prog.critical_path_levels, calls=prog.n_calls,
                        us_per_level=round(1e3 * best.ms_garble / max(prog.critical_path_levels, 1), 3),
