@@ -361,6 +361,7 @@ def main():
               "batch": dict(circuit="fq12_mul", instances=6144, sessions=1, exec_mode=2, group=0, ct_mode="commit",
                             steps=3)}[args.workload]
     args.sessions_auto = args.sessions is None
+    args.instances_auto = args.instances is None
     for k, v in preset.items():
         if getattr(args, k) is None:
             setattr(args, k, v)
@@ -409,6 +410,19 @@ def main():
         # few host CPUs per rank (8 GPUs on a 32-CPU host): one fold thread per session, each interleaving all four
         # quads of its session (the VAES throughput cap, 640 M blocks/s per thread), and one session per CPU
         S = max(S, min(4, cpu_share))
+    instances_note = None
+    if ct_mode == g.CT_COMMIT_HOST and args.instances_auto:
+        # The serial chains are folded by host AES-NI threads (~0.5 G blocks/s per CPU with several chains interleaved):
+        # when a rank has very few CPUs (many GPUs on a small host) a 16-instance step can take so long that
+        # `--steps 20 --warmup 5` no longer ends within the driver's window.  Shrink the step then, and say so.
+        n_steps_all = max(1, args.warmup + args.steps)
+        per_step_s = 720.0 / n_steps_all
+        cap = int(per_step_s * min(cpu_share, S * ((B + 3) // 4)) * 0.5e9 / max(1, prog.n_ciphertexts))
+        if cap < B:
+            B_new = max(4, cap // 4 * 4)
+            instances_note = (f"{B_new} instead of {B} instances per step: {cpu_share} host CPUs per rank fold about "
+                              f"{0.5 * cpu_share:.1f} G ciphertexts/s, a {B}-instance step would not fit the run's time window")
+            B = B_new
     fold_threads = args.host_threads or max(1, min((B + 3) // 4, max(1, cpu_share - (1 if cpu_share >= 6 else 0)) // S))
     sm_total = torch.cuda.get_device_properties(local).multi_processor_count
     sm_limit = 0 if S == 1 else (sm_total - SM_RESERVE) // S
@@ -600,6 +614,7 @@ def main():
                 "seeds": "ChaCha20Rng::seed_from_u64(1234) u64 draws (garbler.rs:201-203)",
                 "l2": "inputs larger than L2 (label + ciphertext state >> 126 MB)",
                 "parallelism": f"instances sharded over {world} GPU(s); NCCL all-gather of commitments only",
+                **({"instances_note": instances_note} if instances_note else {}),
             },
             "phases_ms_per_step": {"seed_expand": seed_ms / args.steps, "garble_kernel": garble_ms / args.steps,
                                    "commit_tail_after_kernel": commit_ms / args.steps, "step_in_flight": step_ms / args.steps},
