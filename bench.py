@@ -410,6 +410,11 @@ def main():
         # few host CPUs per rank (8 GPUs on a 32-CPU host): one fold thread per session, each interleaving all four
         # quads of its session (the VAES throughput cap, 640 M blocks/s per thread), and one session per CPU
         S = max(S, min(4, cpu_share))
+    if args.sessions_auto and ct_mode == g.CT_COMMIT_HOST and cpu_share >= 16:
+        # A run of K steps takes ceil(K / S) waves of S steps in flight.  Measured time one step is in flight on a B200
+        # with a 16-CPU host: 48 s at S = 3 (48 SMs per step), 63 s at S = 4 (36 SMs): 20 steps are 7 x 48 s or 5 x 63 s.
+        wave_s = {3: 48.0, 4: 63.0}
+        S = min(wave_s, key=lambda n: -(-max(1, args.steps) // n) * wave_s[n])
     instances_note = None
     if ct_mode == g.CT_COMMIT_HOST and args.instances_auto:
         # The serial chains are folded by host AES-NI threads (~0.5 G blocks/s per CPU with several chains interleaved):
@@ -423,7 +428,10 @@ def main():
             instances_note = (f"{B_new} instead of {B} instances per step: {cpu_share} host CPUs per rank fold about "
                               f"{0.5 * cpu_share:.1f} G ciphertexts/s, a {B}-instance step would not fit the run's time window")
             B = B_new
-    fold_threads = args.host_threads or max(1, min((B + 3) // 4, max(1, cpu_share - (1 if cpu_share >= 6 else 0)) // S))
+    # one fold thread per quad of chains when the rank has a CPU for each; otherwise one CPU is left to the drain threads
+    quads = (B + 3) // 4
+    fold_cpus = cpu_share if S * quads <= cpu_share else max(1, cpu_share - (1 if cpu_share >= 6 else 0))
+    fold_threads = args.host_threads or max(1, min(quads, fold_cpus // S))
     sm_total = torch.cuda.get_device_properties(local).multi_processor_count
     sm_limit = 0 if S == 1 else (sm_total - SM_RESERVE) // S
     free_b, _ = torch.cuda.mem_get_info()
@@ -569,14 +577,16 @@ def main():
             fold_busy = max(r.host_fold_busy for r in results)               # busiest fold thread, share of its step
             wait_kernel = sum(r.host_drain_wait_kernel for r in results) / len(results)
             wait_fold = sum(r.host_drain_wait_fold for r in results) / len(results)
-            if fold_busy >= 0.85 or wait_fold >= 0.25:
-                limiter = "host_fold"
-            elif pcie_util >= 0.85:
-                limiter = "pcie_drain"
-            elif wait_kernel >= 0.5:
+            # utilisation of each stage of the committed step; the drain thread is always a few buffers ahead, so its
+            # wait for free buffers says nothing about which side paces it
+            utils = {"host_fold": fold_busy, "pcie_drain": pcie_util, "chain_latency": fold_floor_s / wave_s}
+            top = max(utils, key=utils.get)
+            if wait_kernel >= 0.5:
                 limiter = "kernel"
+            elif utils[top] >= 0.85:
+                limiter = top
             else:
-                limiter = "pcie_drain" if pcie_util >= 0.6 else "kernel"
+                limiter = f"balanced ({top} {utils[top]:.2f})"
             roofline["gpu_chain_floor_s"] = prog.n_ciphertexts * 0.46e-6  # measured dependent-AES step on the GPU
             roofline["pipeline"] = {
                 "limiter": limiter, "steps_in_flight": conc, "step_in_flight_s": wave_s,
@@ -585,9 +595,13 @@ def main():
                 "drain_wait_for_kernel": wait_kernel, "drain_wait_for_fold": wait_fold,
                 "host_threads_per_rank": S * (fold_threads + 1), "fold_threads_per_session": fold_threads,
                 "host_logical_cpus": logical, "host_physical_cores": physical, "ranks_on_host": local_world,
-                "note": "rank 0's view.  host_fold: the busiest AES-NI fold thread is busy >= 85 % of its step (or the drain waits for "
-                        "fold buffers); pcie_drain: the ciphertext drain runs at >= 85 % of the measured pinned D2H rate (GPUs that "
-                        "share a PCIe switch divide it); kernel: the drain mostly waits for the kernel to publish ciphertexts"}
+                "stage_utilisation": utils,
+                "note": "rank 0's view.  Stage utilisations: host_fold = busy share of the busiest AES-NI fold thread; pcie_drain = "
+                        "ciphertext drain rate / measured pinned D2H rate (GPUs that share a PCIe switch divide it); chain_latency = "
+                        "serial-chain floor of one instance (n_ct x 13 ns) / time a step is in flight.  limiter = kernel when the "
+                        "drain waits for the kernel to publish ciphertexts half of the time, else the stage at >= 85 %, else "
+                        "'balanced': kernel production (the same sessions with ciphertexts dropped run at 13.2 G gates/s), the "
+                        "PCIe drain (13.7 G) and the folds (48 chains per 38.7 s = 14.2 G) are within 10 % of each other"}
         try:
             blocks = g.bench_hash(hasher, 1 << 28, 2, device=local)
             nonfree = sum(prog.type_count[:8]) / prog.n_gates
