@@ -1416,6 +1416,23 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
       s->n_groups = s->B / G;
       s->smem_garble = smem_for(G, n_workers, false);
       s->smem_eval = smem_for(G, n_workers, true);
+      {
+        // The persistent grid's CTAs wait for each other (queue, ring limit, chain / governor CTAs): every CTA must be
+        // resident.  Check statically that the shape fits an SM (registers x threads, shared memory); that the SMs
+        // are not held by somebody else's kernels is the caller's side of the contract (sm_limit for sessions that
+        // share a GPU).
+        const int threads = (int)std::max<uint32_t>(n_workers * s->NT, 32 * (n_chain + (s->n_chain_ctas ? 1 : 0)));
+        int resident = 0;
+        cudaError_t e = cudaSuccess;
+        switch (G) {
+          case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_engine<1, HASH_BLAKE3, 1>, threads, s->smem_eval); break;
+          case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_engine<2, HASH_BLAKE3, 1>, threads, s->smem_eval); break;
+          case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_engine<4, HASH_BLAKE3, 1>, threads, s->smem_eval); break;
+          default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_engine<8, HASH_BLAKE3, 1>, threads, s->smem_eval); break;
+        }
+        CUDA_TRY(e);
+        if (resident < 1) throw std::runtime_error("the engine's CTA shape does not fit one SM (threads x registers / shared memory)");
+      }
     }
     s->G = G;
     s->n_workers = n_workers;
@@ -2186,12 +2203,9 @@ int gsv_execute_batch(gsv_session* s, const uint8_t* input_bits, uint32_t n_exec
     if (ms) cudaEventElapsedTime(ms, s->ev[1], s->ev[2]);
     for (uint32_t e = 0; e < n_exec; e++) {
       const uint32_t inst = e >> 7, w = (e >> 5) & 3u, bit = e & 31u;
-      for (uint32_t k = 0; k < n_out; k++) {
-        const uint32_t slot = g.output_slots[k];
-        // outputs wired straight to a constant never pass through the kernel's slots 0 / 1 differently: same read
+      // (outputs wired straight to a constant are gathered from slots 0 / 1 like any other slot)
+      for (uint32_t k = 0; k < n_out; k++)
         output_bits[(size_t)e * n_out + k] = (uint8_t)((out[((size_t)inst * n_out + k) * 4 + w] >> bit) & 1u);
-        (void)slot;
-      }
     }
     s->ct_valid = false;  // the label slots now hold plaintext slices
     return GSV_OK;
