@@ -123,9 +123,16 @@ enum { PROF_WAIT = 0, PROF_GATHER, PROF_AES_LEVELS, PROF_FREE_LEVELS, PROF_SCATT
        PROF_N_FREE_LEVELS, PROF_N_ITEMS, PROF_N_PASSES, PROF_TOTAL, PROF_WORDS };
 
 // Gate-record staging of the levelised mode: a task's records are contiguous in level order, so
-// they are streamed global -> shared with cp.async in chunks of GATE_CHUNK records, GATE_CHUNKS
-// chunks in flight per worker, independent of the level structure (levels are <= GATE_CHUNK wide
-// and carry their width in their first record).  The level loop then never waits on L2.
+// they are streamed global -> shared in chunks of GATE_CHUNK records (2 KB), GATE_CHUNKS chunks in
+// flight per worker, independent of the level structure (levels are <= GATE_CHUNK wide and carry
+// their width in their first record).  The level loop then never waits on L2.
+// GSV_RECORD_TMA (default): one thread per worker issues each chunk as ONE bulk async copy
+// (cp.async.bulk global -> shared, the TMA engine's 1-D form) that completes on the mbarrier of the
+// chunk's ring slot; the worker's threads wait on that mbarrier's phase when the level loop crosses
+// into the chunk's look-ahead window.  GSV_RECORD_TMA=0: 16-byte cp.async per thread (Ampere style).
+#ifndef GSV_RECORD_TMA
+#define GSV_RECORD_TMA 1
+#endif
 constexpr uint32_t GATE_CHUNK = 128;
 constexpr uint32_t GATE_CHUNKS = 4;
 constexpr uint32_t GATE_RING = GATE_CHUNK * GATE_CHUNKS;  // records (8 KB) per worker
@@ -136,6 +143,32 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+// bulk async copy global -> shared (bytes a multiple of 16, both sides 16-byte aligned), completion counted on mbar
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_addr, const void* g, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr),
+               "l"(g), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(mbar), "r"(parity)
+      : "memory");
+  return done != 0u;
 }
 
 // shared memory through 32-bit shared-window addresses
@@ -549,6 +582,18 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
       reinterpret_cast<uint4*>(tail + tail_bytes) + n_workers * GATE_RING) + worker * PROF_WORDS;
   if (prof)
     for (int i = 0; i < PROF_WORDS; i++) wprof[i] = 0;
+#if GSV_RECORD_TMA
+  // one mbarrier per slot of the worker's record ring, behind the profile words; ring_par holds, per slot, the
+  // phase parity the next wait expects (every issued chunk is waited for exactly once, by every thread)
+  const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<const uint4*>(tail + tail_bytes) + n_workers * GATE_RING) +
+                          n_workers * PROF_WORDS * 8u + worker * (8u * GATE_CHUNKS);
+  uint32_t ring_par = 0;
+  if (wt == 0) {
+#pragma unroll
+    for (uint32_t k = 0; k < GATE_CHUNKS; k++) mbar_init(mbar_s + 8u * k, 1u);
+    mbar_init_fence();
+  }
+#endif
   long long t_prev = prof ? clock64() : 0;
   const long long t_begin = t_prev;
   auto lap = [&](int slot) {
@@ -602,7 +647,27 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
 
     // ---- start streaming the task's gate records (independent of the producers)
     const uint4* gsrc = p.gates + task.gate_off;
-    uint32_t issued = 0;  // chunks requested so far (one cp.async group each, uniform over the worker)
+    uint32_t issued = 0;  // chunks requested so far (uniform over the worker)
+#if GSV_RECORD_TMA
+    const uint32_t n_chunks = (task.n_gates + GATE_CHUNK - 1) / GATE_CHUNK;
+    auto issue_chunk = [&]() {
+      if (wt == 0 && issued < n_chunks) {
+        const uint32_t base = issued * GATE_CHUNK, slot = issued & (GATE_CHUNKS - 1);
+        const uint32_t bytes = min(GATE_CHUNK, task.n_gates - base) * 16u;
+        mbar_expect_tx(mbar_s + 8u * slot, bytes);
+        bulk_g2s(ring_s + slot * (GATE_CHUNK * 16u), gsrc + base, bytes, mbar_s + 8u * slot);
+      }
+      issued++;
+    };
+    auto wait_chunk = [&](uint32_t j) {  // chunk j of this task, requested earlier; every thread of the worker
+      if (j < n_chunks) {
+        const uint32_t slot = j & (GATE_CHUNKS - 1);
+        while (!mbar_try_wait(mbar_s + 8u * slot, (ring_par >> slot) & 1u)) {
+        }
+        ring_par ^= 1u << slot;
+      }
+    };
+#else
     auto issue_chunk = [&]() {
       const uint32_t base = issued * GATE_CHUNK;
       for (uint32_t r = base + wt; r < base + GATE_CHUNK && r < task.n_gates; r += NT)
@@ -610,6 +675,7 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
       cp_async_commit();
       issued++;
     };
+#endif
 #pragma unroll
     for (uint32_t k = 0; k < GATE_CHUNKS; k++) issue_chunk();
 
@@ -664,7 +730,12 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
       if (MODE == 1) sval[s * G + inst] = (uint8_t)s;
     }
     gather_window(0);
+#if GSV_RECORD_TMA
+#pragma unroll
+    for (uint32_t k = 0; k < GATE_CHUNKS; k++) wait_chunk(k);  // chunks 0..3 have landed
+#else
     cp_async_wait<0>();  // chunks 0..3 have landed
+#endif
     named_bar(bar_id, NT);
     lap(PROF_GATHER);
     if (prof) wprof[PROF_N_ITEMS]++;
@@ -804,7 +875,11 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
         }
       }
       const bool cross = pos1 / GATE_CHUNK != chunk;  // uniform over the worker; at most one chunk per level
+#if GSV_RECORD_TMA
+      if (cross && chunk) wait_chunk(chunk + 3);      // chunk c + 3, requested one crossing ago (0..3: at the start)
+#else
       if (cross) cp_async_wait<0>();                  // chunk c + 3, requested one crossing ago
+#endif
       named_bar(bar_id, NT);
       if (cross) {                                    // the chunk left behind is free: request chunk c + 4
         issue_chunk();
@@ -829,7 +904,9 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
     // ---- scatter the labels this window completed to the instance's global slots
     publish_window(win);
     }
+#if !GSV_RECORD_TMA
     cp_async_wait<0>();
+#endif
     if (p.ct_sys) __threadfence_system();  // ciphertexts stored to a peer's ring are ordered before the flags
     else __threadfence();
     named_bar(bar_id, NT);

@@ -1384,7 +1384,7 @@ gsv_session* gsv_session_create(const gsv_program* p, const gsv_session_options*
     auto smem_for = [&](uint32_t G, uint32_t nw, bool eval) {
       size_t lab = (size_t)slots * G;
       return (size_t)AES_TABLE_BYTES + nw * lab * 16 + (((eval ? nw * lab : 0) + nw * 8 + 15) & ~(size_t)15) + (size_t)nw * GATE_RING * 16 +
-             (size_t)nw * PROF_WORDS * 8;
+             (size_t)nw * PROF_WORDS * 8 + (size_t)nw * GATE_CHUNKS * 8;  // + one mbarrier per ring slot
     };
     // execution mode: lane mode (warp = 32 instances) for batches that fill warps, the levelised
     // shared-memory mode otherwise
