@@ -58,6 +58,42 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def host_plan(S, B, steps, warmup, cpu_share, n_ct, commit_host=True, sessions_auto=True, instances_auto=True,
+              host_threads=0):
+    """Steps in flight per GPU (S), instances per step (B) and AES-NI fold threads per step for a rank that owns
+    `cpu_share` host CPUs.  Returns (S, B, fold_threads, note).  The serial chain commitments are folded on the host:
+    this is the part of the workload that depends on the host, and the bench says what it chose."""
+    note = None
+    if commit_host and sessions_auto:
+        if cpu_share < 6:
+            # few host CPUs per rank (8 GPUs on a 32-CPU host): one fold thread per session, each interleaving all
+            # four quads of its session (the VAES throughput cap, 640 M blocks/s per thread), one session per CPU
+            S = max(S, min(4, cpu_share))
+        elif cpu_share >= 16:
+            # A run of K steps takes ceil(K / S) waves of S steps in flight.  Measured time one step is in flight on a
+            # B200 with a 16-CPU host: 48 s at S = 3 (48 SMs per step), 63 s at S = 4 (36 SMs): 20 steps are
+            # 7 x 48 s or 5 x 63 s.
+            wave_s = {3: 48.0, 4: 63.0}
+            S = min(wave_s, key=lambda n: -(-max(1, steps) // n) * wave_s[n])
+    if commit_host and instances_auto:
+        # The folds do about 0.5 G blocks/s per CPU with several chains interleaved: when a rank has very few CPUs
+        # (many GPUs on a small host) a 16-instance step can take so long that `--steps 20 --warmup 5` no longer ends
+        # within the driver's window.  Shrink the step then, and say so.
+        per_step_s = 720.0 / max(1, warmup + steps)
+        cap = int(per_step_s * min(cpu_share, S * ((B + 3) // 4)) * 0.5e9 / max(1, n_ct))
+        if cap < B:
+            B_new = max(4, cap // 4 * 4)
+            note = (f"{B_new} instead of {B} instances per step: {cpu_share} host CPUs per rank fold about "
+                    f"{0.5 * cpu_share:.1f} G ciphertexts/s, a {B}-instance step would not fit the run's time window")
+            B = B_new
+    # one fold thread per quad of chains when the rank has a CPU for each; otherwise one CPU is left to the drain threads
+    quads = (B + 3) // 4
+    fold_cpus = cpu_share if S * quads <= cpu_share else max(1, cpu_share - (1 if cpu_share >= 6 else 0))
+    fold_threads = host_threads or max(1, min(quads, fold_cpus // S))
+    return S, B, fold_threads, note
+
+
+
 def plan_cache_dir():
     """The ranks of a job (and successive runs on one box) plan the circuit once and share the result through a
     file (GSV_PLAN_CACHE_DIR, see gsv_program_build): 23 s and 17 GB of host memory per process otherwise."""
@@ -406,32 +442,9 @@ def main():
     # drain thread (mostly asleep) and `fold_threads` AES-NI fold threads
     logical, physical = host_cpus()
     cpu_share = max(1, logical // max(1, local_world))
-    if args.sessions_auto and ct_mode == g.CT_COMMIT_HOST and cpu_share < 6:
-        # few host CPUs per rank (8 GPUs on a 32-CPU host): one fold thread per session, each interleaving all four
-        # quads of its session (the VAES throughput cap, 640 M blocks/s per thread), and one session per CPU
-        S = max(S, min(4, cpu_share))
-    if args.sessions_auto and ct_mode == g.CT_COMMIT_HOST and cpu_share >= 16:
-        # A run of K steps takes ceil(K / S) waves of S steps in flight.  Measured time one step is in flight on a B200
-        # with a 16-CPU host: 48 s at S = 3 (48 SMs per step), 63 s at S = 4 (36 SMs): 20 steps are 7 x 48 s or 5 x 63 s.
-        wave_s = {3: 48.0, 4: 63.0}
-        S = min(wave_s, key=lambda n: -(-max(1, args.steps) // n) * wave_s[n])
-    instances_note = None
-    if ct_mode == g.CT_COMMIT_HOST and args.instances_auto:
-        # The serial chains are folded by host AES-NI threads (~0.5 G blocks/s per CPU with several chains interleaved):
-        # when a rank has very few CPUs (many GPUs on a small host) a 16-instance step can take so long that
-        # `--steps 20 --warmup 5` no longer ends within the driver's window.  Shrink the step then, and say so.
-        n_steps_all = max(1, args.warmup + args.steps)
-        per_step_s = 720.0 / n_steps_all
-        cap = int(per_step_s * min(cpu_share, S * ((B + 3) // 4)) * 0.5e9 / max(1, prog.n_ciphertexts))
-        if cap < B:
-            B_new = max(4, cap // 4 * 4)
-            instances_note = (f"{B_new} instead of {B} instances per step: {cpu_share} host CPUs per rank fold about "
-                              f"{0.5 * cpu_share:.1f} G ciphertexts/s, a {B}-instance step would not fit the run's time window")
-            B = B_new
-    # one fold thread per quad of chains when the rank has a CPU for each; otherwise one CPU is left to the drain threads
-    quads = (B + 3) // 4
-    fold_cpus = cpu_share if S * quads <= cpu_share else max(1, cpu_share - (1 if cpu_share >= 6 else 0))
-    fold_threads = args.host_threads or max(1, min(quads, fold_cpus // S))
+    S, B, fold_threads, instances_note = host_plan(
+        S, B, args.steps, args.warmup, cpu_share, prog.n_ciphertexts, commit_host=ct_mode == g.CT_COMMIT_HOST,
+        sessions_auto=args.sessions_auto, instances_auto=args.instances_auto, host_threads=args.host_threads)
     sm_total = torch.cuda.get_device_properties(local).multi_processor_count
     sm_limit = 0 if S == 1 else (sm_total - SM_RESERVE) // S
     free_b, _ = torch.cuda.mem_get_info()

@@ -35,3 +35,29 @@ def test_reference_arm_prints_one_json_line(built):
 def test_reference_arm_is_silent_on_other_ranks(built):
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_host_plan_for_the_drivers_hosts():
+    """bench.host_plan: steps in flight, instances per step and fold threads per step from a rank's CPU share.
+    (The committed step folds its serial chains on host AES-NI threads; this is the host-dependent part of the bench.)"""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    n_ct = 2_980_239_027  # the verifier
+    # 1 GPU on a 16-CPU host, the driver's --steps 20 --warmup 5: 5 waves of 4 beat 7 waves of 3; a thread per quad
+    assert bench.host_plan(3, 16, 20, 5, 16, n_ct) == (4, 16, 4, None)
+    # the default run (6 steps): 2 waves of 3
+    assert bench.host_plan(3, 16, 6, 3, 16, n_ct) == (3, 16, 4, None)
+    # 2 GPUs on a 24-CPU host: 12 CPUs per rank, 3 steps in flight, a fold thread per quad
+    assert bench.host_plan(3, 16, 20, 5, 12, n_ct) == (3, 16, 4, None)
+    # 8 CPUs per rank: one CPU is left to the drain threads, 2 fold threads per step (two quads each)
+    assert bench.host_plan(3, 16, 20, 5, 8, n_ct) == (3, 16, 2, None)
+    # 4 GPUs on a 16-CPU host: a session per CPU, one fold thread each, the step still fits
+    assert bench.host_plan(3, 16, 20, 5, 4, n_ct) == (4, 16, 1, None)
+    # 8 GPUs on a 16-CPU host: two CPUs per rank cannot fold 16 chains per step in time -> smaller steps, said so
+    S, B, T, note = bench.host_plan(3, 16, 20, 5, 2, n_ct)
+    assert (S, B, T) == (3, 8, 1) and "8 instead of 16" in note
+    # explicit flags are left alone
+    assert bench.host_plan(2, 32, 20, 5, 2, n_ct, sessions_auto=False, instances_auto=False, host_threads=5) == (2, 32, 5, None)
+    # no host fold without the host-folded commitment
+    assert bench.host_plan(3, 16, 20, 5, 2, n_ct, commit_host=False)[:2] == (3, 16)
