@@ -701,6 +701,9 @@ __global__ void __launch_bounds__(ENGINE_MAX_THREADS, 1) k_engine(const EnginePa
         const uint32_t pos = p.win_in[task.win_in_base + lo + k / G];
         const uint32_t s = p.in_slot[task.in_slot_off + pos];
         const uint32_t gs = p.call_slots[call.in_off + pos];
+        // The label loads below are ld.global.cg (served by L2, the coherence point) and are issued behind the
+        // control dependency on the flag's value; the producer ordered label stores -> __threadfence -> barrier ->
+        // flag store.  No fence here: a membar would also wait for this thread's ciphertext stores in flight.
         if (sflags)
           while (ld_acquire(sflags + gs) != p.epoch) __nanosleep(64);
         const size_t gi = (gbase + gs) * G + inst;
