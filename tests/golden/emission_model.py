@@ -532,6 +532,183 @@ def fq_mul(x, a, b):
     return montgomery_reduce(x, bn_mul(x, a, b))
 
 
+# ---- bigint helpers used by Fp::inverse (bigint/add.rs:128-187, bigint/cmp.rs:24-108)
+def bn_double_without_overflow(x, a):   # #[bn_component], emits no gate: [FALSE, a0 .. a(n-2)]
+    return x.component("bigint::double_without_overflow", a, lambda x, a: [FALSE] + a[:-1])
+
+
+def bn_half(a):                         # plain function: a >> 1
+    return a[1:] + [FALSE]
+
+
+def self_or_zero_inv(x, a, s):
+    def body(x, w):
+        out = []
+        for ai in w[:-1]:
+            o = x.issue()
+            x.gate(and_variant([0, 1, 0]), ai, w[-1], o)
+            out.append(o)
+        return out
+    return x.component("bigint::self_or_zero_inv", a + [s], body)
+
+
+def equal_zero(x, a):
+    def body(x, a):
+        if len(a) == 1:
+            w = x.issue()
+            x.gate(XOR, a[0], TRUE, w)
+            return [w]
+        res = x.issue()
+        x.gate(XNOR, a[0], a[1], res)
+        for ai in a[1:]:
+            nxt = x.issue()
+            x.gate(and_variant([1, 0, 0]), ai, res, nxt)
+            res = nxt
+        return [res]
+    return x.component("bigint::equal_zero", a, body)[0]
+
+
+def equal_constant(x, a, k):
+    n = len(a)
+
+    def body(x, a):
+        if k == 0:
+            return [equal_zero(x, a)]
+        kb = bits_of(k, n)
+        one = kb.index(1)
+        res = a[one]
+        for i, ai in enumerate(a):
+            if i == one:
+                continue
+            nxt = x.issue()
+            x.gate(and_variant([0 if kb[i] else 1, 0, 0]), ai, res, nxt)
+            res = nxt
+        return [res]
+    return x.component(("bigint::equal_constant", k), a, body)[0]
+
+
+def odd_part(x, a):                     # plain function (add.rs:155-187)
+    n = len(a)
+    sel = [a[0]] + [x.issue() for _ in range(n - 1)]
+    for i in range(1, n):
+        x.gate(OR, sel[i - 1], a[i], sel[i])
+    k = [a[0]] + [x.issue() for _ in range(n - 1)]
+    for i in range(1, n):
+        x.gate(and_variant([1, 0, 0]), sel[i - 1], a[i], k[i])
+    acc = list(a)
+    for i in range(n):
+        acc = bn_select(x, acc, bn_half(acc), sel[i])
+    return acc, k
+
+
+def fq_mul_by_constant(x, a, k):        # fp254impl.rs:252-272, k already in Montgomery form
+    def body(x, a):
+        if k == 0:
+            return [FALSE] * N
+        if k == (1 << N) % P:
+            return list(a)
+        return montgomery_reduce(x, mul_by_constant(x, a, k))
+    return x.component(("fq::mul_by_constant_montgomery", k), a, body)
+
+
+def fq_inverse(x, a):                   # fp254impl.rs:333-660
+    PER = 4
+
+    def iteration(cnt):
+        def body(x, w):
+            u, v, r, s, k = (list(w[j * N:(j + 1) * N]) for j in range(5))
+            for _ in range(cnt):
+                not_x1, not_x2 = u[0], v[0]
+                x3 = greater_than(x, u, v)
+                p2 = x.issue()
+                x.gate(and_variant([0, 1, 0]), not_x1, not_x2, p2)
+                p3, w2 = x.issue(), x.issue()
+                x.gate(AND, not_x1, not_x2, w2)
+                x.gate(AND, w2, x3, p3)
+                p4 = x.issue()
+                x.gate(NIMP, w2, x3, p4)
+                # the four candidate updates
+                u1, v1, r1, s1, k1 = bn_half(u), v, r, bn_double_without_overflow(x, s), bn_add_constant(x, k, 1)[:-1]
+                u2, v2, r2, s2, k2 = u, bn_half(v), bn_double_without_overflow(x, r), s, bn_add_constant(x, k, 1)[:-1]
+                u3 = bn_sub_without_borrow(x, u1, v2)
+                v3 = v
+                r3 = bn_add(x, r, s)[:-1]
+                s3 = bn_double_without_overflow(x, s)
+                k3 = bn_add_constant(x, k, 1)[:-1]
+                u4 = u
+                v4 = bn_sub_without_borrow(x, v2, u1)
+                r4 = bn_double_without_overflow(x, r)
+                s4 = bn_add(x, r, s)[:-1]
+                k4 = bn_add_constant(x, k, 1)[:-1]
+                new = []
+                for c1, c2, c3, c4 in ((u1, u2, u3, u4), (v1, v2, v3, v4), (r1, r2, r3, r4), (s1, s2, s3, s4),
+                                       (k1, k2, k3, k4)):
+                    w1 = self_or_zero_inv(x, c1, not_x1)
+                    w2_ = self_or_zero(x, c2, p2)
+                    w3 = self_or_zero(x, c3, p3)
+                    w4 = self_or_zero(x, c4, p4)
+                    acc = bn_add(x, w1, w2_)[:-1]
+                    acc = bn_add(x, acc, w3)[:-1]
+                    new.append(bn_add(x, acc, w4)[:-1])
+                v_is_one = equal_constant(x, v, 1)
+                u, v, r, s, k = (bn_select(x, old, nw, v_is_one) for old, nw in zip((u, v, r, s, k), new))
+            return u + v + r + s + k
+        return body
+
+    def by_even_chunk(cnt):
+        def body(x, w):
+            s, even = list(w[:N]), list(w[N:])
+            for _ in range(cnt):
+                hs, he = fq_half(x, s), fq_half(x, even)
+                sel = equal_constant(x, even, 1)
+                s = bn_select(x, s, hs, sel)
+                even = bn_select(x, even, he, sel)
+            return s + even
+        return body
+
+    def by_even(x, w):
+        s, even = list(w[:N]), list(w[N:])
+        for ci, start in enumerate(range(0, N, PER)):
+            cnt = min(PER, N - start)
+            r = x.component(("inverse::divide_result_by_even_part::chunk", ci), s + even, by_even_chunk(cnt))
+            s, even = r[:N], r[N:]
+        return s
+
+    def by_2k_chunk(cnt):
+        def body(x, w):
+            s, k = list(w[:N]), list(w[N:])
+            for _ in range(cnt):
+                hs = fq_half(x, s)
+                km1 = fq_add_constant(x, k, P - 1)
+                sel = equal_constant(x, k, 0)
+                s = bn_select(x, s, hs, sel)
+                k = bn_select(x, k, km1, sel)
+            return s + k
+        return body
+
+    def by_2k(x, w):
+        s, k = list(w[:N]), list(w[N:])
+        for start in range(0, 2 * N, PER):
+            r = x.component("inverse::divide_result_by_2^k::chunk", s + k, by_2k_chunk(min(PER, 2 * N - start)))
+            s, k = r[:N], r[N:]
+        return s
+
+    def body(x, a):
+        odd, even = odd_part(x, a)
+        u = bn_half(fq_neg(x, odd))
+        state = u + odd + bits_of(1, N) + bits_of(2, N) + bits_of(1, N)     # u, v, r, s, k
+        for start in range(0, 2 * N, PER):
+            state = x.component("inverse_iteration", state, iteration(min(PER, 2 * N - start)))
+        s, k = state[3 * N:4 * N], state[4 * N:]
+        s = x.component("inverse::divide_result_by_even_part", s + even, by_even)
+        return x.component("inverse::divide_result_by_2^k", s + k, by_2k)
+    return x.component("fq::inverse", a, body)
+
+
+def fq_inverse_montgomery(x, a):        # fp254impl.rs:676-686: inverse, then times R^3
+    return fq_mul_by_constant(x, fq_inverse(x, a), pow(1 << N, 3, P))
+
+
 # ======================================================================================== fq2 / fq6 / fq12
 def fq2_map(f):
     return lambda x, a, *r: [f(x, a[0], *[q[0] for q in r]), f(x, a[1], *[q[1] for q in r])]
@@ -647,6 +824,265 @@ def fq12_mul(x, a, b):   # fq12.rs:198-221, #[component]
     return x.component("fq12::mul_montgomery", a + b, body)
 
 
+# ======================================================================================== squares, inverses, Frobenius maps
+R_MONT = (1 << N) % P
+
+
+def _f2mul(a, b):      # host arithmetic in Fq2 = Fq[u] / (u^2 + 1), for the Frobenius constants only
+    return ((a[0] * b[0] - a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+
+
+def _f2pow(a, e):
+    r = (1, 0)
+    while e:
+        if e & 1:
+            r = _f2mul(r, a)
+        a = _f2mul(a, a)
+        e >>= 1
+    return r
+
+
+XI = (9, 1)            # the sextic non-residue 9 + u
+FROB_FP2_C1 = [1, P - 1]
+FROB_FP6_C1 = [_f2pow(XI, (P ** i - 1) // 3) for i in range(6)]
+FROB_FP6_C2 = [_f2pow(XI, (2 * P ** i - 2) // 3) for i in range(6)]
+FROB_FP12_C1 = [_f2pow(XI, (P ** i - 1) // 6) for i in range(12)]
+
+
+def _mont2(c):
+    return (c[0] * R_MONT % P, c[1] * R_MONT % P)
+
+
+fq2_half = fq2_map(fq_half)
+fq2_neg = fq2_map(fq_neg)
+
+
+def fq2_square(x, a):                   # fq2.rs:341-354
+    s = fq_add(x, a[0], a[1])
+    d = fq_sub(x, a[0], a[1])
+    a0a1 = fq_mul(x, a[0], a[1])
+    c0 = fq_mul(x, s, d)
+    return [c0, fq_double(x, a0a1)]
+
+
+def fq2_inverse(x, a):                  # fq2.rs:356-372, #[component]
+    def body(x, w):
+        a0, a1 = list(w[:N]), list(w[N:])
+        a0s = fq_mul(x, a0, a0)
+        a1s = fq_mul(x, a1, a1)
+        norm = fq_add(x, a0s, a1s)
+        inv = fq_inverse_montgomery(x, norm)
+        c0 = fq_mul(x, a0, inv)
+        na1 = fq_neg(x, a1)
+        return c0 + fq_mul(x, na1, inv)
+    r = x.component("fq2::inverse_montgomery", a[0] + a[1], body)
+    return [r[:N], r[N:]]
+
+
+def fq2_mul_by_constant(x, a, k):       # fq2.rs:257-280; k = (c0, c1) as the caller passes it (Montgomery form)
+    if k == (1, 0):
+        return [list(a[0]), list(a[1])]
+    a_sum = fq_add(x, a[0], a[1])
+    a0b0 = fq_mul_by_constant(x, a[0], k[0])
+    a1b1 = fq_mul_by_constant(x, a[1], k[1])
+    sms = fq_mul_by_constant(x, a_sum, (k[0] + k[1]) % P)
+    c0 = fq_sub(x, a0b0, a1b1)
+    t = fq_add(x, a0b0, a1b1)
+    return [c0, fq_sub(x, sms, t)]
+
+
+def fq2_frobenius(x, a, i):             # fq2.rs:374-384
+    return [list(a[0]), fq_mul_by_constant(x, a[1], FROB_FP2_C1[i % 2] * R_MONT % P)]
+
+
+fq6_double = fq6_map(fq2_double)
+fq6_neg = fq6_map(fq2_neg)
+
+
+def fq6_square(x, a):                   # fq6.rs:421-448
+    a0, a1, a2 = a
+    s0 = fq2_square(x, a0)
+    w1 = fq2_add(x, a0, a2)
+    w2 = fq2_add(x, w1, a1)
+    w3 = fq2_sub(x, w1, a1)
+    s1 = fq2_square(x, w2)
+    s2 = fq2_square(x, w3)
+    w4 = fq2_mul(x, a1, a2)
+    s3 = fq2_double(x, w4)
+    s4 = fq2_square(x, a2)
+    w5 = fq2_add(x, s1, s2)
+    t1 = fq2_half(x, w5)
+    w6 = fq2_mul_by_nonresidue(x, s3)
+    c0 = fq2_add(x, s0, w6)
+    w7 = fq2_mul_by_nonresidue(x, s4)
+    w8 = fq2_sub(x, s1, s3)
+    w9 = fq2_sub(x, w8, t1)
+    c1 = fq2_add(x, w9, w7)
+    w10 = fq2_sub(x, t1, s0)
+    return [c0, c1, fq2_sub(x, w10, s4)]
+
+
+def fq6_inverse(x, r):                  # fq6.rs:450-487
+    a, b, c = r
+    a_sq = fq2_square(x, a)
+    b_sq = fq2_square(x, b)
+    c_sq = fq2_square(x, c)
+    ab = fq2_mul(x, a, b)
+    ac = fq2_mul(x, a, c)
+    bc = fq2_mul(x, b, c)
+    bc_beta = fq2_mul_by_nonresidue(x, bc)
+    t0 = fq2_sub(x, a_sq, bc_beta)                  # a^2 - bc beta
+    c_sq_beta = fq2_mul_by_nonresidue(x, c_sq)
+    t1 = fq2_sub(x, c_sq_beta, ab)                  # c^2 beta - ab
+    t2 = fq2_sub(x, b_sq, ac)                       # b^2 - ac
+    w1 = fq2_mul(x, t1, c)
+    w2 = fq2_mul(x, t2, b)
+    w12 = fq2_add(x, w1, w2)
+    w3 = fq2_mul_by_nonresidue(x, w12)
+    w4 = fq2_mul(x, a, t0)
+    norm = fq2_add(x, w4, w3)
+    inv = fq2_inverse(x, norm)
+    return [fq2_mul(x, t0, inv), fq2_mul(x, t1, inv), fq2_mul(x, t2, inv)]
+
+
+def fq6_frobenius(x, a, i):             # fq6.rs:489-514
+    f0 = fq2_frobenius(x, a[0], i)
+    f1 = fq2_frobenius(x, a[1], i)
+    f2 = fq2_frobenius(x, a[2], i)
+    f1u = fq2_mul_by_constant(x, f1, _mont2(FROB_FP6_C1[i % 6]))
+    f2u = fq2_mul_by_constant(x, f2, _mont2(FROB_FP6_C2[i % 6]))
+    return [f0, f1u, f2u]
+
+
+def fq6_mul_by_constant_fq2(x, a, k):   # fq6.rs:334-344
+    return [fq2_mul_by_constant(x, a[j], k) for j in range(3)]
+
+
+def fq12_square(x, a):                  # fq12.rs:311-324, #[component]
+    def body(x, w):
+        a0, a1 = _fq6_of(w[:6 * N]), _fq6_of(w[6 * N:])
+        w1 = fq6_add(x, a0, a1)
+        w2 = fq6_mul_by_nonresidue(x, a1)
+        w3 = fq6_add(x, a0, w2)
+        w4 = fq6_mul(x, a0, a1)
+        w5 = fq6_mul(x, w1, w3)
+        w6 = fq6_mul_by_nonresidue(x, w4)
+        w7 = fq6_add(x, w4, w6)
+        c0 = fq6_sub(x, w5, w7)
+        return _flat6(c0) + _flat6(fq6_double(x, w4))
+    return x.component("fq12::square_montgomery", list(a), body)
+
+
+def fq12_cyclotomic_square(x, a):       # fq12.rs:326-392, plain function
+    a0, a1 = _fq6_of(a[:6 * N]), _fq6_of(a[6 * N:])
+    c0, c1, c2, c3, c4, c5 = a0[0], a0[1], a0[2], a1[0], a1[1], a1[2]
+
+    def fp4_square(p, q, yb_of, other):
+        xy = fq2_mul(x, p, q)
+        x_plus_y = fq2_add(x, p, q)
+        y_beta = fq2_mul_by_nonresidue(x, yb_of)
+        x_plus_y_beta = fq2_add(x, other, y_beta)
+        xy_beta = fq2_mul_by_nonresidue(x, xy)
+        w1 = fq2_mul(x, x_plus_y, x_plus_y_beta)
+        w2 = fq2_add(x, xy, xy_beta)
+        return fq2_sub(x, w1, w2), fq2_double(x, xy)
+    t0, t1 = fp4_square(c0, c4, c4, c0)
+    t2, t3 = fp4_square(c2, c3, c2, c3)
+    t4, t5 = fp4_square(c1, c5, c5, c1)
+
+    def comb_sub(t, c):
+        return fq2_add(x, fq2_double(x, fq2_sub(x, t, c)), t)
+
+    def comb_add(t, c):
+        return fq2_add(x, fq2_double(x, fq2_add(x, t, c)), t)
+    z0 = comb_sub(t0, c0)
+    z4 = comb_sub(t2, c1)
+    z3 = comb_sub(t4, c2)
+    t5_beta = fq2_mul_by_nonresidue(x, t5)
+    z2 = comb_add(t5_beta, c3)
+    z1 = comb_add(t1, c4)
+    z5 = comb_add(t3, c5)
+    return _flat6([z0, z4, z3]) + _flat6([z2, z1, z5])
+
+
+def fq12_inverse(x, a):                 # fq12.rs:413-428, #[component]
+    def body(x, w):
+        a0, a1 = _fq6_of(w[:6 * N]), _fq6_of(w[6 * N:])
+        a0s = fq6_square(x, a0)
+        a1s = fq6_square(x, a1)
+        a1sb = fq6_mul_by_nonresidue(x, a1s)
+        norm = fq6_sub(x, a0s, a1sb)
+        inv = fq6_inverse(x, norm)
+        c0 = fq6_mul(x, a0, inv)
+        na1 = fq6_neg(x, a1)
+        return _flat6(c0) + _flat6(fq6_mul(x, inv, na1))
+    return x.component("fq12::inverse_montgomery", list(a), body)
+
+
+def fq12_frobenius(x, a, i):            # fq12.rs:430-442
+    a0, a1 = _fq6_of(a[:6 * N]), _fq6_of(a[6 * N:])
+    f0 = fq6_frobenius(x, a0, i)
+    f1 = fq6_frobenius(x, a1, i)
+    return _flat6(f0) + _flat6(fq6_mul_by_constant_fq2(x, f1, _mont2(FROB_FP12_C1[i % 12])))
+
+
+# ======================================================================================== multiplexers, G1
+def basic_multiplexer(x, a, s, w):      # basic.rs:73-105, #[component(offcircuit_args = "w")]
+    n = len(a)
+
+    def body(x, inp):
+        cur, sel = list(inp[:n]), inp[n:]
+        for sl in sel:                  # pairs reduced from the LSB selector up: selector(high, low, sel)
+            cur = [selector(x, cur[i + 1], cur[i], sl) for i in range(0, len(cur), 2)]
+        return [cur[0]]
+    assert n == 1 << w and len(s) == w
+    return x.component(("basic::multiplexer", w), list(a) + list(s), body)[0]
+
+
+def bn_multiplexer(x, a, s, w):         # bigint/cmp.rs:171-193, #[bn_component]
+    nb, cnt = len(a[0]), len(a)
+
+    def body(x, inp):
+        arr, sel = [inp[j * nb:(j + 1) * nb] for j in range(cnt)], inp[cnt * nb:]
+        return [basic_multiplexer(x, [ai[i] for ai in arr], sel, w) for i in range(nb)]
+    return x.component(("bigint::multiplexer", w), [b for ai in a for b in ai] + list(s), body)
+
+
+def g1_add(x, p, q):                    # g1.rs:159-235, #[component]
+    def body(x, w):
+        x1, y1, z1, x2, y2, z2 = (list(w[j * N:(j + 1) * N]) for j in range(6))
+        z1s = fq_mul(x, z1, z1)
+        z2s = fq_mul(x, z2, z2)
+        z1c = fq_mul(x, z1s, z1)
+        z2c = fq_mul(x, z2s, z2)
+        u1 = fq_mul(x, x1, z2s)
+        u2 = fq_mul(x, x2, z1s)
+        s1 = fq_mul(x, y1, z2c)
+        s2 = fq_mul(x, y2, z1c)
+        r = fq_sub(x, s1, s2)
+        h = fq_sub(x, u1, u2)
+        h2 = fq_mul(x, h, h)
+        g = fq_mul(x, h, h2)
+        v = fq_mul(x, u1, h2)
+        r2 = fq_mul(x, r, r)
+        r2g = fq_add(x, r2, g)
+        vd = fq_double(x, v)
+        x3 = fq_sub(x, r2g, vd)
+        vx3 = fq_sub(x, v, x3)
+        ww = fq_mul(x, r, vx3)
+        s1g = fq_mul(x, s1, g)
+        y3 = fq_sub(x, ww, s1g)
+        z1z2 = fq_mul(x, z1, z2)
+        z3 = fq_mul(x, z1z2, h)
+        z1_0 = equal_constant(x, z1, 0)
+        z2_0 = equal_constant(x, z2, 0)
+        zero = [FALSE] * N
+        sel = [z1_0, z2_0]
+        return (bn_multiplexer(x, [x3, x2, x1, zero], sel, 2) + bn_multiplexer(x, [y3, y2, y1, zero], sel, 2) +
+                bn_multiplexer(x, [z3, z2, z1, zero], sel, 2))
+    return x.component("g1::add_montgomery", list(p) + list(q), body)
+
+
 # ======================================================================================== roots (the product's named circuits)
 def build(circuit):
     """(type, a, b, c, outputs, n_inputs) of a named circuit; names as in gsv_program_build."""
@@ -676,4 +1112,18 @@ def build(circuit):
         x = Ctx(24 * N)
         w = list(range(2, 2 + 24 * N))
         return x.finish(fq12_mul(x, w[:12 * N], w[12 * N:]))
+    if circuit in ("fq12_square", "fq12_cyclotomic_square", "fq12_inverse") or circuit.startswith("fq12_frobenius"):
+        x = Ctx(12 * N)
+        w = list(range(2, 2 + 12 * N))
+        if circuit.startswith("fq12_frobenius"):
+            return x.finish(fq12_frobenius(x, w, int(circuit[14:])))
+        return x.finish({"fq12_square": fq12_square, "fq12_cyclotomic_square": fq12_cyclotomic_square,
+                         "fq12_inverse": fq12_inverse}[circuit](x, w))
+    if circuit == "g1_add":
+        x = Ctx(6 * N)
+        w = list(range(2, 2 + 6 * N))
+        return x.finish(g1_add(x, w[:3 * N], w[3 * N:]))
+    if circuit == "fq_inverse":
+        x = Ctx(N)
+        return x.finish(fq_inverse_montgomery(x, list(range(2, 2 + N))))
     raise ValueError(circuit)

@@ -1,7 +1,9 @@
 """Row a8 (gate stream = gadget emission order) pinned against an independent restatement.
 
 tests/golden/emission_model.py re-states the reference's gadgets (src/gadgets/basic.rs, bigint/*.rs,
-bn254/{fp254impl,fq2,fq6,fq12}.rs) with a different mechanism than the product's recorder (global SSA wires and a
+bn254/{fp254impl,fq2,fq6,fq12,g1}.rs: additions, multiplications, squares, inverses (the 2 x 254-round binary
+inverse of Fp and the tower inverses above it), Frobenius maps with independently derived coefficients, cyclotomic
+squaring, projective G1 addition with its multiplexers) with a different mechanism than the product's recorder (global SSA wires and a
 global liveness rule instead of per-component credit templates).  The product's generator must produce the same
 canonical stream -- gate order, gate types, wiring and dead gates -- as the hashes that model committed.
 """
@@ -21,9 +23,10 @@ with open(os.path.join(HERE, "golden", "stream_hashes.json")) as f:
 
 
 @pytest.mark.parametrize("name", ["fq_add", "bn_mul4", "bn_mul19", "bn_mul21", "bn_mul64", "bn_mul254", "fq_mul", "fq2_mul",
-                                  "fq6_mul", "fq12_mul"])
+                                  "fq6_mul", "fq12_mul", "fq_inverse", "g1_add", "fq12_square", "fq12_cyclotomic_square",
+                                  "fq12_frobenius1", "fq12_frobenius2", "fq12_frobenius3", "fq12_inverse"])
 def test_product_stream_matches_independent_model(gsv, name):
-    p = gsv.Program(name)
+    p = gsv.Program(name, lane_only=True)  # the flat stream does not depend on the plan
     t, a, b, c, outs, _ = p.flat_stream()
     h, info = em.canonical_hash(t, a, b, c, list(outs), p.n_inputs)
     assert info["n_gates"] == GOLDEN[name]["n_gates"] == p.n_gates
@@ -32,7 +35,7 @@ def test_product_stream_matches_independent_model(gsv, name):
     assert h == GOLDEN[name]["sha256"]
 
 
-@pytest.mark.parametrize("name", ["fq_add", "bn_mul64", "fq_mul"])
+@pytest.mark.parametrize("name", ["fq_add", "bn_mul64", "fq_mul", "g1_add", "fq12_cyclotomic_square", "fq12_frobenius2"])
 def test_model_reproduces_committed_hashes(name):
     h, info = em.canonical_hash(*em.build(name))
     assert h == GOLDEN[name]["sha256"] and info["n_dead"] == GOLDEN[name]["n_dead"]
