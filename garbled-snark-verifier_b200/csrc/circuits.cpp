@@ -25,6 +25,12 @@ uint32_t build_named_circuit(Builder& b, const std::string& c) {
   if (c == "fq12_cyclotomic_square") return build_fq12_cyclotomic_square(b);
   if (c == "fq12_inverse") return build_fq12_inverse(b);
   if (c.rfind("fq12_frobenius", 0) == 0) return build_fq12_frobenius(b, (size_t)std::stoul(c.substr(14)));
+  if (c == "g2_double_step") return build_g2_double_step(b);
+  if (c == "g2_add_step") return build_g2_add_step(b);
+  if (c == "g2_mul_by_char") return build_g2_mul_by_char(b);
+  if (c == "ell") return build_ell(b);
+  if (c == "ell_const") return build_ell_const(b);
+  if (c == "g1_to_affine") return build_g1_to_affine(b);
   if (c == "final_exponentiation") return build_final_exponentiation(b);
   if (c == "miller_loop_groth16" || c == "groth16_verify_compressed" || c == "groth16_verify") {
     host::VerifyingKey vk;

@@ -1224,6 +1224,46 @@ uint32_t build_fq12_frobenius(Builder& b, size_t i) {
     return to_wires(fq12_frobenius_montgomery(c, fq12_from_wires(in.data()), i));
   });
 }
+// single steps of the pairing layer as roots: small enough for the independent emission model (tests/golden)
+uint32_t build_g2_double_step(Builder& b) {
+  return b.build_root("g2_double_step", 1524, [](Builder& c, const Wires& in) {
+    G2P r;
+    Fq6 coeffs;
+    double_in_place_circuit_montgomery(c, g2_from_wires(in.data()), r, coeffs);
+    return concat(to_wires(r), to_wires(coeffs));
+  });
+}
+uint32_t build_g2_add_step(Builder& b) {
+  return b.build_root("g2_add_step", 3048, [](Builder& c, const Wires& in) {
+    G2P r;
+    Fq6 coeffs;
+    add_in_place_montgomery(c, g2_from_wires(in.data()), g2_from_wires(in.data() + 1524), r, coeffs);
+    return concat(to_wires(r), to_wires(coeffs));
+  });
+}
+uint32_t build_g2_mul_by_char(Builder& b) {
+  return b.build_root("g2_mul_by_char", 1524, [](Builder& c, const Wires& in) {
+    return to_wires(mul_by_char_montgomery(c, g2_from_wires(in.data())));
+  });
+}
+uint32_t build_ell(Builder& b) {
+  return b.build_root("ell", 3048 + 1524 + 762, [](Builder& c, const Wires& in) {
+    return to_wires(ell_montgomery(c, fq12_from_wires(in.data()), fq6_from_wires(in.data() + 3048), g1_from_wires(in.data() + 4572)));
+  });
+}
+uint32_t build_ell_const(Builder& b) {
+  // line coefficients (3 + 5u, 7 + 11u, 13 + 17u), standard form
+  const host::Fp6 coeffs{{host::Fp::from_u64(3), host::Fp::from_u64(5)}, {host::Fp::from_u64(7), host::Fp::from_u64(11)},
+                         {host::Fp::from_u64(13), host::Fp::from_u64(17)}};
+  return b.build_root("ell_const", 3048 + 762, [coeffs](Builder& c, const Wires& in) {
+    return to_wires(ell_by_constant_montgomery(c, fq12_from_wires(in.data()), coeffs, g1_from_wires(in.data() + 3048)));
+  });
+}
+uint32_t build_g1_to_affine(Builder& b) {
+  return b.build_root("g1_to_affine", 762, [](Builder& c, const Wires& in) {
+    return to_wires(projective_to_affine_montgomery(c, g1_from_wires(in.data())));
+  });
+}
 uint32_t build_final_exponentiation(Builder& b) {
   return b.build_root("final_exponentiation", 3048, [](Builder& c, const Wires& in) {
     return to_wires(final_exponentiation_montgomery(c, fq12_from_wires(in.data())));

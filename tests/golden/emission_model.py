@@ -1026,6 +1026,190 @@ def fq12_frobenius(x, a, i):            # fq12.rs:430-442
     return _flat6(f0) + _flat6(fq6_mul_by_constant_fq2(x, f1, _mont2(FROB_FP12_C1[i % 12])))
 
 
+# ======================================================================================== pairing layer (single steps)
+def _f2inv(a):
+    d = pow((a[0] * a[0] + a[1] * a[1]) % P, -1, P)
+    return (a[0] * d % P, (-a[1]) * d % P)
+
+
+G2_COEFF_B = _f2mul((3, 0), _f2inv(XI))             # b' = 3 / (9 + u), the twist's coefficient
+TWIST_MUL_BY_Q_X = _f2pow(XI, (P - 1) // 3)
+TWIST_MUL_BY_Q_Y = _f2pow(XI, (P - 1) // 2)
+
+
+def fq2_mul_by_fq(x, a, b):             # fq2.rs:282-291
+    return [fq_mul(x, a[0], b), fq_mul(x, a[1], b)]
+
+
+def fq2_mul_constant_by_fq(x, k, b):    # fq2.rs:307-322, #[component(offcircuit_args = "a")]; k in standard form
+    def body(x, b):
+        return fq_mul_by_constant(x, b, k[0] * R_MONT % P) + fq_mul_by_constant(x, b, k[1] * R_MONT % P)
+    r = x.component(("fq2::mul_constant_by_fq_montgomery", k), list(b), body)
+    return [r[:N], r[N:]]
+
+
+def fq2_add_constant(x, a, k):          # fq2.rs:170-177
+    return [fq_add_constant(x, a[0], k[0]), fq_add_constant(x, a[1], k[1])]
+
+
+def fq6_mul_by_fq2(x, a, b):            # fq6.rs:326-332
+    return [fq2_mul(x, a[j], b) for j in range(3)]
+
+
+def _mul_by_01(x, a, c0, mul_c1, c0_plus_c1):
+    """fq6.rs:351-410: the two sparse products differ only in how `* c1` and `c0 + c1` are formed."""
+    a0, a1, a2 = a
+    w1 = fq2_mul(x, a0, c0)
+    w2 = mul_c1(a1)
+    w3 = fq2_add(x, a1, a2)
+    w4 = mul_c1(w3)
+    w5 = fq2_sub(x, w4, w2)
+    w6 = fq2_mul_by_nonresidue(x, w5)
+    w7 = fq2_add(x, w6, w1)
+    w8 = fq2_add(x, a0, a1)
+    w9 = c0_plus_c1()
+    w10 = fq2_mul(x, w8, w9)
+    w11 = fq2_sub(x, w10, w1)
+    w12 = fq2_sub(x, w11, w2)
+    w13 = fq2_add(x, a0, a2)
+    w14 = fq2_mul(x, w13, c0)
+    w15 = fq2_sub(x, w14, w1)
+    return [w7, w12, fq2_add(x, w15, w2)]
+
+
+def fq6_mul_by_01(x, a, c0, c1):
+    return _mul_by_01(x, a, c0, lambda v: fq2_mul(x, v, c1), lambda: fq2_add(x, c0, c1))
+
+
+def fq6_mul_by_01_constant1(x, a, c0, k1):   # k1 already in Montgomery form
+    return _mul_by_01(x, a, c0, lambda v: fq2_mul_by_constant(x, v, k1), lambda: fq2_add_constant(x, c0, k1))
+
+
+def _mul_by_034(x, key, a, c0, c3, sparse):
+    def body(x, w):
+        a0, a1 = _fq6_of(w[:6 * N]), _fq6_of(w[6 * N:12 * N])
+        c0 = [list(w[12 * N:13 * N]), list(w[13 * N:14 * N])]
+        c3 = [list(w[14 * N:15 * N]), list(w[15 * N:16 * N])]
+        rest = w[16 * N:]
+        w1 = sparse(x, a1, c3, rest)
+        w2 = fq6_mul_by_nonresidue(x, w1)
+        w3 = fq6_mul_by_fq2(x, a0, c0)
+        new_c0 = fq6_add(x, w2, w3)
+        w4 = fq6_add(x, a0, a1)
+        w5 = fq2_add(x, c3, c0)
+        w6 = sparse(x, w4, w5, rest)
+        w7 = fq6_add(x, w1, w3)
+        return _flat6(new_c0) + _flat6(fq6_sub(x, w6, w7))
+    return body
+
+
+def fq12_mul_by_034(x, a, c0, c3, c4):  # fq12.rs:267-285, #[component]
+    body = _mul_by_034(x, None, a, c0, c3, lambda x, v, c, rest: fq6_mul_by_01(x, v, c, [list(rest[:N]), list(rest[N:])]))
+    return x.component("fq12::mul_by_034_montgomery", list(a) + c0[0] + c0[1] + c3[0] + c3[1] + c4[0] + c4[1], body)
+
+
+def fq12_mul_by_034_constant4(x, a, c0, c3, k4):   # fq12.rs:287-309, #[component(offcircuit_args = "c4")]
+    body = _mul_by_034(x, None, a, c0, c3, lambda x, v, c, rest: fq6_mul_by_01_constant1(x, v, c, k4))
+    return x.component(("fq12::mul_by_034_constant4_montgomery", k4), list(a) + c0[0] + c0[1] + c3[0] + c3[1], body)
+
+
+def _g2_of(w):
+    return [[list(w[(2 * i + j) * N:(2 * i + j + 1) * N]) for j in range(2)] for i in range(3)]
+
+
+def g2_double_step(x, r):               # pairing.rs:359-407, #[component]: (R, line coefficients)
+    def body(x, w):
+        rx, ry, rz = _g2_of(w)
+        a = fq2_half(x, fq2_mul(x, rx, ry))
+        b = fq2_square(x, ry)
+        c = fq2_square(x, rz)
+        c3 = fq2_triple(x, c)
+        e = fq2_mul_by_constant(x, c3, _mont2(G2_COEFF_B))
+        f = fq2_triple(x, e)
+        g = fq2_half(x, fq2_add(x, b, f))
+        ryrz = fq2_add(x, ry, rz)
+        ryrzs = fq2_square(x, ryrz)
+        bc = fq2_add(x, b, c)
+        h = fq2_sub(x, ryrzs, bc)
+        i = fq2_sub(x, e, b)
+        j = fq2_square(x, rx)
+        es = fq2_square(x, e)
+        j3 = fq2_triple(x, j)
+        bf = fq2_sub(x, b, f)
+        new_x = fq2_mul(x, a, bf)
+        es3 = fq2_triple(x, es)
+        gs = fq2_square(x, g)
+        new_y = fq2_sub(x, gs, es3)
+        new_z = fq2_mul(x, b, h)
+        hn = fq2_neg(x, h)
+        return _flat6([new_x, new_y, new_z]) + _flat6([hn, j3, i])
+    return x.component("pairing::double_in_place_circuit_montgomery", list(r), body)
+
+
+def g2_add_step(x, r, q):               # pairing.rs:409-462, #[component]
+    def body(x, w):
+        rx, ry, rz = _g2_of(w[:6 * N])
+        qx, qy, _ = _g2_of(w[6 * N:])
+        theta = fq2_sub(x, ry, fq2_mul(x, qy, rz))
+        lam = fq2_sub(x, rx, fq2_mul(x, qx, rz))
+        c = fq2_square(x, theta)
+        d = fq2_square(x, lam)
+        e = fq2_mul(x, lam, d)
+        f = fq2_mul(x, rz, c)
+        g = fq2_mul(x, rx, d)
+        w3 = fq2_add(x, e, f)
+        w4 = fq2_double(x, g)
+        h = fq2_sub(x, w3, w4)
+        neg_theta = fq2_neg(x, theta)
+        w5 = fq2_mul(x, theta, qx)
+        w6 = fq2_mul(x, lam, qy)
+        j = fq2_sub(x, w5, w6)
+        new_x = fq2_mul(x, lam, h)
+        w7 = fq2_sub(x, g, h)
+        w8 = fq2_mul(x, theta, w7)
+        w9 = fq2_mul(x, e, ry)
+        new_y = fq2_sub(x, w8, w9)
+        new_z = fq2_mul(x, rz, e)
+        return _flat6([new_x, new_y, new_z]) + _flat6([lam, neg_theta, j])
+    return x.component("pairing::add_in_place_montgomery", list(r) + list(q), body)
+
+
+def g2_mul_by_char(x, r):               # pairing.rs:475-498, #[component]
+    def body(x, w):
+        rx, ry, rz = _g2_of(w)
+        sx = fq2_mul_by_constant(x, fq2_frobenius(x, rx, 1), _mont2(TWIST_MUL_BY_Q_X))
+        sy = fq2_mul_by_constant(x, fq2_frobenius(x, ry, 1), _mont2(TWIST_MUL_BY_Q_Y))
+        return _flat6([sx, sy, rz])
+    return x.component("pairing::mul_by_char_montgomery", list(r), body)
+
+
+def ell(x, f, coeffs, p):               # pairing.rs:160-171, plain function; p = (x, y, z) affine
+    co = _fq6_of(coeffs)
+    px, py = list(p[:N]), list(p[N:2 * N])
+    c0 = fq2_mul_by_fq(x, co[0], py)
+    c3 = fq2_mul_by_fq(x, co[1], px)
+    return fq12_mul_by_034(x, f, c0, c3, co[2])
+
+
+def ell_by_constant(x, f, k, p):        # pairing.rs:923-942, #[component(offcircuit_args = "coeffs")]; k standard form
+    def body(x, w):
+        f, px, py = list(w[:12 * N]), list(w[12 * N:13 * N]), list(w[13 * N:14 * N])
+        c0 = fq2_mul_constant_by_fq(x, k[0], py)
+        c1 = fq2_mul_constant_by_fq(x, k[1], px)
+        return fq12_mul_by_034_constant4(x, f, c0, c1, _mont2(k[2]))
+    return x.component(("pairing::ell_by_constant_montgomery", k), list(f) + list(p), body)
+
+
+def g1_to_affine(x, p):                 # groth16.rs:26-47, #[component]
+    def body(x, w):
+        px, py, pz = (list(w[j * N:(j + 1) * N]) for j in range(3))
+        zi = fq_inverse_montgomery(x, pz)
+        zi2 = fq_mul(x, zi, zi)
+        zi3 = fq_mul(x, zi, zi2)
+        return fq_mul(x, px, zi2) + fq_mul(x, py, zi3) + bits_of(R_MONT, N)
+    return x.component("groth16::projective_to_affine_montgomery", list(p), body)
+
+
 # ======================================================================================== multiplexers, G1
 def basic_multiplexer(x, a, s, w):      # basic.rs:73-105, #[component(offcircuit_args = "w")]
     n = len(a)
@@ -1119,6 +1303,23 @@ def build(circuit):
             return x.finish(fq12_frobenius(x, w, int(circuit[14:])))
         return x.finish({"fq12_square": fq12_square, "fq12_cyclotomic_square": fq12_cyclotomic_square,
                          "fq12_inverse": fq12_inverse}[circuit](x, w))
+    if circuit in ("g2_double_step", "g2_mul_by_char", "g1_to_affine"):
+        n = 6 * N if circuit != "g1_to_affine" else 3 * N
+        x = Ctx(n)
+        w = list(range(2, 2 + n))
+        return x.finish({"g2_double_step": g2_double_step, "g2_mul_by_char": g2_mul_by_char, "g1_to_affine": g1_to_affine}[circuit](x, w))
+    if circuit == "g2_add_step":
+        x = Ctx(12 * N)
+        w = list(range(2, 2 + 12 * N))
+        return x.finish(g2_add_step(x, w[:6 * N], w[6 * N:]))
+    if circuit == "ell":
+        x = Ctx(21 * N)
+        w = list(range(2, 2 + 21 * N))
+        return x.finish(ell(x, w[:12 * N], w[12 * N:18 * N], w[18 * N:]))
+    if circuit == "ell_const":
+        x = Ctx(15 * N)
+        w = list(range(2, 2 + 15 * N))
+        return x.finish(ell_by_constant(x, w[:12 * N], ((3, 5), (7, 11), (13, 17)), w[12 * N:]))
     if circuit == "g1_add":
         x = Ctx(6 * N)
         w = list(range(2, 2 + 6 * N))

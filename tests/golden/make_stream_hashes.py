@@ -15,7 +15,8 @@ import emission_model as em  # noqa: E402
 
 CIRCUITS = ["fq_add", "bn_mul4", "bn_mul19", "bn_mul21", "bn_mul64", "bn_mul254", "fq_mul", "fq2_mul", "fq6_mul", "fq12_mul",
             "fq_inverse", "g1_add", "fq12_square", "fq12_cyclotomic_square", "fq12_frobenius1", "fq12_frobenius2",
-            "fq12_frobenius3", "fq12_inverse"]
+            "fq12_frobenius3", "fq12_inverse", "g2_double_step", "g2_add_step", "g2_mul_by_char", "ell", "ell_const",
+            "g1_to_affine"]
 
 out = {}
 for c in CIRCUITS:

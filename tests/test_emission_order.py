@@ -3,7 +3,9 @@
 tests/golden/emission_model.py re-states the reference's gadgets (src/gadgets/basic.rs, bigint/*.rs,
 bn254/{fp254impl,fq2,fq6,fq12,g1}.rs: additions, multiplications, squares, inverses (the 2 x 254-round binary
 inverse of Fp and the tower inverses above it), Frobenius maps with independently derived coefficients, cyclotomic
-squaring, projective G1 addition with its multiplexers) with a different mechanism than the product's recorder (global SSA wires and a
+squaring, projective G1 addition with its multiplexers, and from pairing.rs / groth16.rs the single steps of the
+pairing layer: G2 doubling and addition steps with their line coefficients, the twist Frobenius, line evaluation with
+variable and with constant coefficients (sparse 034 multiplications), projective -> affine) with a different mechanism than the product's recorder (global SSA wires and a
 global liveness rule instead of per-component credit templates).  The product's generator must produce the same
 canonical stream -- gate order, gate types, wiring and dead gates -- as the hashes that model committed.
 """
@@ -24,7 +26,8 @@ with open(os.path.join(HERE, "golden", "stream_hashes.json")) as f:
 
 @pytest.mark.parametrize("name", ["fq_add", "bn_mul4", "bn_mul19", "bn_mul21", "bn_mul64", "bn_mul254", "fq_mul", "fq2_mul",
                                   "fq6_mul", "fq12_mul", "fq_inverse", "g1_add", "fq12_square", "fq12_cyclotomic_square",
-                                  "fq12_frobenius1", "fq12_frobenius2", "fq12_frobenius3", "fq12_inverse"])
+                                  "fq12_frobenius1", "fq12_frobenius2", "fq12_frobenius3", "fq12_inverse",
+                                  "g2_double_step", "g2_add_step", "g2_mul_by_char", "ell", "ell_const", "g1_to_affine"])
 def test_product_stream_matches_independent_model(gsv, name):
     p = gsv.Program(name, lane_only=True)  # the flat stream does not depend on the plan
     t, a, b, c, outs, _ = p.flat_stream()
@@ -35,7 +38,8 @@ def test_product_stream_matches_independent_model(gsv, name):
     assert h == GOLDEN[name]["sha256"]
 
 
-@pytest.mark.parametrize("name", ["fq_add", "bn_mul64", "fq_mul", "g1_add", "fq12_cyclotomic_square", "fq12_frobenius2"])
+@pytest.mark.parametrize("name", ["fq_add", "bn_mul64", "fq_mul", "g1_add", "fq12_cyclotomic_square", "fq12_frobenius2",
+                                  "g2_mul_by_char", "g2_double_step"])
 def test_model_reproduces_committed_hashes(name):
     h, info = em.canonical_hash(*em.build(name))
     assert h == GOLDEN[name]["sha256"] and info["n_dead"] == GOLDEN[name]["n_dead"]
