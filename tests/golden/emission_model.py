@@ -824,6 +824,24 @@ def fq12_mul(x, a, b):   # fq12.rs:198-221, #[component]
     return x.component("fq12::mul_montgomery", a + b, body)
 
 
+def fq_exp_by_constant(x, a, e):        # fp254impl.rs:692-725, #[bn_component(offcircuit_args = "exp")]
+    def body(x, a):
+        if e == 0:
+            return bits_of(1, N)
+        if e == 1:
+            return list(a)
+        r = list(a)
+        for bit in bin(e)[3:]:          # below the leading one, most significant first
+            sq = fq_mul(x, r, r)
+            r = fq_mul(x, a, sq) if bit == "1" else sq
+        return r
+    return x.component(("fq::exp_by_constant_montgomery", e), list(a), body)
+
+
+def fq_sqrt(x, a):                      # fq.rs:291-299: a^((p + 1) / 4)
+    return fq_exp_by_constant(x, a, (P + 1) // 4)
+
+
 # ======================================================================================== squares, inverses, Frobenius maps
 R_MONT = (1 << N) % P
 
@@ -1324,6 +1342,9 @@ def build(circuit):
         x = Ctx(6 * N)
         w = list(range(2, 2 + 6 * N))
         return x.finish(g1_add(x, w[:3 * N], w[3 * N:]))
+    if circuit == "fq_sqrt":
+        x = Ctx(N)
+        return x.finish(fq_sqrt(x, list(range(2, 2 + N))))
     if circuit == "fq_inverse":
         x = Ctx(N)
         return x.finish(fq_inverse_montgomery(x, list(range(2, 2 + N))))

@@ -38,6 +38,12 @@ def test_product_stream_matches_independent_model(gsv, name):
     assert h == GOLDEN[name]["sha256"]
 
 
+@pytest.mark.skipif(not os.environ.get("GSV_SLOW_TESTS"), reason="148.7 M gates: 90 s and 17 GB; set GSV_SLOW_TESTS=1")
+def test_fq_sqrt_stream_matches_independent_model(gsv):
+    """Fq::sqrt_montgomery = exp_by_constant((p + 1) / 4): 253 squarings and 124 multiplications in one component."""
+    test_product_stream_matches_independent_model(gsv, "fq_sqrt")
+
+
 @pytest.mark.parametrize("name", ["fq_add", "bn_mul64", "fq_mul", "g1_add", "fq12_cyclotomic_square", "fq12_frobenius2",
                                   "g2_mul_by_char", "g2_double_step"])
 def test_model_reproduces_committed_hashes(name):
