@@ -1,7 +1,9 @@
 """An INDEPENDENT second statement of the reference's gate emission order (TEST INFRASTRUCTURE).
 
 Written from the reference's Rust gadgets (src/gadgets/basic.rs, bigint/{add,cmp,mul}.rs,
-bn254/{fp254impl,fq2,fq6,fq12}.rs), NOT from the product's C++ generator
+bn254/{fp254impl,fq2,fq6,fq12,g1,pairing}.rs, groth16.rs:26-47) -- multiplications, the
+binary Fp inverse and the tower inverses, squares, Frobenius maps, exponentiation by a constant, G1 addition,
+the G2 / line-evaluation steps of the pairing -- NOT from the product's C++ generator
 (csrc/gadgets*.cpp, csrc/circuit.cpp), and with a different mechanism on purpose:
 
   * wires are global SSA ids in `issue_wire` order, gates go to one flat (type, a, b, c) stream in `add_gate`
