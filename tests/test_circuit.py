@@ -278,3 +278,121 @@ def test_call_pipelining_plans(gsv, name, window):
         want = plain.execute(bits)
         assert np.array_equal(piped.execute_plan(bits, lane_form=False), want)
         assert np.array_equal(piped.execute_plan(bits, lane_form=True), want)
+
+
+# ---- single steps of the pairing layer (pairing.rs, groth16.rs:26-47) against plain Fq2 / Fq12 arithmetic
+def _f2(a, b):
+    return ((a[0] * b[0] - a[1] * b[1]) % bn.P, (a[0] * b[1] + a[1] * b[0]) % bn.P)
+
+
+def _f2inv(a):
+    d = pow((a[0] * a[0] + a[1] * a[1]) % bn.P, -1, bn.P)
+    return (a[0] * d % bn.P, (-a[1]) * d % bn.P)
+
+
+def _f2add(a, b):
+    return ((a[0] + b[0]) % bn.P, (a[1] + b[1]) % bn.P)
+
+
+def _f2sub(a, b):
+    return ((a[0] - b[0]) % bn.P, (a[1] - b[1]) % bn.P)
+
+
+def _f2pow(a, e):
+    r = (1, 0)
+    while e:
+        if e & 1:
+            r = _f2(r, a)
+        a = _f2(a, a)
+        e >>= 1
+    return r
+
+
+G2_GEN = ((10857046999023057135944570762232829481370756359578518086990519993285655852781,
+           11559732032986387107991004021392285783925812861821192530917403151452391805634),
+          (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+           4082367875863433681332203403145435568316851327593401208105741076214120093531))   # EIP-197
+TWIST_B = _f2((3, 0), _f2inv((9, 1)))
+
+
+def _on_twist(pt):
+    return _f2(pt[1], pt[1]) == _f2add(_f2(_f2(pt[0], pt[0]), pt[0]), TWIST_B)
+
+
+def _g2_affine_add(p, q):
+    lam = _f2(_f2sub(q[1], p[1]), _f2inv(_f2sub(q[0], p[0]))) if p != q else \
+        _f2(_f2((3, 0), _f2(p[0], p[0])), _f2inv(_f2add(p[1], p[1])))
+    x = _f2sub(_f2sub(_f2(lam, lam), p[0]), q[0])
+    return x, _f2sub(_f2(lam, _f2sub(p[0], x)), p[1])
+
+
+def _fq2_bits(a):
+    return _mont_bits(a[0]) + _mont_bits(a[1])
+
+
+def _fq2_out(out, k):
+    return (_from_mont(out[2 * k * 254:(2 * k + 1) * 254]), _from_mont(out[(2 * k + 1) * 254:(2 * k + 2) * 254]))
+
+
+def test_g2_steps_functional(gsv):
+    """double_in_place / add_in_place (pairing.rs:359-462) on homogeneous projective points and the twist Frobenius
+    mul_by_char (pairing.rs:475-498): the results are the affine chord / tangent sums, respectively stay on the twist."""
+    assert _on_twist(G2_GEN)
+    z = (5, 7)                                                    # R = 2G in projective form with an arbitrary z
+    g2x2 = _g2_affine_add(G2_GEN, G2_GEN)
+    r = (_f2(g2x2[0], z), _f2(g2x2[1], z), z)
+    dbl = gsv.Program("g2_double_step", lane_only=True)
+    out = dbl.execute(_fq2_bits(r[0]) + _fq2_bits(r[1]) + _fq2_bits(r[2]))
+    x, y, zz = (_fq2_out(out, k) for k in range(3))
+    zi = _f2inv(zz)
+    assert (_f2(x, zi), _f2(y, zi)) == _g2_affine_add(g2x2, g2x2)
+    add = gsv.Program("g2_add_step", lane_only=True)
+    q = G2_GEN
+    out = add.execute(_fq2_bits(r[0]) + _fq2_bits(r[1]) + _fq2_bits(r[2]) + _fq2_bits(q[0]) + _fq2_bits(q[1]) + _fq2_bits((1, 0)))
+    x, y, zz = (_fq2_out(out, k) for k in range(3))
+    zi = _f2inv(zz)
+    assert (_f2(x, zi), _f2(y, zi)) == _g2_affine_add(g2x2, G2_GEN)
+    # line coefficients of the addition step: (lambda, -theta, theta qx - lambda qy) with theta = ry - qy rz, lambda = rx - qx rz
+    theta, lam = _f2sub(r[1], _f2(q[1], r[2])), _f2sub(r[0], _f2(q[0], r[2]))
+    assert _fq2_out(out, 3) == lam and _fq2_out(out, 4) == _f2sub((0, 0), theta)
+    assert _fq2_out(out, 5) == _f2sub(_f2(theta, q[0]), _f2(lam, q[1]))
+    frob = gsv.Program("g2_mul_by_char", lane_only=True)
+    out = frob.execute(_fq2_bits(G2_GEN[0]) + _fq2_bits(G2_GEN[1]) + _fq2_bits((1, 0)))
+    px, py = _fq2_out(out, 0), _fq2_out(out, 1)
+    conj = lambda a: (a[0], (-a[1]) % bn.P)
+    assert px == _f2(conj(G2_GEN[0]), _f2pow((9, 1), (bn.P - 1) // 3)) and py == _f2(conj(G2_GEN[1]), _f2pow((9, 1), (bn.P - 1) // 2))
+    assert _on_twist((px, py)) and _fq2_out(out, 2) == (1, 0)
+
+
+def test_g1_to_affine_functional(gsv):
+    """projective_to_affine_montgomery (groth16.rs:26-47): Jacobian (X, Y, Z) -> (X / Z^2, Y / Z^3, 1)."""
+    p = gsv.Program("g1_to_affine", lane_only=True)
+    z = 0x1234567890ABCDEF1234567890ABCDEF % bn.P
+    X, Y = 1 * z * z % bn.P, 2 * z * z * z % bn.P                 # the generator (1, 2)
+    out = p.execute(_mont_bits(X) + _mont_bits(Y) + _mont_bits(z))
+    assert [_from_mont(out[k * 254:(k + 1) * 254]) for k in range(3)] == [1, 2, 1]
+
+
+def test_line_evaluation_functional(gsv):
+    """ell / ell_by_constant (pairing.rs:160-171, 923-942): f * (c0 py + c1 px w^3 + c2 w^4) through the sparse
+    034 products, against a dense Fq12 multiplication."""
+    import random
+
+    rng = random.Random(21)
+    f = bn.rand_fq12(rng)
+    px, py = bn.rand_fq(rng), bn.rand_fq(rng)
+    co = [(bn.rand_fq(rng), bn.rand_fq(rng)) for _ in range(3)]
+
+    def expect(co):
+        c0 = (co[0][0] * py % bn.P, co[0][1] * py % bn.P)
+        c3 = (co[1][0] * px % bn.P, co[1][1] * px % bn.P)
+        sparse = ((c0, (0, 0), (0, 0)), (c3, co[2], (0, 0)))
+        return bn.fq12_flatten(bn.fq12_mul(f, sparse))
+    ell = gsv.Program("ell", lane_only=True)
+    bits = bn.fq12_bits_mont(f) + sum((_fq2_bits(c) for c in co), []) + _mont_bits(px) + _mont_bits(py) + _mont_bits(1)
+    out = ell.execute(bits)
+    assert [_from_mont(out[k * 254:(k + 1) * 254]) for k in range(12)] == expect(co)
+    const = ((3, 5), (7, 11), (13, 17))                            # the constants of the `ell_const` root
+    ellc = gsv.Program("ell_const", lane_only=True)
+    out = ellc.execute(bn.fq12_bits_mont(f) + _mont_bits(px) + _mont_bits(py) + _mont_bits(1))
+    assert [_from_mont(out[k * 254:(k + 1) * 254]) for k in range(12)] == expect(const)
