@@ -31,6 +31,7 @@ uint32_t build_named_circuit(Builder& b, const std::string& c) {
   if (c == "ell") return build_ell(b);
   if (c == "ell_const") return build_ell_const(b);
   if (c == "g1_to_affine") return build_g1_to_affine(b);
+  if (c == "decompress_g1") return build_decompress_g1(b);
   if (c == "final_exponentiation") return build_final_exponentiation(b);
   if (c == "miller_loop_groth16" || c == "groth16_verify_compressed" || c == "groth16_verify") {
     host::VerifyingKey vk;

@@ -130,6 +130,7 @@ uint32_t build_g2_mul_by_char(Builder& b);
 uint32_t build_ell(Builder& b);
 uint32_t build_ell_const(Builder& b);
 uint32_t build_g1_to_affine(Builder& b);
+uint32_t build_decompress_g1(Builder& b);
 uint32_t build_final_exponentiation(Builder& b);
 uint32_t build_miller_loop_groth16(Builder& b, const host::G2Affine& q1, const host::G2Affine& q2);
 

@@ -1264,6 +1264,11 @@ uint32_t build_g1_to_affine(Builder& b) {
     return to_wires(projective_to_affine_montgomery(c, g1_from_wires(in.data())));
   });
 }
+uint32_t build_decompress_g1(Builder& b) {
+  return b.build_root("decompress_g1", 255, [](Builder& c, const Wires& in) {
+    return to_wires(decompress_g1_from_compressed(c, slice(in, 0, 254), in[254]));
+  });
+}
 uint32_t build_final_exponentiation(Builder& b) {
   return b.build_root("final_exponentiation", 3048, [](Builder& c, const Wires& in) {
     return to_wires(final_exponentiation_montgomery(c, fq12_from_wires(in.data())));

@@ -1230,6 +1230,18 @@ def g1_to_affine(x, p):                 # groth16.rs:26-47, #[component]
     return x.component("groth16::projective_to_affine_montgomery", list(p), body)
 
 
+def decompress_g1(x, x_m, y_flag):      # groth16.rs:113-143, #[component]
+    def body(x, w):
+        xm, flag = list(w[:N]), w[N]
+        x2 = fq_mul(x, xm, xm)
+        x3 = fq_mul(x, x2, xm)
+        rhs = fq_add_constant(x, x3, 3 * R_MONT % P)      # + b, b = 3
+        sy = fq_sqrt(x, rhs)
+        sy_neg = fq_neg(x, sy)
+        return xm + bn_select(x, sy, sy_neg, flag) + bits_of(R_MONT, N)
+    return x.component("groth16::decompress_g1_from_compressed", list(x_m) + [y_flag], body)
+
+
 # ======================================================================================== multiplexers, G1
 def basic_multiplexer(x, a, s, w):      # basic.rs:73-105, #[component(offcircuit_args = "w")]
     n = len(a)
@@ -1344,6 +1356,10 @@ def build(circuit):
         x = Ctx(6 * N)
         w = list(range(2, 2 + 6 * N))
         return x.finish(g1_add(x, w[:3 * N], w[3 * N:]))
+    if circuit == "decompress_g1":
+        x = Ctx(N + 1)
+        w = list(range(2, 2 + N + 1))
+        return x.finish(decompress_g1(x, w[:N], w[N]))
     if circuit == "fq_sqrt":
         x = Ctx(N)
         return x.finish(fq_sqrt(x, list(range(2, 2 + N))))

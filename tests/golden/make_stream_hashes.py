@@ -18,12 +18,14 @@ CIRCUITS = ["fq_add", "bn_mul4", "bn_mul19", "bn_mul21", "bn_mul64", "bn_mul254"
             "fq12_frobenius3", "fq12_inverse", "g2_double_step", "g2_add_step", "g2_mul_by_char", "ell", "ell_const",
             "g1_to_affine"]
 
-# fq_sqrt (Fq::sqrt_montgomery = a^((p + 1) / 4), 148.7 M gates) takes 70 s and 17 GB here: only with --slow
+# fq_sqrt (Fq::sqrt_montgomery = a^((p + 1) / 4), 148.7 M gates) and decompress_g1 (149.6 M) take 70-90 s and 17 GB
+# each here: only with --slow
+SLOW = ["fq_sqrt", "decompress_g1"]
 if "--slow" in sys.argv:
-    CIRCUITS.append("fq_sqrt")
+    CIRCUITS += SLOW
 else:
     with open(os.path.join(HERE, "stream_hashes.json")) as f:
-        KEEP = {k: v for k, v in json.load(f)["circuits"].items() if k == "fq_sqrt"}
+        KEEP = {k: v for k, v in json.load(f)["circuits"].items() if k in SLOW}
 
 out = {}
 for c in CIRCUITS:

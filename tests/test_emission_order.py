@@ -39,9 +39,11 @@ def test_product_stream_matches_independent_model(gsv, name):
 
 
 @pytest.mark.skipif(not os.environ.get("GSV_SLOW_TESTS"), reason="148.7 M gates: 90 s and 17 GB; set GSV_SLOW_TESTS=1")
-def test_fq_sqrt_stream_matches_independent_model(gsv):
-    """Fq::sqrt_montgomery = exp_by_constant((p + 1) / 4): 253 squarings and 124 multiplications in one component."""
-    test_product_stream_matches_independent_model(gsv, "fq_sqrt")
+@pytest.mark.parametrize("name", ["fq_sqrt", "decompress_g1"])
+def test_large_streams_match_independent_model(gsv, name):
+    """Fq::sqrt_montgomery = exp_by_constant((p + 1) / 4): 253 squarings and 124 multiplications in one component;
+    decompress_g1_from_compressed (groth16.rs:113-143) around it."""
+    test_product_stream_matches_independent_model(gsv, name)
 
 
 @pytest.mark.parametrize("name", ["fq_add", "bn_mul64", "fq_mul", "g1_add", "fq12_cyclotomic_square", "fq12_frobenius2",
