@@ -58,8 +58,11 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+HOST_DRAM_GBS = 300.0   # assumed host memory bandwidth shared by the ranks' drains (DMA writes) and folds (reads)
+
+
 def host_plan(S, B, steps, warmup, cpu_share, n_ct, commit_host=True, sessions_auto=True, instances_auto=True,
-              host_threads=0):
+              host_threads=0, ranks_on_host=1):
     """Steps in flight per GPU (S), instances per step (B) and AES-NI fold threads per step for a rank that owns
     `cpu_share` host CPUs.  Returns (S, B, fold_threads, note).  The serial chain commitments are folded on the host:
     this is the part of the workload that depends on the host, and the bench says what it chose."""
@@ -81,10 +84,13 @@ def host_plan(S, B, steps, warmup, cpu_share, n_ct, commit_host=True, sessions_a
         # within the driver's window.  Shrink the step then, and say so.
         per_step_s = 720.0 / max(1, warmup + steps)
         cap = int(per_step_s * min(cpu_share, S * ((B + 3) // 4)) * 0.5e9 / max(1, n_ct))
-        if cap < B:
-            B_new = max(4, cap // 4 * 4)
-            note = (f"{B_new} instead of {B} instances per step: {cpu_share} host CPUs per rank fold about "
-                    f"{0.5 * cpu_share:.1f} G ciphertexts/s, a {B}-instance step would not fit the run's time window")
+        # every ciphertext byte is written to host memory by the drain and read once by a fold thread
+        cap_mem = int(per_step_s * HOST_DRAM_GBS * 1e9 / max(1, ranks_on_host) / (32.0 * max(1, n_ct)))
+        if min(cap, cap_mem) < B:
+            B_new = max(4, min(cap, cap_mem) // 4 * 4)
+            why = (f"{cpu_share} host CPUs per rank fold about {0.5 * cpu_share:.1f} G ciphertexts/s" if cap <= cap_mem else
+                   f"{ranks_on_host} ranks share about {HOST_DRAM_GBS:.0f} GB/s of host memory bandwidth (32 B per ciphertext)")
+            note = f"{B_new} instead of {B} instances per step: {why}, a {B}-instance step would not fit the run's time window"
             B = B_new
     # one fold thread per quad of chains when the rank has a CPU for each; otherwise one CPU is left to the drain threads
     quads = (B + 3) // 4
@@ -444,7 +450,8 @@ def main():
     cpu_share = max(1, logical // max(1, local_world))
     S, B, fold_threads, instances_note = host_plan(
         S, B, args.steps, args.warmup, cpu_share, prog.n_ciphertexts, commit_host=ct_mode == g.CT_COMMIT_HOST,
-        sessions_auto=args.sessions_auto, instances_auto=args.instances_auto, host_threads=args.host_threads)
+        sessions_auto=args.sessions_auto, instances_auto=args.instances_auto, host_threads=args.host_threads,
+        ranks_on_host=local_world)
     sm_total = torch.cuda.get_device_properties(local).multi_processor_count
     sm_limit = 0 if S == 1 else (sm_total - SM_RESERVE) // S
     free_b, _ = torch.cuda.mem_get_info()

@@ -57,6 +57,12 @@ def test_host_plan_for_the_drivers_hosts():
     # 8 GPUs on a 16-CPU host: two CPUs per rank cannot fold 16 chains per step in time -> smaller steps, said so
     S, B, T, note = bench.host_plan(3, 16, 20, 5, 2, n_ct)
     assert (S, B, T) == (3, 8, 1) and "8 instead of 16" in note
+    # 8 GPUs on a large host (16 CPUs per rank): the folds have the CPUs, but eight drains + folds share the host's
+    # memory bandwidth -> smaller steps; 4 GPUs still fit
+    S, B, T, note = bench.host_plan(3, 16, 20, 5, 16, n_ct, ranks_on_host=8)
+    assert (S, B, T) == (4, 8, 2) and "memory bandwidth" in note
+    assert bench.host_plan(3, 16, 20, 5, 16, n_ct, ranks_on_host=4) == (4, 16, 4, None)
+    assert bench.host_plan(3, 16, 20, 5, 12, n_ct, ranks_on_host=2) == (3, 16, 4, None)
     # explicit flags are left alone
     assert bench.host_plan(2, 32, 20, 5, 2, n_ct, sessions_auto=False, instances_auto=False, host_threads=5) == (2, 32, 5, None)
     # no host fold without the host-folded commitment
