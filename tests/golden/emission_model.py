@@ -1242,6 +1242,302 @@ def decompress_g1(x, x_m, y_flag):      # groth16.rs:113-143, #[component]
     return x.component("groth16::decompress_g1_from_compressed", list(x_m) + [y_flag], body)
 
 
+# ======================================================================================== final exponentiation
+BN_X = 4965661367192848881                    # ark_bn254::Config::X
+
+
+def _naf(v):                                  # ark_ff::biginteger::arithmetic::find_naf: digits, least significant first
+    out = []
+    while v:
+        if v & 1:
+            z = 2 - (v % 4)
+            v -= z
+        else:
+            z = 0
+        out.append(z)
+        v >>= 1
+    return out
+
+
+def fq12_conjugate(x, a):                     # fq12.rs:444-447
+    a1 = _fq6_of(a[6 * N:])
+    return list(a[:6 * N]) + _flat6(fq6_neg(x, a1))
+
+
+def fq12_one():                               # Fq12::new_constant(ONE): Montgomery one in c0.c0.c0, zeros elsewhere
+    return bits_of(R_MONT, N) + [FALSE] * (11 * N)
+
+
+def cyclotomic_exp_fast_inverse(x, f):        # final_exponentiation.rs:65-93
+    res = fq12_one()
+    f_inv = fq12_inverse(x, f)
+    found = False
+    for d in reversed(_naf(BN_X)):
+        if found:
+            res = fq12_cyclotomic_square(x, res)
+        if d:
+            found = True
+            res = fq12_mul(x, res, f if d > 0 else f_inv)
+    return res
+
+
+def exp_by_neg_x(x, f):                       # final_exponentiation.rs:95-98
+    return fq12_conjugate(x, cyclotomic_exp_fast_inverse(x, f))
+
+
+def final_exponentiation(x, f):               # final_exponentiation.rs:100-134, #[component]
+    def body(x, f):
+        f = list(f)
+        f_inv = fq12_inverse(x, f)
+        f_conj = fq12_conjugate(x, f)
+        u = fq12_mul(x, f_inv, f_conj)
+        u_frob = fq12_frobenius(x, u, 2)
+        r = fq12_mul(x, u_frob, u)
+        y0 = exp_by_neg_x(x, r)
+        y1 = fq12_square(x, y0)
+        y2 = fq12_square(x, y1)
+        y3 = fq12_mul(x, y1, y2)
+        y4 = exp_by_neg_x(x, y3)
+        y5 = fq12_square(x, y4)
+        y6 = exp_by_neg_x(x, y5)
+        y7 = fq12_conjugate(x, y3)
+        y8 = fq12_conjugate(x, y6)
+        y9 = fq12_mul(x, y8, y4)
+        y10 = fq12_mul(x, y9, y7)
+        y11 = fq12_mul(x, y10, y1)
+        y12 = fq12_mul(x, y10, y4)
+        y13 = fq12_mul(x, y12, r)
+        y14 = fq12_frobenius(x, y11, 1)
+        y15 = fq12_mul(x, y14, y13)
+        y16 = fq12_frobenius(x, y10, 2)
+        y17 = fq12_mul(x, y16, y15)
+        r2 = fq12_conjugate(x, r)
+        y18 = fq12_mul(x, r2, y11)
+        y19 = fq12_frobenius(x, y18, 3)
+        return fq12_mul(x, y19, y17)
+    return x.component("final_exponentiation_montgomery", list(f), body)
+
+
+# ======================================================================================== Miller loop (Groth16 form)
+ATE_LOOP_COUNT = [0, 0, 0, 1, 0, 1, 0, -1, 0, 0, 1, -1, 0, 0, 1, 0, 0, 1, 1, 0, -1, 0, 0, 1, 0, -1, 0, 0, 0, 0, 1, 1, 1, 0, 0,
+                  -1, 0, 0, 1, 0, 0, 0, 0, 0, -1, 0, 0, 1, 1, 0, 0, -1, 0, 0, 0, 1, 1, 0, -1, 0, 0, 1, 0, 1, 1]
+assert sum(d << i for i, d in enumerate(ATE_LOOP_COUNT)) == 6 * BN_X + 2
+
+
+def _f2add(a, b):
+    return ((a[0] + b[0]) % P, (a[1] + b[1]) % P)
+
+
+def _f2sub(a, b):
+    return ((a[0] - b[0]) % P, (a[1] - b[1]) % P)
+
+
+def _f2neg(a):
+    return ((-a[0]) % P, (-a[1]) % P)
+
+
+def _f2scale(a, k):
+    return (a[0] * k % P, a[1] * k % P)
+
+
+def host_ell_coeffs(q):
+    """pairing.rs:30-126 on plain integers: the line coefficients of a CONSTANT G2 point (affine, standard form)."""
+    half = (P + 1) // 2
+    r = [q[0], q[1], (1, 0)]
+
+    def double():
+        rx, ry, rz = r
+        a = _f2scale(_f2mul(rx, ry), half)
+        b, c = _f2mul(ry, ry), _f2mul(rz, rz)
+        e = _f2mul(G2_COEFF_B, _f2add(_f2add(c, c), c))
+        f = _f2add(_f2add(e, e), e)
+        g = _f2scale(_f2add(b, f), half)
+        s = _f2add(ry, rz)
+        h = _f2sub(_f2mul(s, s), _f2add(b, c))
+        i = _f2sub(e, b)
+        j = _f2mul(rx, rx)
+        es = _f2mul(e, e)
+        r[:] = [_f2mul(a, _f2sub(b, f)), _f2sub(_f2mul(g, g), _f2add(_f2add(es, es), es)), _f2mul(b, h)]
+        return (_f2neg(h), _f2add(_f2add(j, j), j), i)
+
+    def add(p):
+        rx, ry, rz = r
+        theta = _f2sub(ry, _f2mul(p[1], rz))
+        lam = _f2sub(rx, _f2mul(p[0], rz))
+        c, d = _f2mul(theta, theta), _f2mul(lam, lam)
+        e = _f2mul(lam, d)
+        f = _f2mul(rz, c)
+        g = _f2mul(rx, d)
+        h = _f2sub(_f2add(e, f), _f2add(g, g))
+        j = _f2sub(_f2mul(theta, p[0]), _f2mul(lam, p[1]))
+        r[:] = [_f2mul(lam, h), _f2sub(_f2mul(theta, _f2sub(g, h)), _f2mul(e, ry)), _f2mul(rz, e)]
+        return (lam, _f2neg(theta), j)
+
+    def by_char(p):
+        conj = lambda v: (v[0], (-v[1]) % P)
+        return (_f2mul(conj(p[0]), TWIST_MUL_BY_Q_X), _f2mul(conj(p[1]), TWIST_MUL_BY_Q_Y))
+    out = []
+    neg_q = (q[0], _f2neg(q[1]))
+    for bit in ATE_LOOP_COUNT[::-1][1:]:
+        out.append(double())
+        if bit == 1:
+            out.append(add(q))
+        elif bit == -1:
+            out.append(add(neg_q))
+    q1 = by_char(q)
+    q2 = by_char(q1)
+    q2 = (q2[0], _f2neg(q2[1]))
+    out.append(add(q1))
+    out.append(add(q2))
+    return out
+
+
+def ell_coeffs(x, q):                   # pairing.rs:507-545: the same walk on G2 wires
+    q = list(q)
+    qx, qy, qz = _g2_of(q)
+    neg_q = _flat6([qx, fq2_neg(x, qy), qz])
+    out, r = [], q
+    for bit in ATE_LOOP_COUNT[::-1][1:]:
+        res = g2_double_step(x, r)
+        r = res[:6 * N]
+        out.append(res[6 * N:])
+        if bit:
+            res = g2_add_step(x, r, q if bit == 1 else neg_q)
+            r = res[:6 * N]
+            out.append(res[6 * N:])
+    q1 = g2_mul_by_char(x, q)
+    q2 = g2_mul_by_char(x, q1)
+    q2x, q2y, q2z = _g2_of(q2)
+    q2 = _flat6([q2x, fq2_neg(x, q2y), q2z])
+    res = g2_add_step(x, r, q1)
+    r = res[:6 * N]
+    out.append(res[6 * N:])
+    res = g2_add_step(x, r, q2)
+    out.append(res[6 * N:])
+    return out
+
+
+def miller_loop_groth16(x, p1, p2, p3, k1, k2, q3):   # pairing.rs:944-1009, #[component(offcircuit_args = "q1,q2")]
+    def body(x, w):
+        p1, p2, p3, q3 = list(w[:3 * N]), list(w[3 * N:6 * N]), list(w[6 * N:9 * N]), list(w[9 * N:])
+        e1, e2 = iter(host_ell_coeffs(k1)), iter(host_ell_coeffs(k2))
+        e3 = iter(ell_coeffs(x, q3))
+        f = fq12_one()
+
+        def lines(f):
+            f = ell_by_constant(x, f, next(e1), p1)
+            f = ell_by_constant(x, f, next(e2), p2)
+            return ell(x, f, next(e3), p3)
+        n = len(ATE_LOOP_COUNT)
+        for i in range(n - 1, 0, -1):
+            if i != n - 1:
+                f = fq12_square(x, f)
+            f = lines(f)
+            if ATE_LOOP_COUNT[i - 1]:
+                f = lines(f)
+        f = lines(f)
+        return lines(f)
+    return x.component(("pairing::multi_miller_loop_groth16_evaluate_montgomery_fast", k1, k2),
+                       list(p1) + list(p2) + list(p3) + list(q3), body)
+
+
+# ---- the synthetic verification key of the product's named circuits (csrc/bn254_host.cpp synthetic_groth16(7, ..)):
+# test data, not reference code -- scalars from a splitmix64 stream, points = scalar * generator
+G2_GENERATOR = ((10857046999023057135944570762232829481370756359578518086990519993285655852781,
+                 11559732032986387107991004021392285783925812861821192530917403151452391805634),
+                (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+                 4082367875863433681332203403145435568316851327593401208105741076214120093531))
+
+
+def _g2_affine_add(p, q):
+    if p is None:
+        return q
+    if p == q:
+        lam = _f2mul(_f2scale(_f2mul(p[0], p[0]), 3), _f2inv(_f2add(p[1], p[1])))
+    else:
+        lam = _f2mul(_f2sub(q[1], p[1]), _f2inv(_f2sub(q[0], p[0])))
+    x3 = _f2sub(_f2sub(_f2mul(lam, lam), p[0]), q[0])
+    return (x3, _f2sub(_f2mul(lam, _f2sub(p[0], x3)), p[1]))
+
+
+def _g2_mul(p, k):
+    acc = None
+    while k:
+        if k & 1:
+            acc = _g2_affine_add(acc, p)
+        p = _g2_affine_add(p, p)
+        k >>= 1
+    return acc
+
+
+def synthetic_vk_scalars(seed=7):
+    m = (1 << 64) - 1
+    state = [(seed * 0x2545F4914F6CDD1D + 0x1234567) & m]
+
+    def splitmix():
+        state[0] = (state[0] + 0x9E3779B97F4A7C15) & m
+        z = state[0]
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+        return z ^ (z >> 31)
+
+    def scalar():
+        l = [splitmix() for _ in range(4)]
+        l[3] &= 0x0FFFFFFFFFFFFFFF
+        return (l[0] | l[1] << 64 | l[2] << 128 | l[3] << 192) or 1
+    return dict(zip(("alpha", "beta", "gamma", "delta", "ic0", "ic1", "a", "b"), (scalar() for _ in range(8))))
+
+
+# ======================================================================================== Fq2 square root, G2 decompression
+def bn_equal(x, a, b):                  # bigint/cmp.rs:44-59, #[component]
+    n = len(a)
+
+    def body(x, w):
+        xs = []
+        for ai, bi in zip(w[:n], w[n:]):
+            o = x.issue()
+            x.gate(XOR, ai, bi, o)
+            xs.append(o)
+        return [equal_constant(x, xs, 0)]
+    return x.component("bigint::equal", list(a) + list(b), body)[0]
+
+
+def fq_is_qnr(x, a):                    # fq.rs:177-192: a^((p - 1) / 2) == -1
+    y = fq_exp_by_constant(x, a, (P - 1) // 2)
+    return bn_equal(x, y, bits_of((P - 1) * R_MONT % P, N))
+
+
+def fq2_sqrt_general(x, a):             # fq2.rs:425-447, #[component]
+    def body(x, w):
+        a0, a1 = list(w[:N]), list(w[N:])
+        alpha = fq_add(x, fq_mul(x, a0, a0), fq_mul(x, a1, a1))      # norm_montgomery
+        alpha_sqrt = fq_sqrt(x, alpha)
+        delta = fq_half(x, fq_add(x, alpha_sqrt, a0))
+        is_qnr = fq_is_qnr(x, delta)
+        delta_alt = fq_sub(x, delta, alpha_sqrt)
+        delta_final = bn_select(x, delta_alt, delta, is_qnr)
+        c0 = fq_sqrt(x, delta_final)
+        c0_inv = fq_inverse_montgomery(x, c0)
+        c1_half = fq_half(x, a1)
+        return c0 + fq_mul(x, c0_inv, c1_half)
+    r = x.component("fq2::sqrt_general_montgomery", a[0] + a[1], body)
+    return [r[:N], r[N:]]
+
+
+def decompress_g2(x, xw, y_flag):       # groth16.rs:145-182, #[component]
+    def body(x, w):
+        px, flag = [list(w[:N]), list(w[N:2 * N])], w[2 * N]
+        x2 = fq2_square(x, px)
+        x3 = fq2_mul(x, x2, px)
+        y2 = fq2_add_constant(x, x3, _mont2(G2_COEFF_B))
+        y = fq2_sqrt_general(x, y2)
+        neg_y = fq2_neg(x, y)
+        y0 = bn_select(x, y[0], neg_y[0], flag)
+        y1 = bn_select(x, y[1], neg_y[1], flag)
+        return px[0] + px[1] + y0 + y1 + bits_of(R_MONT, N) + [FALSE] * N
+    return x.component("groth16::decompress_g2_from_compressed", list(xw) + [y_flag], body)
+
+
 # ======================================================================================== multiplexers, G1
 def basic_multiplexer(x, a, s, w):      # basic.rs:73-105, #[component(offcircuit_args = "w")]
     n = len(a)
@@ -1297,6 +1593,290 @@ def g1_add(x, p, q):                    # g1.rs:159-235, #[component]
         return (bn_multiplexer(x, [x3, x2, x1, zero], sel, 2) + bn_multiplexer(x, [y3, y2, y1, zero], sel, 2) +
                 bn_multiplexer(x, [z3, z2, z1, zero], sel, 2))
     return x.component("g1::add_montgomery", list(p) + list(q), body)
+
+
+# ======================================================================================== MSM with constant bases
+# The multiplexer tables are constants: multiples of the base in arkworks' Jacobian coordinates (ark-ec 0.5
+# short_weierstrass::Projective, absent from /root/reference: `+=` is add-2007-bl, doubling dbl-2009-l with a = 0, the
+# identity is (1, 1, 0)).  Their VALUES are restated from the published formulas -- the one shared assumption of this
+# section; the gadget structure around them is from g1.rs:275-400.
+def _jac_double(p):
+    X, Y, Z = p
+    if Z == 0:
+        return p
+    A, B = X * X % P, Y * Y % P
+    C = B * B % P
+    D = 2 * ((X + B) * (X + B) - A - C) % P
+    E = 3 * A % P
+    F = E * E % P
+    X3 = (F - 2 * D) % P
+    return (X3, (E * (D - X3) - 8 * C) % P, 2 * Y * Z % P)
+
+
+def _jac_add(p, q):
+    if p[2] == 0:
+        return q
+    if q[2] == 0:
+        return p
+    X1, Y1, Z1 = p
+    X2, Y2, Z2 = q
+    Z1Z1, Z2Z2 = Z1 * Z1 % P, Z2 * Z2 % P
+    U1, U2 = X1 * Z2Z2 % P, X2 * Z1Z1 % P
+    S1, S2 = Y1 * Z2 * Z2Z2 % P, Y2 * Z1 * Z1Z1 % P
+    if U1 == U2 and S1 == S2:
+        return _jac_double(p)
+    H = (U2 - U1) % P
+    I = 4 * H * H % P
+    J = (-H * I) % P
+    r = 2 * (S2 - S1) % P
+    V = U1 * I % P
+    X3 = (r * r + J - 2 * V) % P
+    return (X3, (r * (V - X3) + 2 * S1 * J) % P, 2 * Z1 * Z2 * H % P)
+
+
+def _g1_const(p):                       # G1Projective::new_constant(as_montgomery(p))
+    return bits_of(p[0] * R_MONT % P, N) + bits_of(p[1] * R_MONT % P, N) + bits_of(p[2] * R_MONT % P, N)
+
+
+def g1_multiplexer(x, pts, sel, w):     # g1.rs:275-306, #[component(offcircuit_args = "w")]
+    cnt = len(pts)
+
+    def body(x, inp):
+        ps, s = [list(inp[j * 3 * N:(j + 1) * 3 * N]) for j in range(cnt)], list(inp[cnt * 3 * N:])
+        return sum((bn_multiplexer(x, [q[c * N:(c + 1) * N] for q in ps], s, w) for c in range(3)), [])
+    return x.component(("g1::multiplexer", w), [b for q in pts for b in q] + list(sel), body)
+
+
+def g1_scalar_mul_const(x, scalar, base, W=10):      # g1.rs:308-368, base = Jacobian (x, y, z), standard form
+    def body(x, s):
+        n = 1 << W
+        bases, p = [], (1, 1, 0)
+        for _ in range(n):
+            bases.append(p)
+            p = _jac_add(p, base)
+        parts, idx = [], 0
+        while idx < N:
+            w = min(W, N - idx)
+            parts.append(g1_multiplexer(x, [_g1_const(b) for b in bases[:1 << w]], s[idx:idx + w], w))
+            idx += W
+            nb = []
+            for b in bases:
+                for _ in range(w):
+                    b = _jac_add(b, b)
+                nb.append(b)
+            bases = nb
+        acc = parts[0]
+        for q in parts[1:]:
+            acc = g1_add(x, acc, q)
+        return acc
+    return x.component(("g1::scalar_mul_by_constant_base_montgomery", W, base), list(scalar), body)
+
+
+def g1_msm_const(x, scalars, bases, W=10):           # g1.rs:370-400
+    def body(x, w):
+        parts = [g1_scalar_mul_const(x, w[i * N:(i + 1) * N], b, W) for i, b in enumerate(bases)]
+        acc = parts[0]
+        for q in parts[1:]:
+            acc = g1_add(x, acc, q)
+        return acc
+    assert scalars
+    return x.component(("g1::msm_with_constant_bases_montgomery", W, tuple(bases)), [b for s_ in scalars for b in s_], body)
+
+
+# ======================================================================================== host pairing (for one constant)
+def _f6mul(a, b):                       # Fq6 = Fq2[v] / (v^3 - xi)
+    a0, a1, a2 = a
+    b0, b1, b2 = b
+    t0, t1, t2 = _f2mul(a0, b0), _f2mul(a1, b1), _f2mul(a2, b2)
+    c0 = _f2add(t0, _f2mul(XI, _f2sub(_f2mul(_f2add(a1, a2), _f2add(b1, b2)), _f2add(t1, t2))))
+    c1 = _f2add(_f2sub(_f2mul(_f2add(a0, a1), _f2add(b0, b1)), _f2add(t0, t1)), _f2mul(XI, t2))
+    c2 = _f2add(_f2sub(_f2mul(_f2add(a0, a2), _f2add(b0, b2)), _f2add(t0, t2)), t1)
+    return (c0, c1, c2)
+
+
+def _f6add(a, b):
+    return tuple(_f2add(u, v) for u, v in zip(a, b))
+
+
+def _f6sub(a, b):
+    return tuple(_f2sub(u, v) for u, v in zip(a, b))
+
+
+def _f6neg(a):
+    return tuple(_f2neg(u) for u in a)
+
+
+def _f6mulv(a):
+    return (_f2mul(XI, a[2]), a[0], a[1])
+
+
+def _f6inv(a):
+    a0, a1, a2 = a
+    c0 = _f2sub(_f2mul(a0, a0), _f2mul(XI, _f2mul(a1, a2)))
+    c1 = _f2sub(_f2mul(XI, _f2mul(a2, a2)), _f2mul(a0, a1))
+    c2 = _f2sub(_f2mul(a1, a1), _f2mul(a0, a2))
+    t = _f2inv(_f2add(_f2mul(a0, c0), _f2mul(XI, _f2add(_f2mul(a2, c1), _f2mul(a1, c2)))))
+    return (_f2mul(c0, t), _f2mul(c1, t), _f2mul(c2, t))
+
+
+def _f12mul(a, b):                      # Fq12 = Fq6[w] / (w^2 - v)
+    t0, t1 = _f6mul(a[0], b[0]), _f6mul(a[1], b[1])
+    return (_f6add(t0, _f6mulv(t1)), _f6sub(_f6mul(_f6add(a[0], a[1]), _f6add(b[0], b[1])), _f6add(t0, t1)))
+
+
+def _f12inv(a):
+    t = _f6inv(_f6sub(_f6mul(a[0], a[0]), _f6mulv(_f6mul(a[1], a[1]))))
+    return (_f6mul(a[0], t), _f6neg(_f6mul(a[1], t)))
+
+
+def _f12conj(a):
+    return (a[0], _f6neg(a[1]))
+
+
+def _f12frob(a, i):
+    conj = (lambda v: (v[0], (-v[1]) % P)) if i % 2 else (lambda v: v)
+
+    def f6(c):
+        return (conj(c[0]), _f2mul(conj(c[1]), FROB_FP6_C1[i % 6]), _f2mul(conj(c[2]), FROB_FP6_C2[i % 6]))
+    c1 = f6(a[1])
+    return (f6(a[0]), tuple(_f2mul(v, FROB_FP12_C1[i % 12]) for v in c1))
+
+
+F12_ONE = (((1, 0), (0, 0), (0, 0)), ((0, 0), (0, 0), (0, 0)))
+
+
+def _f12pow(a, e):
+    r = F12_ONE
+    while e:
+        if e & 1:
+            r = _f12mul(r, a)
+        a = _f12mul(a, a)
+        e >>= 1
+    return r
+
+
+def host_miller_loop(p, q):
+    """ark-ec's BN multi_miller_loop for one pair, through the line coefficients above (p, q affine, standard form)."""
+    co = iter(host_ell_coeffs(q))
+
+    def ell(f):
+        c0, c1, c2 = next(co)
+        line = ((_f2scale(c0, p[1]), (0, 0), (0, 0)), (_f2scale(c1, p[0]), c2, (0, 0)))
+        return _f12mul(f, line)
+    f = F12_ONE
+    n = len(ATE_LOOP_COUNT)
+    for i in range(n - 1, 0, -1):
+        if i != n - 1:
+            f = _f12mul(f, f)
+        f = ell(f)
+        if ATE_LOOP_COUNT[i - 1]:
+            f = ell(f)
+    return ell(ell(f))
+
+
+def host_final_exponentiation(f):
+    """final_exponentiation.rs:38-63 (= ark-ec's BN final exponentiation) on plain integers."""
+    neg_x = lambda v: _f12conj(_f12pow(v, BN_X))
+    u = _f12mul(_f12inv(f), _f12conj(f))
+    r = _f12mul(_f12frob(u, 2), u)
+    y0 = neg_x(r)
+    y1 = _f12mul(y0, y0)
+    y2 = _f12mul(y1, y1)
+    y3 = _f12mul(y1, y2)
+    y4 = neg_x(y3)
+    y5 = _f12mul(y4, y4)
+    y6 = neg_x(y5)
+    y7, y8 = _f12conj(y3), _f12conj(y6)
+    y9 = _f12mul(y8, y4)
+    y10 = _f12mul(y9, y7)
+    y11 = _f12mul(y10, y1)
+    y12 = _f12mul(y10, y4)
+    y13 = _f12mul(y12, r)
+    y14 = _f12frob(y11, 1)
+    y15 = _f12mul(y14, y13)
+    y16 = _f12frob(y10, 2)
+    y17 = _f12mul(y16, y15)
+    y18 = _f12mul(_f12conj(r), y11)
+    return _f12mul(_f12frob(y18, 3), y17)
+
+
+# ======================================================================================== Groth16 verifier
+def fq2_equal_constant(x, a, k):        # fq2.rs:148-158 (k in the wires' form)
+    u, v = equal_constant(x, a[0], k[0]), equal_constant(x, a[1], k[1])
+    w = x.issue()
+    x.gate(AND, u, v, w)
+    return w
+
+
+def fq6_equal_constant(x, a, k):        # fq6.rs:139-152
+    u, v, w = (fq2_equal_constant(x, a[j], k[j]) for j in range(3))
+    t, y = x.issue(), x.issue()
+    x.gate(AND, u, v, t)
+    x.gate(AND, t, w, y)
+    return y
+
+
+def fq12_equal_constant(x, a, k):       # fq12.rs:158-168
+    u = fq6_equal_constant(x, _fq6_of(a[:6 * N]), k[0])
+    v = fq6_equal_constant(x, _fq6_of(a[6 * N:]), k[1])
+    w = x.issue()
+    x.gate(AND, u, v, w)
+    return w
+
+
+def _g1_mul_affine(k):                  # k * (1, 2) as an affine point
+    acc, p = (1, 1, 0), (1, 2, 1)
+    while k:
+        if k & 1:
+            acc = _jac_add(acc, p)
+        p = _jac_double(p)
+        k >>= 1
+    zi = pow(acc[2], -1, P)
+    return (acc[0] * zi * zi % P, acc[1] * zi * zi * zi % P)
+
+
+def synthetic_vk(seed=7):
+    sc = synthetic_vk_scalars(seed)
+    return dict(alpha_g1=_g1_mul_affine(sc["alpha"]), beta_g2=_g2_mul(G2_GENERATOR, sc["beta"]),
+                gamma_g2=_g2_mul(G2_GENERATOR, sc["gamma"]), delta_g2=_g2_mul(G2_GENERATOR, sc["delta"]),
+                gamma_abc_g1=[_g1_mul_affine(sc["ic0"]), _g1_mul_affine(sc["ic1"])])
+
+
+def groth16_verify(x, publics, a, b, c, vk):          # groth16.rs:50-105 (plain function)
+    neg2 = lambda q: (q[0], _f2neg(q[1]))
+    bases = [(pt[0], pt[1], 1) for pt in vk["gamma_abc_g1"][1:1 + len(publics)]]
+    msm_temp = g1_msm_const(x, publics, bases)
+    g0 = vk["gamma_abc_g1"][0]
+    msm = g1_add(x, msm_temp, _g1_const((g0[0], g0[1], 1)))
+    msm_affine = g1_to_affine(x, msm)
+    f = miller_loop_groth16(x, msm_affine, c, a, neg2(vk["gamma_g2"]), neg2(vk["delta_g2"]), b)
+    alpha_beta = _f12inv(host_final_exponentiation(host_miller_loop(vk["alpha_g1"], neg2(vk["beta_g2"]))))
+    f = final_exponentiation(x, f)
+    ab_m = tuple(tuple(_mont2(c2) for c2 in c6) for c6 in alpha_beta)
+    return fq12_equal_constant(x, f, ab_m)
+
+
+def groth16_verify_compressed(x, w, n_public, vk):     # groth16.rs:250-268; input layout of the product's root
+    o = n_public * N
+    publics = [list(w[i * N:(i + 1) * N]) for i in range(n_public)]
+    a = decompress_g1(x, w[o:o + N], w[o + N])
+    o += N + 1
+    b = decompress_g2(x, w[o:o + 2 * N], w[o + 2 * N])
+    o += 2 * N + 1
+    c = decompress_g1(x, w[o:o + N], w[o + N])
+    return [groth16_verify(x, publics, a, b, c, vk)]
+
+
+def groth16_verify_uncompressed(x, w, n_public, vk):   # garbled_groth16.rs:108-176: affine points, z = 1 constants
+    o = n_public * N
+    publics = [list(w[i * N:(i + 1) * N]) for i in range(n_public)]
+    one, zero = bits_of(R_MONT, N), [FALSE] * N
+    a = list(w[o:o + 2 * N]) + one
+    o += 2 * N
+    b = list(w[o:o + 4 * N]) + one + zero
+    o += 4 * N
+    c = list(w[o:o + 2 * N]) + one
+    return [groth16_verify(x, publics, a, b, c, vk)]
 
 
 # ======================================================================================== roots (the product's named circuits)
