@@ -1,9 +1,10 @@
 """An INDEPENDENT second statement of the reference's gate emission order (TEST INFRASTRUCTURE).
 
 Written from the reference's Rust gadgets (src/gadgets/basic.rs, bigint/{add,cmp,mul}.rs,
-bn254/{fp254impl,fq2,fq6,fq12,g1,pairing}.rs, groth16.rs:26-47) -- multiplications, the
-binary Fp inverse and the tower inverses, squares, Frobenius maps, exponentiation by a constant, G1 addition,
-the G2 / line-evaluation steps of the pairing -- NOT from the product's C++ generator
+bn254/{fp254impl,fq,fq2,fq6,fq12,g1,pairing,final_exponentiation}.rs, groth16.rs) -- the
+whole Groth16 verifier: multiplications, the binary Fp inverse and the tower inverses, squares, Frobenius maps,
+exponentiation by a constant and the square roots, point decompression, G1 addition, the windowed constant-base
+MSM, the G2 / line-evaluation steps, the Miller loop, the final exponentiation -- NOT from the product's C++ generator
 (csrc/gadgets*.cpp, csrc/circuit.cpp), and with a different mechanism on purpose:
 
   * wires are global SSA ids in `issue_wire` order, gates go to one flat (type, a, b, c) stream in `add_gate`
@@ -14,6 +15,12 @@ the G2 / line-evaluation steps of the pairing -- NOT from the product's C++ gene
     credit templates per output-liveness mask instead.)
   * a component body is recorded once per key and replayed by renumbering (numpy), which is what keeps
     Fq12::mul (20 M gates) fast enough for the CPU suite.
+
+Constants are derived here (powers of the non-residue for Frobenius / twist coefficients, line coefficients of
+constant G2 points and the alpha-beta target through the host arithmetic at the end of this file); the multiples of
+a constant G1 base in the MSM tables follow arkworks' Jacobian formulas, restated from the published formulas (see
+the MSM section).  Circuits too large to flatten are compared through structural_hash.py, which records the same
+gadget functions into a component DAG.
 
 `canonical_hash` renumbers wires by first live write, so the stream can be compared with the product's
 `Program.flat_stream()` whatever the two sides' wire numbering; tests/golden/stream_hashes.json holds the
