@@ -181,6 +181,33 @@ impl Program {
         Self::wrap(unsafe { ffi::gsv_program_build(c.as_ptr(), std::ptr::null()) })
     }
 
+    /// The recorded circuit as its memoised template DAG (`gsv_program_export_templates`): the root template's index
+    /// and the six arrays tmpl / gates / calls / items / call_wires / outs.
+    pub fn export_templates(&self) -> Result<(u32, [Vec<u32>; 6])> {
+        let mut sizes = [0u64; 6];
+        let mut root = 0u32;
+        let null = std::ptr::null_mut::<u32>();
+        check(unsafe {
+            ffi::gsv_program_export_templates(self.raw, sizes.as_mut_ptr(), &mut root, null, null, null, null, null, null)
+        })?;
+        let mut a: [Vec<u32>; 6] = std::array::from_fn(|k| vec![0u32; sizes[k] as usize]);
+        let [t, g, c, i, w, o] = &mut a;
+        check(unsafe {
+            ffi::gsv_program_export_templates(
+                self.raw,
+                sizes.as_mut_ptr(),
+                &mut root,
+                t.as_mut_ptr(),
+                g.as_mut_ptr(),
+                c.as_mut_ptr(),
+                i.as_mut_ptr(),
+                w.as_mut_ptr(),
+                o.as_mut_ptr(),
+            )
+        })?;
+        Ok((root, a))
+    }
+
     fn wrap(raw: *mut ffi::GsvProgram) -> Result<Self> {
         if raw.is_null() {
             return Err(last_error(ffi::GSV_ERR_INVALID));

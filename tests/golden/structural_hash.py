@@ -172,7 +172,12 @@ def model_hash(root_fn, n_inputs):
 # ======================================================================================== product side
 def product_hash(program):
     """The same hash from the product's exported template DAG (gsv_program_export_templates)."""
-    root, tmpl, gates, calls, items, call_wires, outs = program.export_templates()
+    return templates_hash(*program.export_templates())
+
+
+def templates_hash(root, tmpl, gates, calls, items, call_wires, outs):
+    """Hash of an exported template DAG (the arrays of gsv_program_export_templates, from any recorder that went
+    through the C ABI -- the product's own generator, or the reference's Rust gadgets behind gsv-cuda's GpuRecorder)."""
     tmpl = np.asarray(tmpl, np.int64).reshape(-1, 12)
     gates = np.asarray(gates, np.int64).reshape(-1, 4)
     calls = np.asarray(calls, np.int64).reshape(-1, 3)
