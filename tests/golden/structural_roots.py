@@ -4,10 +4,6 @@ import emission_model as em
 N = em.N
 
 
-def _fq12(f):
-    return lambda x, w: f(x, w)
-
-
 def _miller(x, w):
     sc = em.synthetic_vk_scalars(7)
     neg = lambda q: (q[0], em._f2neg(q[1]))
