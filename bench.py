@@ -640,7 +640,7 @@ def main():
                 "workload": f"{args.circuit} x {B} cut-and-choose instances per step and GPU ({S} steps in flight per GPU), "
                             f"garble + {commit_txt}, {args.hasher} gate hasher"
                             + (" (BASELINE.json configs 2/4: Groth16 verifier, 1 public input, synthetic vk; "
-                               "11.46 G gates here vs the reference's 11.17 G for its own vk)"
+                               "11.46 G gates as recorded from the current gadget sources; the reference's README quotes 11.17 G)"
                                if args.circuit == "groth16_verify_compressed" else ""),
                 "kernel": kernel_name, "plan_s": round(t_plan, 1), "plan_cache": os.environ.get("GSV_PLAN_CACHE_DIR"),
                 "gates_per_instance": prog.n_gates, "ciphertexts_per_instance": prog.n_ciphertexts,
