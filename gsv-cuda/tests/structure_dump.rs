@@ -5,6 +5,9 @@
 //! that the engine's own generator already equals (tests/test_structural_hash.py), up to the whole verifier.
 //! Equal hashes mean: the reference's gadgets emit exactly the gate stream (order, types, wiring, dead gates) the
 //! engine was built and measured on.  Needs no GPU: recording and planning are host code.
+//! The whole verifier can be added the same way: `structural_hashes.json` lists the scalars of the synthetic key
+//! (`synthetic_key.scalars`: every key element is scalar * generator) behind its `groth16_verify_compressed` /
+//! `groth16_verify` / `miller_loop_groth16` hashes.
 use std::{fs, io::Write, path::PathBuf};
 
 use garbled_snark_verifier::{

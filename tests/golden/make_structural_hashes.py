@@ -22,4 +22,9 @@ for name, (n, fn) in sr.ROOTS.items():
 with open(os.path.join(HERE, "structural_hashes.json"), "w") as f:
     json.dump({"generator": "tests/golden/make_structural_hashes.py (emission_model.py gadgets over structural_hash.SCtx)",
                "definition": "structural_hash.py: sha256 over the component DAG, bottom-up, per (body, output-liveness mask)",
+               "synthetic_key": {
+                   "note": "key of the groth16_* / miller_loop_groth16 circuits: points = scalar * generator (G1 (1, 2); G2 the "
+                           "EIP-197 generator); alpha_g1, beta_g2, gamma_g2, delta_g2, gamma_abc_g1 = [ic0, ic1]; "
+                           "csrc/bn254_host.cpp synthetic_groth16(7, ..)",
+                   "scalars": {k: hex(v) for k, v in sr.em.synthetic_vk_scalars(7).items()}},
                "circuits": out}, f, indent=1)
