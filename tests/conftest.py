@@ -51,3 +51,19 @@ def circuit(gsv, orc):
         return _streams[name]
 
     return get
+
+
+_lane_programs = {}
+
+
+@pytest.fixture(scope="session")
+def lane_program(gsv):
+    """lane_program(name) -> Program(name, lane_only=True), cached for the session (the verifier takes ~25 s to record
+    and ~10 GB; two CPU tests look at it)."""
+
+    def get(name):
+        if name not in _lane_programs:
+            _lane_programs[name] = gsv.Program(name, lane_only=True)
+        return _lane_programs[name]
+
+    return get

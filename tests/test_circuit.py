@@ -216,13 +216,13 @@ def test_g1_add_functional(gsv):
     assert (x * zi * zi % bn.P, y * zi * zi * zi % bn.P) == aff_add(g2, g3)
 
 
-def test_groth16_verifier_accepts_and_rejects(gsv):
+def test_groth16_verifier_accepts_and_rejects(gsv, lane_program):
     """groth16_verify_compressed (groth16.rs:250-268) over a synthetic key: 11.46 G gates walked in
     ExecuteMode; the valid proof yields 1, a different public input yields 0 (the reference's
     true / bit-flip cases, groth16.rs:510-604).  The README's 11 174 708 821 is 2.5 % lower; the key moves the
     count by a few 1e-5 only, so that difference is between the current sources and the
     published figure, not the key."""
-    p = gsv.Program("groth16_verify_compressed", lane_only=True)
+    p = lane_program("groth16_verify_compressed")
     assert p.n_inputs == 1273 and p.n_outputs == 1
     assert 11.0e9 < p.n_gates < 11.8e9 and 0.25 < p.n_ciphertexts / p.n_gates < 0.28
     good, bad = gsv.groth16_synthetic_inputs(424242, False), gsv.groth16_synthetic_inputs(424242, True)
